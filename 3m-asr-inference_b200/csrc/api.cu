@@ -1,0 +1,418 @@
+// C-ABI layer: argument validation, workspace carving, stage sequencing. See include/b200moe.h for the contract and the
+// reference interfaces each entry point replaces.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+
+namespace b200moe {
+
+namespace {
+thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(B200MOE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+bool dtype_ok(int d) { return d == B200MOE_F32 || d == B200MOE_F16 || d == B200MOE_BF16; }
+
+
+__global__ void __launch_bounds__(256) to_f32_kernel(const void* src, int dtype, float* dst, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v;
+    if (dtype == B200MOE_F32)
+      v = static_cast<const float*>(src)[i];
+    else if (dtype == B200MOE_F16)
+      v = __half2float(static_cast<const __half*>(src)[i]);
+    else
+      v = __bfloat162float(static_cast<const bf16*>(src)[i]);
+    dst[i] = v;
+  }
+}
+
+}  // namespace
+
+void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+
+}  // namespace b200moe
+
+using namespace b200moe;
+
+struct b200moe_plugin {
+  int data_type;
+  int num_expert;
+  int idim;
+  int hidden_units;
+  int act_type;
+  // identity of the weights packed into the workspace by the last enqueue
+  const void* packed_src[4];
+  void* packed_ws;
+};
+
+extern "C" {
+
+const char* b200moe_last_error(void) { return g_last_error.c_str(); }
+
+int b200moe_version(void) { return B200MOE_VERSION; }
+
+unsigned long long b200moe_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200moe_device_supported(int dev) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  return major == 10 ? 1 : 0;
+}
+
+int b200moe_pack_bf16(const void* src, int src_dtype, void* dst_bf16, size_t n, cudaStream_t stream) {
+  if ((!src || !dst_bf16) && n > 0) return fail(B200MOE_ERR_ARG, "pack_bf16: null pointer");
+  if (!dtype_ok(src_dtype)) return fail(B200MOE_ERR_ARG, "pack_bf16: bad dtype %d", src_dtype);
+  cudaError_t e = launch_pack_bf16(src, src_dtype, static_cast<bf16*>(dst_bf16), n, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pack_bf16");
+  return B200MOE_OK;
+}
+
+size_t b200moe_workspace_bytes(int S, int E, int D, int H, int top_k) {
+  if (S < 0 || E < 1 || D < 1 || H < 0 || top_k < 1) return 0;
+  return carve_workspace(nullptr, S, E, D, H, top_k).bytes;
+}
+
+int b200moe_gate(const void* x, const void* embed, const float* Wr, const float* br, const int* x_len, int B, int T,
+                 int D, int Demb, int E, int top_k, int gate_mode, int dtype, int* idx, float* score,
+                 cudaStream_t stream) {
+  if (B < 0 || T < 0 || D < 1) return fail(B200MOE_ERR_ARG, "gate: bad shape B=%d T=%d D=%d", B, T, D);
+  if (B * T > 0 && (!x || !Wr || !idx || !score)) return fail(B200MOE_ERR_ARG, "gate: null pointer");
+  if (!dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "gate: bad dtype %d", dtype);
+  if (gate_mode != B200MOE_GATE_3M && gate_mode != B200MOE_GATE_NAIVE)
+    return fail(B200MOE_ERR_ARG, "gate: bad gate_mode %d", gate_mode);
+  if (E < 1 || E > kMaxExperts) return fail(B200MOE_ERR_ARG, "gate: E=%d outside [1, %d]", E, kMaxExperts);
+  if (top_k < 1 || top_k > 8 || top_k > E) return fail(B200MOE_ERR_ARG, "gate: top_k=%d unsupported", top_k);
+  if (gate_mode == B200MOE_GATE_3M && top_k != 1)
+    return fail(B200MOE_ERR_ARG, "gate: the 3M router is top-1 (got top_k=%d)", top_k);
+  cudaError_t e = launch_gate(x, embed, Wr, br, x_len, B, T, D, embed ? Demb : 0, E, top_k, gate_mode, dtype, idx,
+                              score, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "gate");
+  return B200MOE_OK;
+}
+
+int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int T, int E, int data_type, void* value,
+                                 int* idx, cudaStream_t stream) {
+  if (B * T > 0 && (!logits || !value || !idx)) return fail(B200MOE_ERR_ARG, "softmax_topk: null pointer");
+  if (!dtype_ok(data_type)) return fail(B200MOE_ERR_ARG, "softmax_topk: bad data_type %d", data_type);
+  // the reference kernel handles dim <= 128 and returns -1 beyond that (softmax_topk_kernel.cu:96-116)
+  if (E < 1 || E > kMaxExperts) return fail(B200MOE_ERR_ARG, "softmax_topk: E=%d outside [1, %d]", E, kMaxExperts);
+  cudaError_t e = launch_softmax_topk(logits, mask, B, T, E, data_type, value, idx, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "softmax_topk");
+  return B200MOE_OK;
+}
+
+int b200moe_dispatch(const void* x, const int* idx, int S, int D, int E, int top_k, int dtype, int* counts,
+                     int* offsets, int* mapping, void* xbuf, void* ws, cudaStream_t stream) {
+  if (S < 0 || D < 1 || top_k < 1) return fail(B200MOE_ERR_ARG, "dispatch: bad shape");
+  if (E < 1 || E > kMaxExperts) return fail(B200MOE_ERR_ARG, "dispatch: E=%d outside [1, %d]", E, kMaxExperts);
+  if (D % 8 != 0) return fail(B200MOE_ERR_ARG, "dispatch: D=%d must be a multiple of 8", D);
+  if (!dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "dispatch: bad dtype %d", dtype);
+  if (!ws || (S > 0 && (!x || !idx || !xbuf))) return fail(B200MOE_ERR_ARG, "dispatch: null pointer");
+  RouteWs w = carve_workspace(ws, S, E, D, 0, top_k);
+  cudaError_t e = launch_dispatch(x, idx, nullptr, S, D, E, top_k, dtype, choose_bn(S * top_k, E), w, counts, offsets,
+                                  mapping, static_cast<bf16*>(xbuf), nullptr, nullptr, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "dispatch");
+  return B200MOE_OK;
+}
+
+int b200moe_expert_ffn(const void* xbuf, const int* offsets, int n_rows, const void* W1, const float* b1,
+                       const void* W2, const float* b2, int E, int D, int H, int act_type, int out_dtype, void* ybuf,
+                       void* ws, cudaStream_t stream) {
+  if (n_rows < 0) return fail(B200MOE_ERR_ARG, "expert_ffn: n_rows < 0");
+  if (E < 1 || E > kMaxExperts) return fail(B200MOE_ERR_ARG, "expert_ffn: E=%d outside [1, %d]", E, kMaxExperts);
+  if (D % 128 != 0 || H % 128 != 0)
+    return fail(B200MOE_ERR_ARG, "expert_ffn: D=%d and H=%d must be multiples of 128", D, H);
+  if (act_type < 0 || act_type > 2) return fail(B200MOE_ERR_ARG, "expert_ffn: bad act_type %d", act_type);
+  if (!dtype_ok(out_dtype)) return fail(B200MOE_ERR_ARG, "expert_ffn: bad out_dtype %d", out_dtype);
+  if (!ws || !offsets || !W1 || !W2 || (n_rows > 0 && (!xbuf || !ybuf)))
+    return fail(B200MOE_ERR_ARG, "expert_ffn: null pointer");
+  if (n_rows == 0) return B200MOE_OK;
+  RouteWs w = carve_workspace(ws, n_rows, E, D, H, 1);
+  const int bn = choose_bn(n_rows, E);
+  const int gmax = max_groups(n_rows, E, bn);
+  cudaError_t e = launch_build_groups(offsets, E, bn, w.groups, w.n_groups, w.h_ready, gmax, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "expert_ffn/build_groups");
+  FfnLaunch a{};
+  a.xbuf = static_cast<const bf16*>(xbuf);
+  a.hbuf = static_cast<bf16*>(w.hbuf);
+  a.W1 = static_cast<const bf16*>(W1);
+  a.W2 = static_cast<const bf16*>(W2);
+  a.b1 = b1;
+  a.b2 = b2;
+  a.groups = w.groups;
+  a.n_groups = w.n_groups;
+  a.h_ready = w.h_ready;
+  a.n_rows = n_rows;
+  a.E = E;
+  a.D = D;
+  a.H = H;
+  a.bn = bn;
+  a.act = act_type;
+  a.gmax = gmax;
+  a.fused = 0;
+  a.out_dtype = out_dtype;
+  a.out = ybuf;
+  a.top_k = 1;
+  a.ff_scale = 1.0f;
+  e = launch_ffn(a, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "expert_ffn");
+  return B200MOE_OK;
+}
+
+int b200moe_combine(const void* ybuf, const int* mapping, const float* score, const void* residual, float ff_scale,
+                    int S, int D, int top_k, int dtype, void* out, cudaStream_t stream) {
+  if (S < 0 || D < 1 || top_k < 1) return fail(B200MOE_ERR_ARG, "combine: bad shape");
+  if (D % 8 != 0) return fail(B200MOE_ERR_ARG, "combine: D=%d must be a multiple of 8", D);
+  if (!dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "combine: bad dtype %d", dtype);
+  if (S > 0 && (!ybuf || !mapping || !out)) return fail(B200MOE_ERR_ARG, "combine: null pointer");
+  cudaError_t e = launch_combine(ybuf, mapping, score, residual, ff_scale, S, D, top_k, dtype, out, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "combine");
+  return B200MOE_OK;
+}
+
+int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!a) return fail(B200MOE_ERR_ARG, "forward: null args");
+  const int S = a->B * a->T;
+  if (a->B < 0 || a->T < 0) return fail(B200MOE_ERR_ARG, "forward: bad B/T");
+  if (a->E < 1 || a->E > kMaxExperts) return fail(B200MOE_ERR_ARG, "forward: E=%d outside [1, %d]", a->E, kMaxExperts);
+  if (a->D % 128 != 0 || a->H % 128 != 0)
+    return fail(B200MOE_ERR_ARG, "forward: D=%d and H=%d must be multiples of 128", a->D, a->H);
+  if (!dtype_ok(a->dtype)) return fail(B200MOE_ERR_ARG, "forward: bad dtype %d", a->dtype);
+  if (a->top_k < 1 || a->top_k > 8 || a->top_k > a->E) return fail(B200MOE_ERR_ARG, "forward: bad top_k %d", a->top_k);
+  if (a->gate_mode == B200MOE_GATE_3M && a->top_k != 1)
+    return fail(B200MOE_ERR_ARG, "forward: the 3M router is top-1 (got top_k=%d)", a->top_k);
+  if (a->act_type < 0 || a->act_type > 2) return fail(B200MOE_ERR_ARG, "forward: bad act_type %d", a->act_type);
+  if (S == 0) return B200MOE_OK;
+  if (!a->x || !a->out || !a->Wr || !a->W1 || !a->W2 || !ws) return fail(B200MOE_ERR_ARG, "forward: null pointer");
+  const int Demb = a->embed ? a->Demb : 0;
+  RouteWs w = carve_workspace(ws, S, a->E, a->D, a->H, a->top_k);
+  if (ws_bytes < w.bytes)
+    return fail(B200MOE_ERR_WORKSPACE, "forward: workspace %zu B < required %zu B", ws_bytes, w.bytes);
+  const int Sk = S * a->top_k;
+  int* idx = a->idx_out ? a->idx_out : w.idx;
+  float* score = a->score_out ? a->score_out : w.score;
+
+  cudaError_t e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
+                              a->gate_mode, a->dtype, idx, score, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "forward/gate");
+
+  const int bn = choose_bn(Sk, a->E);
+  const int gmax = max_groups(Sk, a->E, bn);
+  const bool fused = a->top_k == 1;
+  e = launch_dispatch(a->x, idx, a->keep_expert_output ? nullptr : score, S, a->D, a->E, a->top_k, a->dtype, bn, w,
+                      a->counts_out, nullptr, a->mapping_out, w.xbuf, fused ? a->out : nullptr, a->residual, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "forward/dispatch");
+
+  FfnLaunch f{};
+  f.xbuf = w.xbuf;
+  f.hbuf = static_cast<bf16*>(w.hbuf);
+  f.W1 = static_cast<const bf16*>(a->W1);
+  f.W2 = static_cast<const bf16*>(a->W2);
+  f.b1 = a->b1;
+  f.b2 = a->b2;
+  f.groups = w.groups;
+  f.n_groups = w.n_groups;
+  f.h_ready = w.h_ready;
+  f.n_rows = Sk;
+  f.E = a->E;
+  f.D = a->D;
+  f.H = a->H;
+  f.bn = bn;
+  f.act = a->act_type;
+  f.gmax = gmax;
+  f.out_dtype = a->dtype;
+  f.top_k = a->top_k;
+  f.ff_scale = a->ff_scale;
+  if (fused) {
+    f.fused = 1;
+    f.out = a->out;
+    f.residual = a->residual;
+    f.pos = w.pos;
+    f.row_score = w.row_score;
+  } else {
+    f.fused = 0;
+    f.out = w.ybuf;
+  }
+  e = launch_ffn(f, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "forward/expert_ffn");
+  if (!fused) {
+    e = launch_combine(w.ybuf, w.mapping, a->keep_expert_output ? nullptr : score, a->residual, a->ff_scale, S, a->D,
+                       a->top_k, a->dtype, a->out, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "forward/combine");
+  }
+  return B200MOE_OK;
+}
+
+// ---- plugin mirror ----------------------------------------------------------------------------------------------
+
+b200moe_plugin* b200moe_plugin_create(int data_type, int num_expert, int idim, int hidden_units, int act_type) {
+  // the reference creator rejects type_id outside {0, 1} (fmoe_expert_plugin.cpp:360-363); bf16 (2) is new here
+  if (!dtype_ok(data_type)) {
+    fail(B200MOE_ERR_ARG, "fmoe: invalid type_id %d", data_type);
+    return nullptr;
+  }
+  if (num_expert < 1 || num_expert > kMaxExperts || idim < 1 || hidden_units < 1 || idim % 128 != 0 ||
+      hidden_units % 128 != 0) {
+    fail(B200MOE_ERR_ARG, "fmoe: unsupported num_expert=%d idim=%d hidden_units=%d", num_expert, idim, hidden_units);
+    return nullptr;
+  }
+  b200moe_plugin* p = new (std::nothrow) b200moe_plugin();
+  if (!p) return nullptr;
+  p->data_type = data_type;
+  p->num_expert = num_expert;
+  p->idim = idim;
+  p->hidden_units = hidden_units;
+  p->act_type = act_type;
+  std::memset(p->packed_src, 0, sizeof(p->packed_src));
+  p->packed_ws = nullptr;
+  return p;
+}
+
+b200moe_plugin* b200moe_plugin_clone(const b200moe_plugin* p) {
+  if (!p) return nullptr;
+  b200moe_plugin* q = b200moe_plugin_create(p->data_type, p->num_expert, p->idim, p->hidden_units, p->act_type);
+  return q;
+}
+
+size_t b200moe_plugin_serialization_size(const b200moe_plugin*) { return 8 * sizeof(int); }
+
+int b200moe_plugin_serialize(const b200moe_plugin* p, void* host_buffer) {
+  if (!p || !host_buffer) return fail(B200MOE_ERR_ARG, "serialize: null pointer");
+  int v[8] = {p->data_type, p->num_expert, p->idim, p->hidden_units, p->act_type, 0, 0, 0};
+  std::memcpy(host_buffer, v, sizeof(v));
+  return B200MOE_OK;
+}
+
+b200moe_plugin* b200moe_plugin_deserialize(const void* host_data, size_t length) {
+  if (!host_data || length < 8 * sizeof(int)) {
+    fail(B200MOE_ERR_ARG, "deserialize: need %zu bytes, got %zu", 8 * sizeof(int), length);
+    return nullptr;
+  }
+  int v[8];
+  std::memcpy(v, host_data, sizeof(v));
+  return b200moe_plugin_create(v[0], v[1], v[2], v[3], v[4]);
+}
+
+void b200moe_plugin_destroy(b200moe_plugin* p) { delete p; }
+
+namespace {
+struct PluginWs {
+  size_t route_bytes;
+  size_t w1_off, w2_off, b1_off, b2_off, total;
+};
+PluginWs plugin_ws_layout(const b200moe_plugin* p, int S) {
+  PluginWs l;
+  const size_t E = p->num_expert, D = p->idim, H = p->hidden_units;
+  l.route_bytes = carve_workspace(nullptr, S, p->num_expert, p->idim, p->hidden_units, 1).bytes;
+  size_t off = align_up(l.route_bytes, 1024);
+  l.w1_off = off;
+  off = align_up(off + E * H * D * sizeof(bf16), 1024);
+  l.w2_off = off;
+  off = align_up(off + E * H * D * sizeof(bf16), 1024);
+  l.b1_off = off;
+  off = align_up(off + E * H * sizeof(float), 1024);
+  l.b2_off = off;
+  off = align_up(off + E * D * sizeof(float), 1024);
+  l.total = off;
+  return l;
+}
+}  // namespace
+
+size_t b200moe_plugin_workspace_bytes(const b200moe_plugin* p, int S) {
+  if (!p || S < 0) return 0;
+  return plugin_ws_layout(p, S).total;
+}
+
+int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate_idx, const void* w1_weight,
+                           const void* w1_bias, const void* w2_weight, const void* w2_bias, int S, void* output,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!p) return fail(B200MOE_ERR_ARG, "enqueue: null plugin");
+  if (S < 0) return fail(B200MOE_ERR_ARG, "enqueue: S < 0");
+  if (S == 0) return B200MOE_OK;
+  if (!input || !gate_idx || !w1_weight || !w1_bias || !w2_weight || !w2_bias || !output || !workspace)
+    return fail(B200MOE_ERR_ARG, "enqueue: null pointer");
+  const PluginWs l = plugin_ws_layout(p, S);
+  if (workspace_bytes < l.total)
+    return fail(B200MOE_ERR_WORKSPACE, "enqueue: workspace %zu B < required %zu B", workspace_bytes, l.total);
+  const int E = p->num_expert, D = p->idim, H = p->hidden_units;
+  char* base = static_cast<char*>(workspace);
+  bf16* w1p = reinterpret_cast<bf16*>(base + l.w1_off);
+  bf16* w2p = reinterpret_cast<bf16*>(base + l.w2_off);
+  float* b1p = reinterpret_cast<float*>(base + l.b1_off);
+  float* b2p = reinterpret_cast<float*>(base + l.b2_off);
+  // The reference receives its weights as plugin inputs on every enqueue (README.md:225) and streams them as fp32.
+  // Here they are cast to bf16 once and reused while the four pointers and the workspace stay the same.
+  const void* src[4] = {w1_weight, w1_bias, w2_weight, w2_bias};
+  if (p->packed_ws != workspace || std::memcmp(p->packed_src, src, sizeof(src)) != 0) {
+    const size_t nw = static_cast<size_t>(E) * H * D;
+    cudaError_t e = launch_pack_bf16(w1_weight, p->data_type, w1p, nw, stream);
+    if (e == cudaSuccess) e = launch_pack_bf16(w2_weight, p->data_type, w2p, nw, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "enqueue/pack");
+    to_f32_kernel<<<64, 256, 0, stream>>>(w1_bias, p->data_type, b1p, static_cast<size_t>(E) * H);
+    to_f32_kernel<<<64, 256, 0, stream>>>(w2_bias, p->data_type, b2p, static_cast<size_t>(E) * D);
+    count_launch(2);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "enqueue/bias");
+    std::memcpy(p->packed_src, src, sizeof(src));
+    p->packed_ws = workspace;
+  }
+  RouteWs w = carve_workspace(workspace, S, E, D, H, 1);
+  const int bn = choose_bn(S, E);
+  const int gmax = max_groups(S, E, bn);
+  cudaError_t e = launch_dispatch(input, gate_idx, nullptr, S, D, E, 1, p->data_type, bn, w, nullptr, nullptr, nullptr,
+                                  w.xbuf, output, nullptr, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "enqueue/dispatch");
+  FfnLaunch f{};
+  f.xbuf = w.xbuf;
+  f.hbuf = static_cast<bf16*>(w.hbuf);
+  f.W1 = w1p;
+  f.W2 = w2p;
+  f.b1 = b1p;
+  f.b2 = b2p;
+  f.groups = w.groups;
+  f.n_groups = w.n_groups;
+  f.h_ready = w.h_ready;
+  f.n_rows = S;
+  f.E = E;
+  f.D = D;
+  f.H = H;
+  f.bn = bn;
+  // the reference stores act_type but always applies SiLU (fmoe_expert_plugin.cpp:106); honour the field here,
+  // with the reference's default 0 = SiLU
+  f.act = (p->act_type >= 0 && p->act_type <= 2) ? p->act_type : B200MOE_ACT_SILU;
+  f.gmax = gmax;
+  f.fused = 1;  // un-weighted output in token order: score = 1, ff_scale = 1, no residual
+  f.out_dtype = p->data_type;
+  f.out = output;
+  f.residual = nullptr;
+  f.pos = w.pos;
+  f.row_score = nullptr;
+  f.ff_scale = 1.0f;
+  f.top_k = 1;
+  e = launch_ffn(f, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "enqueue/expert_ffn");
+  return B200MOE_OK;
+}
+
+}  // extern "C"

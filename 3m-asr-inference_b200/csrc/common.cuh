@@ -1,0 +1,170 @@
+// Internal declarations shared by the kernels and the C-ABI layer (api.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b200moe.h"
+
+namespace b200moe {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kMaxExperts = 256;      // smem tables in gate/dispatch are sized for this
+constexpr int kDispatchThreads = 256;  // 8 warps per dispatch CTA
+constexpr int kMaxChunks = 296;        // 2 x 148 dispatch chunks at most (make_chunking divides by this)
+
+// One GEMM "group" = one expert x one tile of <= BN of its tokens. {expert, first row, rows, unused}
+struct GroupRec {
+  int expert;
+  int row0;
+  int nrows;
+  int pad;
+};
+
+// Device-side routing state produced by dispatch and consumed by the FFN kernel. Lives in the workspace.
+struct RouteWs {
+  int* chunk_hist;   // [kMaxChunks, E]
+  int* counts;       // [E]
+  int* offsets;      // [E + 1]
+  int* mapping;      // [Sk]   entry -> expert-order row (-1 = dropped)
+  int* pos;          // [Sk]   expert-order row -> entry (fastmoe's `pos`)
+  float* row_score;  // [Sk]   gate score of the entry that landed in this row
+  GroupRec* groups;  // [Gmax]
+  int* n_groups;     // [1]
+  int* h_ready;      // [Gmax] G1 tiles finished per group (dependency flags for the second GEMM)
+  int* idx;          // [Sk]   gate output when the caller does not want it
+  float* score;      // [Sk]
+  bf16* xbuf;        // [Sk, D]
+  void* hbuf;        // [Sk, H]  bf16 (or fp32 for the tf32 path)
+  void* ybuf;        // [Sk, D]  staging for the un-fused combine (top_k > 1)
+  size_t bytes;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline int max_groups(int Sk, int E, int bn) { return (Sk + bn - 1) / bn + E; }
+
+// Carves `base` (may be null: then only sizes are computed). Worst case group count uses BN = 32.
+inline RouteWs carve_workspace(void* base, int S, int E, int D, int H, int top_k) {
+  RouteWs w;
+  const size_t Sk = static_cast<size_t>(S) * top_k;
+  const size_t gmax = static_cast<size_t>(max_groups(static_cast<int>(Sk), E, 32));
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return base ? static_cast<char*>(base) + o : static_cast<char*>(nullptr);
+  };
+  w.chunk_hist = reinterpret_cast<int*>(take(sizeof(int) * kMaxChunks * E));
+  w.counts = reinterpret_cast<int*>(take(sizeof(int) * E));
+  w.offsets = reinterpret_cast<int*>(take(sizeof(int) * (E + 1)));
+  w.mapping = reinterpret_cast<int*>(take(sizeof(int) * Sk));
+  w.pos = reinterpret_cast<int*>(take(sizeof(int) * Sk));
+  w.row_score = reinterpret_cast<float*>(take(sizeof(float) * Sk));
+  w.groups = reinterpret_cast<GroupRec*>(take(sizeof(GroupRec) * gmax));
+  w.n_groups = reinterpret_cast<int*>(take(sizeof(int) * 4));
+  w.h_ready = reinterpret_cast<int*>(take(sizeof(int) * gmax));
+  w.idx = reinterpret_cast<int*>(take(sizeof(int) * Sk));
+  w.score = reinterpret_cast<float*>(take(sizeof(float) * Sk));
+  w.xbuf = reinterpret_cast<bf16*>(take(sizeof(bf16) * Sk * D));
+  w.ybuf = take(sizeof(float) * Sk * D);
+  w.hbuf = take(sizeof(bf16) * Sk * H);  // last: the only field whose size depends on H
+  w.bytes = off;
+  return w;
+}
+
+// ---- kernel launchers (each returns a cudaError_t from the launch; none synchronises) ----------------------
+
+// gate.cu
+cudaError_t launch_gate(const void* x, const void* embed, const float* Wr, const float* br, const int* x_len, int B,
+                        int T, int D, int Demb, int E, int top_k, int gate_mode, int dtype, int* idx, float* score,
+                        cudaStream_t stream);
+cudaError_t launch_softmax_topk(const void* logits, const int* mask, int B, int T, int E, int dtype, void* value,
+                                int* idx, cudaStream_t stream);
+
+// dispatch.cu
+// bn: token-tile width the FFN kernel will use (group table is built for it); score may be null (row_score = 1).
+// drop_out (optional, `dtype`, [S, D], top_k == 1 only): rows of dropped tokens (idx < 0) are written here as
+// drop_residual[row] (or zeros), so that a fused FFN epilogue -- which only touches routed tokens -- leaves a
+// fully defined output.
+cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
+                            int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
+                            int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
+                            cudaStream_t stream);
+// Builds only the group table (+ zeroes the flags) from an existing offsets array.
+cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
+                                int gmax, cudaStream_t stream);
+int choose_bn(int Sk, int E);
+
+// ffn.cu
+struct FfnLaunch {
+  const bf16* xbuf;   // [n_rows, D]
+  bf16* hbuf;         // [n_rows, H]
+  const bf16* W1;     // [E, H, D]
+  const bf16* W2;     // [E, D, H]
+  const float* b1;    // [E, H] or null
+  const float* b2;    // [E, D] or null
+  const GroupRec* groups;
+  const int* n_groups;
+  int* h_ready;
+  int n_rows, E, D, H, bn, act;
+  int gmax;           // upper bound on the number of groups (sizes the grid)
+  // epilogue of the second GEMM
+  int fused;          // 0: ybuf[row] = y (expert order). 1: out[pos[row]/top_k] = residual + ff_scale*score*y
+  int out_dtype;
+  void* out;          // ybuf (fused = 0) or the layer output (fused = 1)
+  const void* residual;
+  const int* pos;
+  const float* row_score;  // null => 1
+  float ff_scale;
+  int top_k;
+};
+cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
+
+// combine.cu
+cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
+                           float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream);
+cudaError_t launch_pack_bf16(const void* src, int src_dtype, bf16* dst, size_t n, cudaStream_t stream);
+
+void count_launch(int n = 1);
+
+// ---- small device helpers ------------------------------------------------------------------------------------
+template <typename T>
+struct IoType;
+template <>
+struct IoType<float> {
+  static constexpr int code = B200MOE_F32;
+};
+template <>
+struct IoType<__half> {
+  static constexpr int code = B200MOE_F16;
+};
+template <>
+struct IoType<bf16> {
+  static constexpr int code = B200MOE_BF16;
+};
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_float(bf16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __half from_float<__half>(float v) {
+  return __float2half_rn(v);
+}
+template <>
+__device__ __forceinline__ bf16 from_float<bf16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+}  // namespace b200moe

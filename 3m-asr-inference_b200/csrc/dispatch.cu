@@ -1,0 +1,333 @@
+// Token dispatch: per-expert count, exclusive prefix sum, STABLE scatter of token rows into expert-contiguous order.
+//
+// Reference behaviour: TRTAPI++/plugin/fmoe_expert_plugin/fmoe_expert_kernel.cu:25-128 (one CTA, shared-memory
+// atomicAdd ranks -- order within an expert is nondeterministic -- thread-0 serial scan, then a scalar copy
+// kernel) and trainer_3m_fix/fmoe/functions.py:29-35,72 (torch.sort + unique + fmoe_cuda.local_scatter).
+// Here the within-expert order is defined (stable: by entry index), so mapping is reproducible bit for bit:
+//   mapping[i] = offsets[idx[i]] + #{ j < i : idx[j] == idx[i] },   pos = mapping^-1.
+//
+// Two launches: count (per-chunk histograms) and scatter (every CTA derives its chunk's base offsets from the
+// histograms, ranks its entries with warp match/ballot, and copies rows with 128-bit accesses, casting to bf16).
+// CTA 0 of the scatter kernel also emits counts / offsets / the FFN group table and clears the FFN flags.
+#include "common.cuh"
+
+namespace b200moe {
+
+namespace {
+
+struct Chunking {
+  int chunk;    // entries per CTA (multiple of 32)
+  int nchunks;  // grid size (<= kMaxChunks)
+};
+
+Chunking make_chunking(int Sk) {
+  // ~2 CTAs per SM; a CTA's chunk is a multiple of 32 entries so that small batches still spread over many SMs
+  // (the row copy is latency bound: 3 200 tokens -> 100 CTAs x 32 rows, 4 rows per warp in flight at once).
+  Chunking c;
+  int chunk = (Sk + 295) / 296;
+  chunk = (chunk + 31) / 32 * 32;
+  if (chunk < 32) chunk = 32;
+  c.chunk = chunk;
+  c.nchunks = (Sk + chunk - 1) / chunk;
+  if (c.nchunks < 1) c.nchunks = 1;
+  return c;
+}
+
+__global__ void __launch_bounds__(kDispatchThreads)
+dispatch_count_kernel(const int* __restrict__ idx, int Sk, int E, int chunk, int* __restrict__ chunk_hist) {
+  __shared__ int hist[kMaxExperts];
+  for (int e = threadIdx.x; e < E; e += blockDim.x) hist[e] = 0;
+  __syncthreads();
+  const int begin = blockIdx.x * chunk;
+  const int end = min(begin + chunk, Sk);
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const int e = idx[i];
+    if (e >= 0 && e < E) atomicAdd(&hist[e], 1);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) chunk_hist[blockIdx.x * E + e] = hist[e];
+}
+
+// 8 consecutive elements -> 8 bf16 packed in a uint4 (one 128-bit store).
+template <typename InT>
+__device__ __forceinline__ uint4 load8_as_bf16(const InT* __restrict__ p);
+
+template <>
+__device__ __forceinline__ uint4 load8_as_bf16<bf16>(const bf16* __restrict__ p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <>
+__device__ __forceinline__ uint4 load8_as_bf16<float>(const float* __restrict__ p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  uint4 o;
+  o.x = pack_bf16x2(a.x, a.y);
+  o.y = pack_bf16x2(a.z, a.w);
+  o.z = pack_bf16x2(b.x, b.y);
+  o.w = pack_bf16x2(b.z, b.w);
+  return o;
+}
+
+template <>
+__device__ __forceinline__ uint4 load8_as_bf16<__half>(const __half* __restrict__ p) {
+  uint4 in = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&in);
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __half22float2(h[k]);
+    ow[k] = pack_bf16x2(f.x, f.y);
+  }
+  return o;
+}
+
+// Group table: expert e contributes ceil(count[e] / bn) groups, in expert order. Runs in one CTA.
+__device__ void build_groups_block(const int* offsets_sm /*[E+1] in smem or global*/, int E, int bn,
+                                   GroupRec* groups, int* n_groups, int* h_ready, int gmax, int* scratch /*[E+1]*/) {
+  // scratch[e] = exclusive prefix of tiles per expert
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < E; ++e) {
+      scratch[e] = acc;
+      const int c = offsets_sm[e + 1] - offsets_sm[e];
+      acc += (c + bn - 1) / bn;
+    }
+    scratch[E] = acc;
+    n_groups[0] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int c = offsets_sm[e + 1] - offsets_sm[e];
+    const int nt = (c + bn - 1) / bn;
+    const int g0 = scratch[e];
+    for (int j = 0; j < nt; ++j) {
+      GroupRec r;
+      r.expert = e;
+      r.row0 = offsets_sm[e] + j * bn;
+      r.nrows = min(bn, c - j * bn);
+      r.pad = 0;
+      groups[g0 + j] = r;
+    }
+  }
+  for (int g = threadIdx.x; g < gmax; g += blockDim.x) h_ready[g] = 0;
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(kDispatchThreads)
+dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, const float* __restrict__ score,
+                        int Sk, int D, int E, int top_k, int chunk, int nchunks,
+                        const int* __restrict__ chunk_hist, int bn, int gmax, int* __restrict__ counts,
+                        int* __restrict__ offsets, int* __restrict__ mapping, int* __restrict__ pos,
+                        float* __restrict__ row_score, bf16* __restrict__ xbuf, GroupRec* groups, int* n_groups,
+                        int* h_ready, int* counts_out, int* offsets_out, int* mapping_out, InT* __restrict__ drop_out,
+                        const InT* __restrict__ drop_residual) {
+  constexpr int kWarps = kDispatchThreads / 32;
+  constexpr int kRowsPerBatch = 4;            // rows a warp keeps in flight during the copy
+  __shared__ int s_total[kMaxExperts];        // tokens per expert over all chunks
+  __shared__ int s_cursor[kMaxExperts];       // next expert-order row for this CTA's entries
+  __shared__ int s_off[kMaxExperts + 1];      // global exclusive offsets
+  __shared__ int s_scratch[kMaxExperts + 1];
+  __shared__ int s_dst[kDispatchThreads];     // destination row of each entry of the current segment
+  extern __shared__ int s_wcnt[];             // [kWarps][E] per-warp counts of the current segment
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // 1. column sums of the chunk histograms: totals and the part that precedes this chunk
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    int before = 0, total = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int v = chunk_hist[c * E + e];
+      if (c < static_cast<int>(blockIdx.x)) before += v;
+      total += v;
+    }
+    s_cursor[e] = before;
+    s_total[e] = total;
+  }
+  for (int i = threadIdx.x; i < kWarps * E; i += blockDim.x) s_wcnt[i] = 0;
+  __syncthreads();
+  // 2. exclusive scan over experts (E <= 256: a serial scan by one thread is a few hundred cycles)
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < E; ++e) {
+      s_off[e] = acc;
+      acc += s_total[e];
+    }
+    s_off[E] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) s_cursor[e] += s_off[e];
+  __syncthreads();
+
+  const int begin = blockIdx.x * chunk;
+  const int end = min(begin + chunk, Sk);
+  for (int seg = begin; seg < end; seg += kDispatchThreads) {
+    const int n = min(kDispatchThreads, end - seg);
+    // 3. stable rank of the segment's entries: (earlier segments) + (earlier warps) + (earlier lanes)
+    const int i = seg + threadIdx.x;
+    int e = -1;
+    if (static_cast<int>(threadIdx.x) < n) {
+      e = idx[i];
+      if (e < 0 || e >= E) e = -1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, e);
+    if (e >= 0 && lane == __ffs(peers) - 1) s_wcnt[warp * E + e] = __popc(peers);
+    __syncthreads();
+    int dst = -1;
+    if (e >= 0) {
+      int base = s_cursor[e];
+      for (int w = 0; w < warp; ++w) base += s_wcnt[w * E + e];
+      dst = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    s_dst[threadIdx.x] = dst;
+    if (static_cast<int>(threadIdx.x) < n) {
+      mapping[i] = dst;
+      if (mapping_out) mapping_out[i] = dst;
+      if (dst >= 0) {
+        pos[dst] = i;
+        row_score[dst] = score ? score[i] : 1.0f;
+      }
+    }
+    __syncthreads();
+    for (int ee = threadIdx.x; ee < E; ee += blockDim.x) {
+      int add = 0;
+      for (int w = 0; w < kWarps; ++w) {
+        add += s_wcnt[w * E + ee];
+        s_wcnt[w * E + ee] = 0;
+      }
+      s_cursor[ee] += add;
+    }
+    // 4. row copy: warp w moves rows w, w+8, ... of the segment, kRowsPerBatch rows (x 16 B per lane) in flight
+    for (int j0 = warp; j0 < n; j0 += kWarps * kRowsPerBatch) {
+      int d[kRowsPerBatch];
+      const InT* src[kRowsPerBatch];
+#pragma unroll
+      for (int r = 0; r < kRowsPerBatch; ++r) {
+        const int j = j0 + r * kWarps;
+        d[r] = j < n ? s_dst[j] : -1;
+        src[r] = x + static_cast<size_t>((seg + (j < n ? j : 0)) / top_k) * D;
+      }
+      for (int v = lane; v < D / 8; v += 32) {
+        uint4 regs[kRowsPerBatch];
+#pragma unroll
+        for (int r = 0; r < kRowsPerBatch; ++r)
+          if (d[r] >= 0) regs[r] = load8_as_bf16<InT>(src[r] + v * 8);
+#pragma unroll
+        for (int r = 0; r < kRowsPerBatch; ++r)
+          if (d[r] >= 0) reinterpret_cast<uint4*>(xbuf + static_cast<size_t>(d[r]) * D)[v] = regs[r];
+      }
+      if (drop_out != nullptr) {
+        // dropped tokens (padding / invalid expert): output row = residual row (or zero)
+#pragma unroll
+        for (int r = 0; r < kRowsPerBatch; ++r) {
+          const int j = j0 + r * kWarps;
+          if (j < n && d[r] < 0) {
+            const size_t row = static_cast<size_t>(seg + j) / top_k * D;
+            for (int c = lane; c < D; c += 32)
+              drop_out[row + c] = drop_residual ? drop_residual[row + c] : from_float<InT>(0.0f);
+          }
+        }
+      }
+    }
+    __syncthreads();  // s_dst / s_wcnt / s_cursor are reused by the next segment
+  }
+
+  // 5. CTA 0 publishes counts / offsets / FFN group table
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      counts[e] = s_total[e];
+      if (counts_out) counts_out[e] = s_total[e];
+    }
+    for (int e = threadIdx.x; e <= E; e += blockDim.x) {
+      offsets[e] = s_off[e];
+      if (offsets_out) offsets_out[e] = s_off[e];
+    }
+    build_groups_block(s_off, E, bn, groups, n_groups, h_ready, gmax, s_scratch);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+build_groups_kernel(const int* __restrict__ offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
+                    int gmax) {
+  __shared__ int s_off[kMaxExperts + 1];
+  __shared__ int s_scratch[kMaxExperts + 1];
+  for (int e = threadIdx.x; e <= E; e += blockDim.x) s_off[e] = offsets[e];
+  __syncthreads();
+  build_groups_block(s_off, E, bn, groups, n_groups, h_ready, gmax, s_scratch);
+}
+
+}  // namespace
+
+// Token-tile width of the FFN kernel: the smallest of 32/64/128/256 that holds ~1.25x the mean tokens per expert,
+// so a balanced router gives one tile per expert and weights are streamed once.
+int choose_bn(int Sk, int E) {
+  const long long need = (static_cast<long long>(Sk) * 5 + 4LL * E - 1) / (4LL * E);
+  if (need <= 32) return 32;
+  if (need <= 64) return 64;
+  if (need <= 128) return 128;
+  return 256;
+}
+
+cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
+                            int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
+                            int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
+                            cudaStream_t stream) {
+  const int Sk = S * top_k;
+  if (top_k != 1) drop_out = nullptr;
+  if (E > kMaxExperts || E < 1 || D % 8 != 0) return cudaErrorInvalidValue;
+  const int gmax = max_groups(Sk, E, bn);
+  if (Sk == 0) {
+    // nothing to route: still publish zero counts / offsets and an empty group table
+    cudaError_t e = cudaMemsetAsync(ws.counts, 0, sizeof(int) * E, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ws.offsets, 0, sizeof(int) * (E + 1), stream);
+    if (e != cudaSuccess) return e;
+    if (counts_out) cudaMemsetAsync(counts_out, 0, sizeof(int) * E, stream);
+    if (offsets_out) cudaMemsetAsync(offsets_out, 0, sizeof(int) * (E + 1), stream);
+    return cudaMemsetAsync(ws.n_groups, 0, sizeof(int), stream);
+  }
+  const Chunking ck = make_chunking(Sk);
+  dispatch_count_kernel<<<ck.nchunks, kDispatchThreads, 0, stream>>>(idx, Sk, E, ck.chunk, ws.chunk_hist);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  const size_t dyn = sizeof(int) * (kDispatchThreads / 32) * E;
+#define B200MOE_SCATTER(T)                                                                                        \
+  dispatch_scatter_kernel<T><<<ck.nchunks, kDispatchThreads, dyn, stream>>>(                                      \
+      static_cast<const T*>(x), idx, score, Sk, D, E, top_k, ck.chunk, ck.nchunks, ws.chunk_hist, bn, gmax,       \
+      ws.counts, ws.offsets, ws.mapping, ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready,          \
+      counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual))
+  switch (dtype) {
+    case B200MOE_F32:
+      B200MOE_SCATTER(float);
+      break;
+    case B200MOE_F16:
+      B200MOE_SCATTER(__half);
+      break;
+    case B200MOE_BF16:
+      B200MOE_SCATTER(bf16);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef B200MOE_SCATTER
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
+                                int gmax, cudaStream_t stream) {
+  if (E > kMaxExperts) return cudaErrorInvalidValue;
+  build_groups_kernel<<<1, 256, 0, stream>>>(offsets, E, bn, groups, n_groups, h_ready, gmax);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace b200moe

@@ -1,0 +1,452 @@
+// Expert FFN: ONE persistent kernel for  y = act(x . W1[e]^T + b1[e]) . W2[e]^T + b2[e]  over all experts.
+//
+// Replaces the reference's per-expert loop of cublasSgemm + BiasSilu + cublasSgemm + Bias on 8 streams with two
+// host synchronisations (TRTAPI++/plugin/fmoe_expert_plugin/fmoe_expert_plugin.cpp:75-130) and the absent
+// fmoe_cuda.forward grouped GEMM (trainer_3m_fix/fmoe/functions.py:135-152).
+//
+// Design (B200 / sm_100a):
+//  * "swap-AB" orientation: the WEIGHT rows are the UMMA M dimension (always a full 128-row tile), the expert's
+//    TOKENS are the UMMA N dimension (BN = 32..256, chosen per launch from the average tokens per expert).  The
+//    3M-ASR regime is a few to ~100 tokens per expert, where the layer is bound by streaming 64 MiB of bf16
+//    weights from HBM: no tensor-core work is wasted on padding rows and every SM streams weight tiles.
+//  * tile = (group, 128 weight rows).  A group is one expert x one BN-token tile.  Phase-1 tiles compute
+//    h^T[128 hidden, tokens] = W1 tile . x^T (K = D), add b1, apply the activation and store h as bf16 [row, H];
+//    phase-2 tiles compute y^T[128 features, tokens] = W2 tile . h^T (K = H), add b2 and either store y in
+//    expert order or (top-1) write  out[token] = residual + ff_scale * score * y  straight to token order
+//    (the reference's gather, x gate_value, x ff_scale and + residual: fmoe_expert_kernel.cu:191-227,
+//    positionwise_feed_forward.py:257-258, fmoe_transformer.py:155-158).
+//  * both phases live in one static round-robin tile list; phase-2 tiles of a group are scheduled ~3 waves after
+//    its phase-1 tiles and wait on a per-group counter in global memory, so h only ever travels through L2.
+//  * warp roles: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, multi-stage mbarrier ring),
+//    warp 1 = single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, double buffered: 2 x 256 columns),
+//    warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/activation -> global).
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200moe {
+
+namespace {
+
+constexpr int kBlockM = 128;                           // weight rows per tile == UMMA M
+constexpr int kBlockK = 64;                            // bf16 elements per k-block == one 128 B swizzle row
+constexpr int kUmmaK = 16;                             // K per tcgen05.mma for 16-bit inputs
+constexpr int kMaxStages = 10;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;    // 16 KiB
+constexpr int kStageBudget = 200 * 1024;
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kAccStride = 256;                        // TMEM columns per accumulator buffer
+
+struct FfnParams {
+  const GroupRec* groups;
+  const int* n_groups;
+  int* h_ready;
+  const float* b1;
+  const float* b2;
+  bf16* hbuf;
+  void* out;
+  const void* residual;
+  const int* pos;
+  const float* row_score;
+  float ff_scale;
+  int top_k;
+  int E, D, H, bn, act, fused;
+  int stages;
+  int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
+};
+
+struct Tile {
+  int phase;  // 1 or 2
+  int g;      // group
+  int mb;     // 128-row block of the weight matrix
+};
+
+// Static schedule: L "head" slots hold only phase-1 tiles, the middle slots hold phase-1 tiles of group s and
+// phase-2 tiles of group s-L, the last L slots only phase-2 tiles.  Every dependency of a tile has a smaller index.
+__device__ __forceinline__ Tile decode_tile(int t, int ng, int lag, int m1, int m2) {
+  Tile r;
+  const int head = lag * m1;
+  if (t < head) {
+    r.phase = 1;
+    r.g = t / m1;
+    r.mb = t - r.g * m1;
+    return r;
+  }
+  const int per = m1 + m2;
+  const int mid_slots = ng - lag;
+  int u = t - head;
+  if (u < mid_slots * per) {
+    const int s = u / per;
+    const int w = u - s * per;
+    if (w < m1) {
+      r.phase = 1;
+      r.g = lag + s;
+      r.mb = w;
+    } else {
+      r.phase = 2;
+      r.g = s;
+      r.mb = w - m1;
+    }
+    return r;
+  }
+  u -= mid_slots * per;
+  r.phase = 2;
+  r.g = mid_slots + u / m2;
+  r.mb = u % m2;
+  return r;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == B200MOE_ACT_SILU) {
+    // x * sigmoid(x)  (trainer_3m_fix/utils/common.py:24-28; TRTAPI++/plugin/common/common.cuh sigmoid)
+    return __fdividef(v, 1.0f + __expf(-v));
+  } else if (act == B200MOE_ACT_RELU) {
+    return fmaxf(v, 0.0f);
+  } else {
+    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+           const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int stages = p.stages;
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.bn) * kBlockK * 2;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + stages * kAStageBytes;
+  const uint32_t bar_base = smem_b + stages * b_stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+  // generic pointer to the tmem slot for reading it back
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_w1);
+    ptx::prefetch_tensormap(&tm_w2);
+    ptx::prefetch_tensormap(&tm_x);
+    ptx::prefetch_tensormap(&tm_h);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), kEpiThreads / 32);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int ng = *p.n_groups;
+  const int m1 = p.H / kBlockM;
+  const int m2 = p.D / kBlockM;
+  const int lag = min(p.lag, ng);
+  const int n_tiles = ng * (m1 + m2);
+  const int kb1 = p.D / kBlockK;  // k-blocks of the first GEMM
+  const int kb2 = p.H / kBlockK;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kAStageBytes + b_stage_bytes;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(t, ng, lag, m1, m2);
+        const GroupRec gr = p.groups[tl.g];
+        const CUtensorMap* tm_a = tl.phase == 1 ? &tm_w1 : &tm_w2;
+        const CUtensorMap* tm_b = tl.phase == 1 ? &tm_x : &tm_h;
+        const int a_row = gr.expert * (tl.phase == 1 ? p.H : p.D) + tl.mb * kBlockM;
+        const int nkb = tl.phase == 1 ? kb1 : kb2;
+        if (tl.phase == 2) {
+          // wait until every phase-1 tile of this group has published its slice of h
+          while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1) __nanosleep(40);
+          ptx::fence_proxy_async_all();  // generic-proxy writes of h -> async-proxy (TMA) reads
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+          ptx::tma_load_2d(smem_a + stage * kAStageBytes, tm_a, full_bar(stage), kb * kBlockK, a_row,
+                           ptx::kEvictNormal);
+          ptx::tma_load_2d(smem_b + stage * b_stage_bytes, tm_b, full_bar(stage), kb * kBlockK, gr.row0,
+                           ptx::kEvictLast);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (one thread) ============================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc(1u /*bf16*/, kBlockM, static_cast<uint32_t>(p.bn));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const Tile tl = decode_tile(t, ng, lag, m1, m2);
+        const int nkb = tl.phase == 1 ? kb1 : kb2;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator buffer
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a + stage * kAStageBytes);
+          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b + stage * b_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance both descriptors by k * 16 elements * 2 B = 32 B -> +2 in 16-byte units
+            ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
+          if (kb == nkb - 1) ptx::umma_commit(tfull_bar(as));
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue (4 warps, one TMEM lane quarter each) ============================
+    const int q = warp & 3;  // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const Tile tl = decode_tile(t, ng, lag, m1, m2);
+      const GroupRec gr = p.groups[tl.g];
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      const int feat = tl.mb * kBlockM + q * 32 + lane;  // weight row == output feature of this thread
+      const int nrows = gr.nrows;
+      if (tl.phase == 1) {
+        const float bias = p.b1 ? p.b1[static_cast<size_t>(gr.expert) * p.H + feat] : 0.0f;
+        bf16* hrow = p.hbuf + static_cast<size_t>(gr.row0) * p.H + feat;
+        for (int c0 = 0; c0 < nrows; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          if (c0 + 32 >= nrows) {  // last chunk is in registers: hand the accumulator back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < nrows) {
+              const float v = apply_act(__uint_as_float(r[j]) + bias, p.act);
+              hrow[static_cast<size_t>(c0 + j) * p.H] = __float2bfloat16_rn(v);
+            }
+          }
+        }
+        // publish: all 128 epilogue threads' stores -> one release increment of the group's counter
+        ptx::fence_proxy_async_all();
+        __threadfence();
+        ptx::named_bar_sync(1, kEpiThreads);
+        if (threadIdx.x == kThreads - kEpiThreads) ptx::red_release_gpu_add(p.h_ready + tl.g, 1);
+      } else {
+        const float bias = p.b2 ? p.b2[static_cast<size_t>(gr.expert) * p.D + feat] : 0.0f;
+        OutT* out = static_cast<OutT*>(p.out);
+        const OutT* res = static_cast<const OutT*>(p.residual);
+        for (int c0 = 0; c0 < nrows; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          if (c0 + 32 >= nrows) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+          }
+          if (p.fused) {
+            // lane j fetches the routing record of column c0 + j, then it is broadcast per column
+            int my_tok = 0;
+            float my_sc = 0.0f;
+            if (c0 + lane < nrows) {
+              const int row = gr.row0 + c0 + lane;
+              my_tok = p.pos[row] / p.top_k;
+              my_sc = p.ff_scale * (p.row_score ? p.row_score[row] : 1.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int tok = __shfl_sync(0xffffffffu, my_tok, j);
+              const float sc = __shfl_sync(0xffffffffu, my_sc, j);
+              if (c0 + j < nrows) {
+                const size_t o = static_cast<size_t>(tok) * p.D + feat;
+                float v = sc * (__uint_as_float(r[j]) + bias);
+                if (res) v += to_float(res[o]);
+                out[o] = from_float<OutT>(v);
+              }
+            }
+          } else {
+            OutT* yrow = out + static_cast<size_t>(gr.row0) * p.D + feat;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < nrows) {
+                yrow[static_cast<size_t>(c0 + j) * p.D] = from_float<OutT>(__uint_as_float(r[j]) + bias);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols]; box = [box_rows, 64 cols] with 128 B swizzle.
+bool make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(bf16)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int stages_for_bn(int bn) {
+  int s = kStageBudget / (kAStageBytes + bn * kBlockK * 2);
+  return s > kMaxStages ? kMaxStages : s;
+}
+
+size_t smem_bytes_for(int bn, int stages) {
+  return 1024 + static_cast<size_t>(stages) * (kAStageBytes + bn * kBlockK * 2) + 8 * (2 * kMaxStages + 4) + 16;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename OutT>
+cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
+                         const CUtensorMap& th, const FfnParams& p, cudaStream_t stream) {
+  const size_t smem = smem_bytes_for(a.bn, p.stages);
+  static bool attr_set = false;  // per OutT instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ffn_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int m1 = a.H / kBlockM, m2 = a.D / kBlockM;
+  long long tiles_ub = static_cast<long long>(a.gmax) * (m1 + m2);
+  int grid = num_sms();
+  if (tiles_ub < grid) grid = static_cast<int>(tiles_ub);
+  if (grid < 1) grid = 1;
+  ffn_kernel<OutT><<<grid, kThreads, smem, stream>>>(tw1, tw2, tx, th, p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
+  if (a.n_rows <= 0) return cudaSuccess;
+  if (a.D % kBlockM != 0 || a.H % kBlockM != 0) return cudaErrorInvalidValue;
+  if (a.bn % 16 != 0 || a.bn < 16 || a.bn > 256) return cudaErrorInvalidValue;
+  if (a.fused && a.top_k != 1) return cudaErrorInvalidValue;
+  CUtensorMap tw1, tw2, tx, th;
+  if (!make_tmap_bf16(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM) ||
+      !make_tmap_bf16(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM) ||
+      !make_tmap_bf16(&tx, a.xbuf, a.n_rows, a.D, a.bn) || !make_tmap_bf16(&th, a.hbuf, a.n_rows, a.H, a.bn)) {
+    return cudaErrorInvalidValue;
+  }
+  FfnParams p;
+  p.groups = a.groups;
+  p.n_groups = a.n_groups;
+  p.h_ready = a.h_ready;
+  p.b1 = a.b1;
+  p.b2 = a.b2;
+  p.hbuf = a.hbuf;
+  p.out = a.out;
+  p.residual = a.residual;
+  p.pos = a.pos;
+  p.row_score = a.row_score;
+  p.ff_scale = a.ff_scale;
+  p.top_k = a.top_k < 1 ? 1 : a.top_k;
+  p.E = a.E;
+  p.D = a.D;
+  p.H = a.H;
+  p.bn = a.bn;
+  p.act = a.act;
+  p.fused = a.fused;
+  p.stages = stages_for_bn(a.bn);
+  // phase-2 tiles trail their group's phase-1 tiles by ~3 waves of the grid
+  const int m1 = a.H / kBlockM;
+  p.lag = (3 * num_sms() + m1 - 1) / m1;
+  switch (a.out_dtype) {
+    case B200MOE_F32:
+      return launch_typed<float>(a, tw1, tw2, tx, th, p, stream);
+    case B200MOE_F16:
+      return launch_typed<__half>(a, tw1, tw2, tx, th, p, stream);
+    case B200MOE_BF16:
+      return launch_typed<bf16>(a, tw1, tw2, tx, th, p, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace b200moe

@@ -1,0 +1,189 @@
+/*
+ * b200moe.h -- C ABI of the B200-native fast_moe expert layer (gate -> dispatch -> 32-expert FFN -> combine).
+ *
+ * This is the drop-in boundary for ONE hot path of LitLeo/3m-asr-inference: the work its TensorRT plugins
+ * `SoftmaxTopKPluginDynamic` and `FMoEExpertPluginDynamic` do in `enqueue`, and the work trainer_3m_fix/fmoe's
+ * FMoE.forward hands to the (un-vendored) `fmoe_cuda` extension.  Reference citations are relative to the
+ * upstream tree (/root/reference in the build container):
+ *
+ *   b200moe_gate        <- TRTAPI++/plugin/softmax_topk_plugin/softmax_topk_plugin.cpp:88-127 (enqueue),
+ *                          softmax_topk_kernel.cu:26-120, plus the router MatMul/Add that precede it in
+ *                          trainer_3m_fix/layer/positionwise_feed_forward.py:169-207,225; and
+ *                          trainer_3m_fix/fmoe/gates.py:51-66 (NaiveGate.forward) for gate_mode 1.
+ *   b200moe_dispatch    <- fmoe_expert_kernel.cu:25-128 (ScatterMapping + ScatterMappingCopy) and
+ *                          trainer_3m_fix/fmoe/functions.py:13-52,62-86 (moe_prepare_forward, MOEScatter.forward).
+ *   b200moe_expert_ffn  <- fmoe_expert_plugin.cpp:80-128 (per-expert cublasSgemm/BiasSilu/cublasSgemm/Bias loop)
+ *                          and functions.py:135-152 (MOEbiasLinear.forward), fmoe/transformer.py:22-30.
+ *   b200moe_combine     <- fmoe_expert_kernel.cu:191-227 (GatherrMappingCopy), functions.py:175-199 (MOEGather),
+ *                          positionwise_feed_forward.py:257-258 (x gate_value), fmoe/layers.py:204-206 (bmm with
+ *                          the top-k scores), layer/fmoe_transformer.py:155-158 (x ff_scale, + residual).
+ *   b200moe_forward     <- the whole of LocalFmoeCatEmbedFeedForward.forward + the scale/residual that follow it
+ *                          (positionwise_feed_forward.py:209-265, fmoe_transformer.py:145-158).
+ *   b200moe_plugin_*    <- FMoEExpertPlugin / FMoEExpertPluginCreator (fmoe_expert_plugin.h:31-132,
+ *                          fmoe_expert_plugin.cpp:144-377): same creator fields, same six inputs, same
+ *                          32-byte serialisation, same int status convention (0 = ok).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its comment says "host";
+ *   - memory is caller-owned; no entry point allocates device memory, none synchronises the host, all work is
+ *     enqueued on the caller's stream, so every entry point is CUDA-graph capturable;
+ *   - return value: 0 = ok, negative = error (B200MOE_ERR_*); b200moe_last_error() gives the message of the
+ *     calling thread's last failure;
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU the compute entry points return
+ *     B200MOE_ERR_CUDA.
+ */
+#ifndef B200MOE_H_
+#define B200MOE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Opaque CUDA stream (same type the CUDA runtime declares). */
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define B200MOE_VERSION 100
+
+/* Element types of activations at the boundary.  0/1 are the reference plugin's `data_type` field values
+ * (fmoe_expert_plugin.cpp:325-366: 0 = fp32, 1 = fp16); 2 (bf16) is the native type of this implementation. */
+enum { B200MOE_F32 = 0, B200MOE_F16 = 1, B200MOE_BF16 = 2 };
+
+/* Expert activation (reference: act_type is parsed but SiLU is hard-coded, fmoe_expert_plugin.cpp:106). */
+enum { B200MOE_ACT_SILU = 0, B200MOE_ACT_RELU = 1, B200MOE_ACT_GELU = 2 };
+
+/* Gate flavours. 0: 3M-ASR router, softmax over all experts then max (top-1), value = max probability.
+ * 1: FastMoE NaiveGate, top-k of the logits then softmax over the k selected logits. */
+enum { B200MOE_GATE_3M = 0, B200MOE_GATE_NAIVE = 1 };
+
+/* Arithmetic of the expert GEMMs. */
+enum { B200MOE_COMPUTE_BF16 = 0, B200MOE_COMPUTE_TF32 = 1 };
+
+enum {
+  B200MOE_OK = 0,
+  B200MOE_ERR_ARG = -1,      /* bad argument (null pointer, unsupported size or dtype) */
+  B200MOE_ERR_CUDA = -2,     /* a CUDA runtime / driver call failed (message has the CUDA error string) */
+  B200MOE_ERR_WORKSPACE = -3 /* workspace too small */
+};
+
+const char* b200moe_last_error(void);
+int b200moe_version(void);
+/* 1 if device `dev` can run the kernels (compute capability 10.x), 0 if not, negative on CUDA error. */
+int b200moe_device_supported(int dev);
+
+/* ---- weight packing (once per checkpoint load) ------------------------------------------------------------
+ * Expert weights stay in the reference's layout, FMoELinear.weight = [E, out, in] row-major
+ * (trainer_3m_fix/fmoe/layers.py:34), which is already the K-major B operand the tensor cores want; packing
+ * only casts them to bf16.  n = number of elements. */
+int b200moe_pack_bf16(const void* src, int src_dtype, void* dst_bf16, size_t n, cudaStream_t stream);
+
+/* ---- workspace --------------------------------------------------------------------------------------------
+ * Bytes of scratch b200moe_forward / b200moe_plugin_enqueue / the staged entry points need for S tokens.
+ * (Reference: FMoEExpertPlugin::getWorkspaceSize, fmoe_expert_plugin.cpp:224-239.) */
+size_t b200moe_workspace_bytes(int S, int E, int D, int H, int top_k);
+
+/* ---- stage 1: gate -------------------------------------------------------------------------------------------
+ * logits = cat(embed, x) . Wr (+ br); embed may be NULL (then R = D).  x [B*T, D], embed [B*T, Demb] in `dtype`;
+ * Wr [Demb + D, E] fp32 row-major (router_weights, positionwise_feed_forward.py:134-135), br [E] fp32 or NULL.
+ * x_len [B] int32 or NULL: rows t >= x_len[b] are padding; they get idx = -1, score = 0 (the reference leaves
+ * them unwritten, softmax_topk_kernel.cu:40).  Ties resolve to the lowest expert index.
+ * Outputs: idx [B*T, top_k] int32, score [B*T, top_k] fp32 (top-k ordered by descending logit). */
+int b200moe_gate(const void* x, const void* embed, const float* Wr, const float* br, const int* x_len, int B, int T,
+                 int D, int Demb, int E, int top_k, int gate_mode, int dtype, int* idx, float* score,
+                 cudaStream_t stream);
+
+/* ---- stage 2: dispatch -------------------------------------------------------------------------------------
+ * Counts tokens per expert, exclusive-scans, and stably scatters token rows into expert-contiguous order:
+ *   mapping[i] = offsets[idx[i]] + #{ j < i : idx[j] == idx[i] }   for entry i = s*top_k + j; -1 if idx[i] < 0
+ *   xbuf[mapping[i], :] = bf16(x[i / top_k, :])
+ * counts [E], offsets [E+1] (= the reference's acc_histogram), mapping [S*top_k], all int32.
+ * xbuf [S*top_k, D] bf16.  ws = scratch of at least b200moe_workspace_bytes(). */
+int b200moe_dispatch(const void* x, const int* idx, int S, int D, int E, int top_k, int dtype, int* counts,
+                     int* offsets, int* mapping, void* xbuf, void* ws, cudaStream_t stream);
+
+/* ---- stage 3: expert FFN ----------------------------------------------------------------------------------
+ * For every expert e and its rows [offsets[e], offsets[e+1]) of xbuf:
+ *   ybuf = act(xbuf . W1[e]^T + b1[e]) . W2[e]^T + b2[e]
+ * W1 [E, H, D], W2 [E, D, H] bf16 (b200moe_pack_bf16 of the reference tensors), b1 [E, H], b2 [E, D] fp32
+ * (NULL = no bias).  n_rows = S*top_k (capacity of xbuf / ybuf).  ybuf [n_rows, D] in `out_dtype`.
+ * One persistent tcgen05/TMEM/TMA kernel; no host synchronisation (the reference syncs twice and launches up to
+ * 128 kernels on 8 streams, fmoe_expert_plugin.cpp:75-130). */
+int b200moe_expert_ffn(const void* xbuf, const int* offsets, int n_rows, const void* W1, const float* b1,
+                       const void* W2, const float* b2, int E, int D, int H, int act_type, int out_dtype, void* ybuf,
+                       void* ws, cudaStream_t stream);
+
+/* ---- stage 4: combine --------------------------------------------------------------------------------------
+ * out[s, :] = (residual ? residual[s, :] : 0) + ff_scale * sum_j (score ? score[s, j] : 1) * ybuf[mapping[s*k+j], :]
+ * Entries with mapping < 0 contribute nothing.  score NULL = the reference's keep_expert_output.
+ * ybuf / residual / out are in `dtype`. */
+int b200moe_combine(const void* ybuf, const int* mapping, const float* score, const void* residual, float ff_scale,
+                    int S, int D, int top_k, int dtype, void* out, cudaStream_t stream);
+
+/* ---- the fused layer --------------------------------------------------------------------------------------- */
+typedef struct b200moe_layer_args {
+  /* activations, `dtype` */
+  const void* x;        /* [B*T, D]  MoE input (already layer-normed by the caller)                  */
+  const void* embed;    /* [B*T, Demb] or NULL                                                        */
+  const void* residual; /* [B*T, D] or NULL                                                           */
+  void* out;            /* [B*T, D]                                                                    */
+  const int* x_len;     /* [B] or NULL                                                                 */
+  /* router */
+  const float* Wr;      /* [Demb + D, E] fp32                                                         */
+  const float* br;      /* [E] fp32 or NULL                                                            */
+  /* experts (bf16 packed weights, fp32 biases) */
+  const void* W1;       /* [E, H, D] bf16                                                              */
+  const float* b1;      /* [E, H] or NULL                                                              */
+  const void* W2;       /* [E, D, H] bf16                                                              */
+  const float* b2;      /* [E, D] or NULL                                                              */
+  int B, T, D, Demb, E, H, top_k;
+  int gate_mode, act_type, dtype;
+  int keep_expert_output; /* 1: do not multiply by the gate value (positionwise_feed_forward.py:257)  */
+  float ff_scale;         /* 0.5 for the macaron Conformer wiring (fmoe_transformer.py:56-58,155)     */
+  /* optional routing outputs for parity checks (NULL to skip): idx/score [B*T, top_k], counts [E],
+   * mapping [B*T*top_k] */
+  int* idx_out;
+  float* score_out;
+  int* counts_out;
+  int* mapping_out;
+} b200moe_layer_args;
+
+int b200moe_forward(const b200moe_layer_args* args, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- plugin object: mirror of FMoEExpertPlugin / FMoEExpertPluginCreator --------------------------------------
+ * Fields are the creator's (fmoe_expert_plugin.cpp:325-366): data_type (0 fp32, 1 fp16; anything else fails like
+ * the reference creator, except 2 = bf16 which is new), num_expert, idim, hidden_units, act_type. */
+typedef struct b200moe_plugin b200moe_plugin;
+
+b200moe_plugin* b200moe_plugin_create(int data_type, int num_expert, int idim, int hidden_units, int act_type);
+b200moe_plugin* b200moe_plugin_clone(const b200moe_plugin* p);
+/* 32 bytes: data_type, num_expert, idim, hidden_units, act_type + 3 zero ints (fmoe_expert_plugin.cpp:288-304). */
+size_t b200moe_plugin_serialization_size(const b200moe_plugin* p);
+int b200moe_plugin_serialize(const b200moe_plugin* p, void* host_buffer);
+b200moe_plugin* b200moe_plugin_deserialize(const void* host_data, size_t length);
+void b200moe_plugin_destroy(b200moe_plugin* p);
+/* getWorkspaceSize: includes room for the bf16 copy of the weights the first enqueue packs. */
+size_t b200moe_plugin_workspace_bytes(const b200moe_plugin* p, int S);
+/* enqueue: the reference's six inputs in the reference's order -- input [S, idim], gate_idx [S] int32,
+ * w1_weight [E, H, D], w1_bias [E, H], w2_weight [E, D, H], w2_bias [E, D] (all `data_type` except gate_idx) --
+ * and its single un-weighted output [S, idim].  Weights are re-packed only when their pointers change. */
+int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate_idx, const void* w1_weight,
+                           const void* w1_bias, const void* w2_weight, const void* w2_bias, int S, void* output,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- companion gate plugin: SoftmaxTopKPluginDynamic (softmax_topk_plugin.cpp:88-136) --------------------------
+ * logits [B, T, E] in `data_type`, mask [B] int32 (valid lengths) -> value [B, T] (`data_type`), idx [B, T]
+ * int32; top-1 only, value = 1 / sum(exp(l - max)).  Rows >= mask[b] get idx -1 / value 0. */
+int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int T, int E, int data_type,
+                                 void* value, int* idx, cudaStream_t stream);
+
+/* Number of kernels this library launched on behalf of the calling process (for bench accounting). */
+unsigned long long b200moe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MOE_H_ */
