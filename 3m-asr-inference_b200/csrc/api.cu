@@ -46,6 +46,37 @@ __global__ void __launch_bounds__(256) to_f32_kernel(const void* src, int dtype,
   }
 }
 
+// ---- optional per-stage timing with CUDA events (eager mode only; used by bench.py for the roofline numbers) ----------
+constexpr int kStages = 4;  // 0 gate, 1 dispatch, 2 expert_ffn (+ fused combine), 3 combine
+constexpr int kMaxRecords = 8192;
+struct StageTimer {
+  bool enabled = false;
+  cudaEvent_t ev[kMaxRecords][2];
+  int stage[kMaxRecords];
+  int created = 0;
+  int used = 0;
+};
+StageTimer g_timer;
+
+struct StageScope {
+  int slot = -1;
+  cudaStream_t stream;
+  StageScope(int stage, cudaStream_t s) : stream(s) {
+    if (!g_timer.enabled || g_timer.used >= kMaxRecords) return;
+    slot = g_timer.used++;
+    if (slot >= g_timer.created) {
+      cudaEventCreate(&g_timer.ev[slot][0]);
+      cudaEventCreate(&g_timer.ev[slot][1]);
+      g_timer.created = slot + 1;
+    }
+    g_timer.stage[slot] = stage;
+    cudaEventRecord(g_timer.ev[slot][0], stream);
+  }
+  ~StageScope() {
+    if (slot >= 0) cudaEventRecord(g_timer.ev[slot][1], stream);
+  }
+};
+
 }  // namespace
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
@@ -78,6 +109,31 @@ int b200moe_device_supported(int dev) {
   cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
   return major == 10 ? 1 : 0;
+}
+
+int b200moe_profile_enable(int on) {
+  g_timer.enabled = on != 0;
+  g_timer.used = 0;
+  return B200MOE_OK;
+}
+
+int b200moe_profile_read(float* stage_ms, int* stage_calls) {
+  if (!stage_ms || !stage_calls) return fail(B200MOE_ERR_ARG, "profile_read: null pointer");
+  for (int i = 0; i < kStages; ++i) {
+    stage_ms[i] = 0.0f;
+    stage_calls[i] = 0;
+  }
+  for (int r = 0; r < g_timer.used; ++r) {
+    cudaError_t e = cudaEventSynchronize(g_timer.ev[r][1]);
+    if (e != cudaSuccess) return cuda_fail(e, "profile_read");
+    float ms = 0.0f;
+    e = cudaEventElapsedTime(&ms, g_timer.ev[r][0], g_timer.ev[r][1]);
+    if (e != cudaSuccess) return cuda_fail(e, "profile_read");
+    stage_ms[g_timer.stage[r]] += ms;
+    stage_calls[g_timer.stage[r]] += 1;
+  }
+  g_timer.used = 0;
+  return B200MOE_OK;
 }
 
 int b200moe_pack_bf16(const void* src, int src_dtype, void* dst_bf16, size_t n, cudaStream_t stream) {
@@ -213,15 +269,23 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   int* idx = a->idx_out ? a->idx_out : w.idx;
   float* score = a->score_out ? a->score_out : w.score;
 
-  cudaError_t e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
-                              a->gate_mode, a->dtype, idx, score, stream);
+  cudaError_t e;
+  {
+    StageScope t(0, stream);
+    e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k, a->gate_mode,
+                    a->dtype, idx, score, stream);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "forward/gate");
 
   const int bn = choose_bn(Sk, a->E);
   const int gmax = max_groups(Sk, a->E, bn);
   const bool fused = a->top_k == 1;
-  e = launch_dispatch(a->x, idx, a->keep_expert_output ? nullptr : score, S, a->D, a->E, a->top_k, a->dtype, bn, w,
-                      a->counts_out, nullptr, a->mapping_out, w.xbuf, fused ? a->out : nullptr, a->residual, stream);
+  {
+    StageScope t(1, stream);
+    e = launch_dispatch(a->x, idx, a->keep_expert_output ? nullptr : score, S, a->D, a->E, a->top_k, a->dtype, bn, w,
+                        a->counts_out, nullptr, a->mapping_out, w.xbuf, fused ? a->out : nullptr, a->residual,
+                        stream);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "forward/dispatch");
 
   FfnLaunch f{};
@@ -254,9 +318,13 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
     f.fused = 0;
     f.out = w.ybuf;
   }
-  e = launch_ffn(f, stream);
+  {
+    StageScope t(2, stream);
+    e = launch_ffn(f, stream);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "forward/expert_ffn");
   if (!fused) {
+    StageScope t(3, stream);
     e = launch_combine(w.ybuf, w.mapping, a->keep_expert_output ? nullptr : score, a->residual, a->ff_scale, S, a->D,
                        a->top_k, a->dtype, a->out, stream);
     if (e != cudaSuccess) return cuda_fail(e, "forward/combine");

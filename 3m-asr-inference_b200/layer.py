@@ -1,0 +1,98 @@
+"""Mirror of trainer_3m_fix/layer/positionwise_feed_forward.py: Expert (:94-112) and LocalFmoeCatEmbedFeedForward
+(:115-265), the module that replaces a Conformer block's feed_forward with gated FFN experts.
+
+Same constructor arguments, same parameter names and shapes (`experts.w_1.{weight,bias}`, `experts.w_2.{weight,bias}`,
+`router_weights [idim + embed_dim, num_experts * world_size]`, optional `router_bias`), so a 3M-ASR state_dict loads
+unchanged.  The reference's forward takes a TensorRT `network_helper` and emits graph layers; here forward takes the
+tensors and runs the layer: concat + router MatMul + softmax/top-1 + dispatch + 32-expert FFN + gather + x gate_value,
+optionally with the x ff_scale and + residual that the Conformer block applies next (layer/fmoe_transformer.py:145-158).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .fmoe.layers import FMoELinear, PackedExpertCache, activation_code
+
+
+class Swish(torch.nn.Module):
+    """trainer_3m_fix/utils/common.py:24-28"""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return x * torch.sigmoid(x)
+
+
+class Expert(torch.nn.Module):
+    """Parameter holder for the two expert linears (positionwise_feed_forward.py:94-112)."""
+
+    def __init__(self, num_experts, idim, hidden_units, dropout_rate, activation=torch.nn.ReLU(), rank=0):
+        super().__init__()
+        self.w_1 = FMoELinear(num_experts, idim, hidden_units, bias=True, rank=rank)
+        self.activation = activation
+        self.dropout = torch.nn.Dropout(dropout_rate)
+        self.w_2 = FMoELinear(num_experts, hidden_units, idim, bias=True, rank=rank)
+
+
+class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
+    def __init__(self, idim, embed_dim, num_experts=4, rank=0, world_size=1, hidden_units=1024, dropout_rate=0.0,
+                 activation=torch.nn.ReLU(), capacity_factor=-1.0, router_regularization="l1_plus_importance",
+                 router_with_bias=False, keep_expert_output=False, rand_init_router=False, comm=None):
+        super().__init__()
+        self.rank = rank
+        self.world_size = world_size
+        self.comm = comm
+        self.num_experts = num_experts
+        self.capacity_factor = capacity_factor
+        self.router_regularization = router_regularization
+        self.idim = idim
+        self.embed_dim = embed_dim
+        self.hidden_units = hidden_units
+        self.experts = Expert(num_experts, idim, hidden_units, dropout_rate, activation=activation, rank=rank)
+        router_input_dim = idim + embed_dim
+        self.router_weights = torch.nn.Parameter(torch.zeros(router_input_dim, num_experts * world_size))
+        if router_with_bias:
+            self.router_bias = torch.nn.Parameter(torch.zeros(num_experts * world_size))
+        else:
+            self.router_bias = None
+        if rand_init_router:
+            torch.nn.init.xavier_uniform_(self.router_weights, gain=0.5)
+        self.keep_expert_output = keep_expert_output
+        self._cache = PackedExpertCache()
+        if capacity_factor is not None and capacity_factor > 0:
+            raise NotImplementedError("token dropping by capacity is a training-time feature (cf = -1 at inference)")
+
+    def _router(self):
+        w = self.router_weights
+        wr = w.detach()
+        if wr.dtype != torch.float32:
+            wr = wr.float()
+        br = None if self.router_bias is None else self.router_bias.detach().float().contiguous()
+        return wr.contiguous(), br
+
+    def forward(self, inputs: torch.Tensor, embed: Optional[torch.Tensor], mask: Optional[torch.Tensor] = None, *,
+                residual: Optional[torch.Tensor] = None, ff_scale: float = 1.0, return_routing: bool = False):
+        """inputs [B, T, idim]; embed [B, T, embed_dim]; mask [B] int32 valid lengths (the plugin's `mask` input,
+        softmax_topk_plugin.cpp:88-127).  Returns the gate-weighted expert output [B, T, idim]; with `residual` /
+        `ff_scale` the Conformer block's  residual + ff_scale * out  is fused in as well."""
+        assert inputs.dim() == 3
+        B, T, D = inputs.shape
+        x = inputs.contiguous()
+        e = None if embed is None else embed.contiguous()
+        Wr, br = self._router()
+        packed = self._cache.get(self.experts.w_1, self.experts.w_2)
+        act = activation_code(self.experts.activation)
+        x_len = None if mask is None else mask.reshape(-1).to(torch.int32).contiguous()
+        if self.world_size > 1:
+            from . import ep
+            out = ep.ep_moe_layer(x.view(B * T, D), None if e is None else e.view(B * T, -1), Wr, br, packed,
+                                  num_local_expert=self.num_experts, group=self.comm, top_k=1,
+                                  gate_mode=ops.GATE_3M, act_type=act, ff_scale=ff_scale,
+                                  residual=None if residual is None else residual.contiguous().view(B * T, D),
+                                  keep_expert_output=self.keep_expert_output, x_len=x_len, seq_len=T)
+            return out.view(B, T, D)
+        res = ops.moe_layer(x, e, Wr, br, packed, residual=None if residual is None else residual.contiguous(),
+                            x_len=x_len, top_k=1, gate_mode=ops.GATE_3M, act_type=act, ff_scale=ff_scale,
+                            keep_expert_output=self.keep_expert_output, return_routing=return_routing)
+        return res if return_routing else res.out

@@ -1,0 +1,255 @@
+"""PyTorch-facing wrappers over the C ABI (device memory and streams come from torch; the arithmetic does not).
+
+Each function mirrors one stage of the reference path (see include/b200moe.h for file:line citations):
+  gate        -> router MatMul + SoftmaxTopKPluginDynamic / NaiveGate.forward
+  dispatch    -> moe_prepare_forward + MOEScatter.forward / ScatterMapping(+Copy) kernels
+  expert_ffn  -> MOEbiasLinear x2 with the activation / the per-expert cuBLAS loop of FMoEExpertPlugin::enqueue
+  combine     -> MOEGather.forward + x gate score (+ x ff_scale + residual)
+  moe_layer   -> all of the above behind one call (what the modules in fmoe/ and layer.py use)
+Inputs must be CUDA tensors; there is deliberately no CPU implementation.
+"""
+from __future__ import annotations
+
+from typing import Dict, NamedTuple, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_RELU, ACT_SILU, BF16, F16, F32, GATE_3M, GATE_NAIVE  # noqa: F401 (re-exported)
+
+_DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported activation dtype {t.dtype}; use float32, float16 or bfloat16") from None
+
+
+def _need_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("b200moe ops need CUDA tensors: this package has no CPU fallback")
+        if not t.is_contiguous():
+            raise ValueError("b200moe ops need contiguous tensors")
+        dev = t.device if dev is None else dev
+        if t.device != dev:
+            raise ValueError("all tensors must live on the same device")
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(_lib.load().b200moe_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    _lib.check(_lib.load().b200moe_profile_enable(int(on)), "b200moe_profile_enable")
+
+
+def profile_read():
+    """-> ({stage: total ms}, {stage: calls}) since the last read; stages: gate, dispatch, expert_ffn, combine."""
+    import ctypes
+    ms = (ctypes.c_float * 4)()
+    n = (ctypes.c_int * 4)()
+    _lib.check(_lib.load().b200moe_profile_read(ms, n), "b200moe_profile_read")
+    names = ("gate", "dispatch", "expert_ffn", "combine")
+    return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
+
+
+# ---- workspace cache ------------------------------------------------------------------------------------------------
+_WS: Dict[Tuple, torch.Tensor] = {}
+
+
+def workspace_bytes(S: int, E: int, D: int, H: int, top_k: int) -> int:
+    return int(_lib.load().b200moe_workspace_bytes(S, E, D, H, top_k))
+
+
+def get_workspace(device, S: int, E: int, D: int, H: int, top_k: int) -> torch.Tensor:
+    """One cached scratch buffer per (device, stream, shape). Sized by the library, owned by torch's allocator."""
+    key = (str(device), _stream(), S, E, D, H, top_k)
+    ws = _WS.get(key)
+    if ws is None:
+        n = workspace_bytes(S, E, D, H, top_k)
+        ws = torch.empty(max(n, 1), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def clear_workspaces() -> None:
+    _WS.clear()
+
+
+# ---- weights ----------------------------------------------------------------------------------------------------------
+def pack_bf16(w: torch.Tensor) -> torch.Tensor:
+    """Casts expert weights ([E, out, in], the reference's FMoELinear layout) to bf16 on the device, once."""
+    _need_cuda(w)
+    if w.dtype == torch.bfloat16:
+        return w
+    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    lib = _lib.load()
+    _lib.check(lib.b200moe_pack_bf16(_ptr(w), dtype_code(w), _ptr(out), w.numel(), _stream()), "b200moe_pack_bf16")
+    return out
+
+
+class PackedExperts(NamedTuple):
+    W1: torch.Tensor  # [E, H, D] bf16
+    b1: Optional[torch.Tensor]  # [E, H] fp32
+    W2: torch.Tensor  # [E, D, H] bf16
+    b2: Optional[torch.Tensor]  # [E, D] fp32
+
+
+def pack_experts(W1, b1, W2, b2) -> PackedExperts:
+    def f32(b):
+        return None if b is None else b.detach().float().contiguous()
+    return PackedExperts(pack_bf16(W1.detach().contiguous()), f32(b1), pack_bf16(W2.detach().contiguous()), f32(b2))
+
+
+# ---- stages ---------------------------------------------------------------------------------------------------------------
+def gate(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, br: Optional[torch.Tensor] = None,
+         x_len: Optional[torch.Tensor] = None, *, top_k: int = 1, gate_mode: int = GATE_3M,
+         seq_len: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x [S, D] (or [B, T, D]), embed likewise or None, Wr [Demb + D, E] fp32. Returns idx int32, score fp32 [S, top_k]."""
+    dev = _need_cuda(x, embed, Wr, br, x_len)
+    if x.dim() == 3:
+        B, T, D = x.shape
+    else:
+        S, D = x.shape
+        T = seq_len if seq_len is not None else S
+        B = S // T if T else 0
+    S = B * T
+    Demb = 0 if embed is None else embed.shape[-1]
+    E = Wr.shape[1]
+    if Wr.dtype != torch.float32 or Wr.shape[0] != D + Demb:
+        raise ValueError(f"Wr must be fp32 [{D + Demb}, E], got {tuple(Wr.shape)} {Wr.dtype}")
+    idx = torch.empty(S, top_k, dtype=torch.int32, device=dev)
+    score = torch.empty(S, top_k, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.b200moe_gate(_ptr(x), _ptr(embed), _ptr(Wr), _ptr(br), _ptr(x_len), B, T, D, Demb, E, top_k,
+                                gate_mode, dtype_code(x), _ptr(idx), _ptr(score), _stream()), "b200moe_gate")
+    return idx, score
+
+
+def softmax_topk(logits: torch.Tensor, mask: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """SoftmaxTopKPluginDynamic.enqueue: logits [B, T, E], mask [B] int32 -> value [B, T, 1] (logits dtype), idx [B, T, 1]."""
+    dev = _need_cuda(logits, mask)
+    B, T, E = logits.shape
+    value = torch.empty(B, T, 1, dtype=logits.dtype, device=dev)
+    idx = torch.empty(B, T, 1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.b200moe_softmax_topk_enqueue(_ptr(logits), _ptr(mask), B, T, E, dtype_code(logits), _ptr(value),
+                                                _ptr(idx), _stream()), "b200moe_softmax_topk_enqueue")
+    return value, idx
+
+
+class Dispatched(NamedTuple):
+    counts: torch.Tensor   # [E] int32
+    offsets: torch.Tensor  # [E + 1] int32
+    mapping: torch.Tensor  # [S * top_k] int32
+    xbuf: torch.Tensor     # [S * top_k, D] bf16
+    ws: torch.Tensor
+
+
+def dispatch(x: torch.Tensor, idx: torch.Tensor, num_expert: int, *, hidden: int = 0) -> Dispatched:
+    """x [S, D]; idx [S, top_k] (or [S * top_k]) int32. `hidden` sizes the workspace for a following expert_ffn."""
+    dev = _need_cuda(x, idx)
+    S, D = x.shape
+    top_k = idx.numel() // S if S else 1
+    if idx.dtype != torch.int32:
+        raise TypeError("idx must be int32")
+    counts = torch.empty(num_expert, dtype=torch.int32, device=dev)
+    offsets = torch.empty(num_expert + 1, dtype=torch.int32, device=dev)
+    mapping = torch.empty(S * top_k, dtype=torch.int32, device=dev)
+    xbuf = torch.empty(S * top_k, D, dtype=torch.bfloat16, device=dev)
+    ws = get_workspace(dev, S, num_expert, D, hidden, top_k)
+    lib = _lib.load()
+    _lib.check(lib.b200moe_dispatch(_ptr(x), _ptr(idx), S, D, num_expert, top_k, dtype_code(x), _ptr(counts),
+                                    _ptr(offsets), _ptr(mapping), _ptr(xbuf), _ptr(ws), _stream()),
+               "b200moe_dispatch")
+    return Dispatched(counts, offsets, mapping, xbuf, ws)
+
+
+def expert_ffn(xbuf: torch.Tensor, offsets: torch.Tensor, experts: PackedExperts, *, act_type: int = ACT_SILU,
+               out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    dev = _need_cuda(xbuf, offsets, experts.W1, experts.b1, experts.W2, experts.b2)
+    n_rows, D = xbuf.shape
+    E, H, D2 = experts.W1.shape
+    if D2 != D or xbuf.dtype != torch.bfloat16 or experts.W1.dtype != torch.bfloat16:
+        raise ValueError("xbuf must be bf16 [rows, D] and the weights bf16 [E, H, D] / [E, D, H]")
+    ybuf = torch.empty(n_rows, D, dtype=out_dtype, device=dev)
+    ws = get_workspace(dev, n_rows, E, D, H, 1)
+    lib = _lib.load()
+    _lib.check(lib.b200moe_expert_ffn(_ptr(xbuf), _ptr(offsets), n_rows, _ptr(experts.W1), _ptr(experts.b1),
+                                      _ptr(experts.W2), _ptr(experts.b2), E, D, H, act_type, _DTYPE_CODE[out_dtype],
+                                      _ptr(ybuf), _ptr(ws), _stream()), "b200moe_expert_ffn")
+    return ybuf
+
+
+def combine(ybuf: torch.Tensor, mapping: torch.Tensor, score: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+            *, ff_scale: float = 1.0, top_k: int = 1) -> torch.Tensor:
+    dev = _need_cuda(ybuf, mapping, score, residual)
+    D = ybuf.shape[1]
+    S = mapping.numel() // top_k
+    out = torch.empty(S, D, dtype=ybuf.dtype, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.b200moe_combine(_ptr(ybuf), _ptr(mapping), _ptr(score), _ptr(residual), float(ff_scale), S, D,
+                                   top_k, dtype_code(ybuf), _ptr(out), _stream()), "b200moe_combine")
+    return out
+
+
+class LayerOut(NamedTuple):
+    out: torch.Tensor
+    idx: Optional[torch.Tensor]
+    score: Optional[torch.Tensor]
+    counts: Optional[torch.Tensor]
+    mapping: Optional[torch.Tensor]
+
+
+def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, br: Optional[torch.Tensor],
+              experts: PackedExperts, *, residual: Optional[torch.Tensor] = None, x_len: Optional[torch.Tensor] = None,
+              seq_len: Optional[int] = None, top_k: int = 1, gate_mode: int = GATE_3M, act_type: int = ACT_SILU,
+              ff_scale: float = 1.0, keep_expert_output: bool = False, out: Optional[torch.Tensor] = None,
+              return_routing: bool = False, ws: Optional[torch.Tensor] = None) -> LayerOut:
+    """The fused layer: out = (residual) + ff_scale * sum_k score_k * FFN_{e_k}(x).  x [S, D] or [B, T, D]."""
+    dev = _need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out)
+    shape = x.shape
+    if x.dim() == 3:
+        B, T, D = x.shape
+    else:
+        S, D = x.shape
+        T = seq_len if seq_len is not None else S
+        B = S // T if T else 0
+    S = B * T
+    E, H, _ = experts.W1.shape
+    Demb = 0 if embed is None else embed.shape[-1]
+    if out is None:
+        out = torch.empty(shape, dtype=x.dtype, device=dev)
+    if ws is None:
+        ws = get_workspace(dev, S, E, D, H, top_k)
+    idx = score = counts = mapping = None
+    if return_routing:
+        idx = torch.empty(S, top_k, dtype=torch.int32, device=dev)
+        score = torch.empty(S, top_k, dtype=torch.float32, device=dev)
+        counts = torch.empty(E, dtype=torch.int32, device=dev)
+        mapping = torch.empty(S * top_k, dtype=torch.int32, device=dev)
+    a = _lib.LayerArgs(
+        x=_ptr(x), embed=_ptr(embed), residual=_ptr(residual), out=_ptr(out), x_len=_ptr(x_len),
+        Wr=_ptr(Wr), br=_ptr(br), W1=_ptr(experts.W1), b1=_ptr(experts.b1), W2=_ptr(experts.W2), b2=_ptr(experts.b2),
+        B=B, T=T, D=D, Demb=Demb, E=E, H=H, top_k=top_k, gate_mode=gate_mode, act_type=act_type,
+        dtype=dtype_code(x), keep_expert_output=int(keep_expert_output), ff_scale=float(ff_scale),
+        idx_out=_ptr(idx), score_out=_ptr(score), counts_out=_ptr(counts), mapping_out=_ptr(mapping))
+    lib = _lib.load()
+    import ctypes
+    _lib.check(lib.b200moe_forward(ctypes.byref(a), _ptr(ws), ws.numel(), _stream()), "b200moe_forward")
+    return LayerOut(out, idx, score, counts, mapping)

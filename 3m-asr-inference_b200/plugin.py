@@ -1,0 +1,153 @@
+"""Python mirror of the TensorRT plugin surface that builder.py / infer.py drive through network_helper:
+
+  FMoEExpertPluginDynamic   v1  TRTAPI++/plugin/fmoe_expert_plugin/fmoe_expert_plugin.{h,cpp}
+  SoftmaxTopKPluginDynamic  v1  TRTAPI++/plugin/softmax_topk_plugin/softmax_topk_plugin.cpp
+
+Same plugin names / versions, same creator field names (`data_type`, `num_expert`, `idim`, `hidden_units`, optional
+`act_type`), same six inputs in the same order, same single un-weighted output, same 32-byte serialisation
+(fmoe_expert_plugin.cpp:288-304).  TensorRT itself is absent from this image; INTEGRATION.md shows the
+IPluginV2DynamicExt shim a maintainer adds to register these under TensorRT.
+"""
+from __future__ import annotations
+
+import ctypes
+import struct
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, ops
+
+FMOE_EXPERT_NAME = "FMoEExpertPluginDynamic"
+FMOE_EXPERT_VERSION = "1"
+SOFTMAX_TOPK_NAME = "SoftmaxTopKPluginDynamic"
+SOFTMAX_TOPK_VERSION = "1"
+
+_TORCH_DTYPE = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}
+
+
+class FMoEExpertPlugin:
+    """Owns a b200moe_plugin handle. enqueue(inputs=[input, gate_idx, w1_w, w1_b, w2_w, w2_b]) -> output."""
+
+    def __init__(self, handle: int):
+        if not handle:
+            raise RuntimeError("plugin creation failed: " + (_lib.load().b200moe_last_error() or b"").decode())
+        self._h = handle
+        self._ws: Optional[torch.Tensor] = None
+
+    # -- IPluginV2 identity ------------------------------------------------------------------------------------------
+    def get_plugin_type(self) -> str:
+        return FMOE_EXPERT_NAME
+
+    def get_plugin_version(self) -> str:
+        return FMOE_EXPERT_VERSION
+
+    def get_nb_outputs(self) -> int:
+        return 1
+
+    # -- lifetime ----------------------------------------------------------------------------------------------------
+    def clone(self) -> "FMoEExpertPlugin":
+        return FMoEExpertPlugin(_lib.load().b200moe_plugin_clone(self._h))
+
+    def destroy(self) -> None:
+        if self._h:
+            _lib.load().b200moe_plugin_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # -- serialisation --------------------------------------------------------------------------------------------------
+    def get_serialization_size(self) -> int:
+        return int(_lib.load().b200moe_plugin_serialization_size(self._h))
+
+    def serialize(self) -> bytes:
+        buf = ctypes.create_string_buffer(self.get_serialization_size())
+        _lib.check(_lib.load().b200moe_plugin_serialize(self._h, buf), "b200moe_plugin_serialize")
+        return buf.raw
+
+    @property
+    def fields(self) -> Dict[str, int]:
+        v = struct.unpack("8i", self.serialize())
+        return {"data_type": v[0], "num_expert": v[1], "idim": v[2], "hidden_units": v[3], "act_type": v[4]}
+
+    # -- execution ------------------------------------------------------------------------------------------------------
+    def get_workspace_size(self, S: int) -> int:
+        return int(_lib.load().b200moe_plugin_workspace_bytes(self._h, S))
+
+    def enqueue(self, inputs, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x, gate_idx, w1w, w1b, w2w, w2b = inputs
+        f = self.fields
+        dt = _TORCH_DTYPE[f["data_type"]]
+        for t in (x, w1w, w1b, w2w, w2b):
+            if t.dtype != dt:
+                raise TypeError(f"plugin data_type is {dt}, got {t.dtype}")  # supportsFormatCombination
+            if not t.is_cuda or not t.is_contiguous():
+                raise RuntimeError("plugin inputs must be contiguous CUDA tensors")
+        if gate_idx.dtype != torch.int32:
+            raise TypeError("gate_idx must be int32")
+        S = x.numel() // f["idim"]
+        need = self.get_workspace_size(S)
+        if workspace is None:
+            if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            workspace = self._ws
+        out = torch.empty_like(x)
+        st = _lib.load().b200moe_plugin_enqueue(
+            self._h, x.data_ptr(), gate_idx.data_ptr(), w1w.data_ptr(), w1b.data_ptr(), w2w.data_ptr(),
+            w2b.data_ptr(), S, out.data_ptr(), workspace.data_ptr(), workspace.numel(),
+            torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "b200moe_plugin_enqueue")
+        return out
+
+
+class FMoEExpertPluginCreator:
+    """create_plugin(name, fields) with the reference's field names; returns None on a bad data_type like the
+    reference creator does (fmoe_expert_plugin.cpp:360-363)."""
+    name = FMOE_EXPERT_NAME
+    version = FMOE_EXPERT_VERSION
+    field_names = ("data_type", "num_expert", "idim", "hidden_units", "act_type")
+
+    def create_plugin(self, name: str, fields: Dict[str, int]) -> Optional[FMoEExpertPlugin]:
+        h = _lib.load().b200moe_plugin_create(int(fields.get("data_type", -1)), int(fields.get("num_expert", 0)),
+                                              int(fields.get("idim", 0)), int(fields.get("hidden_units", 0)),
+                                              int(fields.get("act_type", 0)))
+        return FMoEExpertPlugin(h) if h else None
+
+    def deserialize_plugin(self, name: str, data: bytes) -> Optional[FMoEExpertPlugin]:
+        h = _lib.load().b200moe_plugin_deserialize(data, len(data))
+        return FMoEExpertPlugin(h) if h else None
+
+
+class SoftmaxTopKPlugin:
+    """enqueue([logits [B,T,E], mask [B] int32]) -> (value [B,T,1], idx [B,T,1] int32); top-1 only."""
+
+    def __init__(self, data_type: int = 0):
+        if data_type not in _TORCH_DTYPE:
+            raise ValueError("invalid data_type")
+        self.data_type = data_type
+
+    def get_plugin_type(self) -> str:
+        return SOFTMAX_TOPK_NAME
+
+    def get_plugin_version(self) -> str:
+        return SOFTMAX_TOPK_VERSION
+
+    def enqueue(self, inputs):
+        logits, mask = inputs
+        return ops.softmax_topk(logits.contiguous(), None if mask is None else mask.reshape(-1).contiguous())
+
+
+class PluginRegistry:
+    """get_plugin_creator(name, version, namespace) as used at positionwise_feed_forward.py:182,233."""
+
+    def get_plugin_creator(self, name: str, version: str = "1", namespace: str = ""):
+        if (name, version, namespace) == (FMOE_EXPERT_NAME, FMOE_EXPERT_VERSION, ""):
+            return FMoEExpertPluginCreator()
+        if (name, version, namespace) == (SOFTMAX_TOPK_NAME, SOFTMAX_TOPK_VERSION, ""):
+            return type("SoftmaxTopKCreator", (), {
+                "create_plugin": staticmethod(lambda n, fields: SoftmaxTopKPlugin(int(fields.get("data_type", 0))))})()
+        return None

@@ -180,6 +180,12 @@ int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate
 int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int T, int E, int data_type,
                                  void* value, int* idx, cudaStream_t stream);
 
+/* Optional per-stage device timing with CUDA events around each stage of b200moe_forward (eager launches only, not
+ * under graph capture). stage_ms / stage_calls are HOST arrays of 4: 0 gate, 1 dispatch, 2 expert_ffn (with the fused
+ * combine epilogue when top_k == 1), 3 combine.  b200moe_profile_read waits for the recorded work and resets. */
+int b200moe_profile_enable(int on);
+int b200moe_profile_read(float* stage_ms, int* stage_calls);
+
 /* Number of kernels this library launched on behalf of the calling process (for bench accounting). */
 unsigned long long b200moe_launch_count(void);
 

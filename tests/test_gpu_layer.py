@@ -1,0 +1,203 @@
+"""GPU parity of the whole layer through b200moe_forward / the plugin enqueue / the module mirrors."""
+import pytest
+import torch
+
+from conftest import load_golden, pkg, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+BF16_REL_L2 = 1e-2   # north_star tolerance for BF16 outputs vs the fp32 reference
+
+
+def dev(t, dtype=None):
+    if t is None:
+        return None
+    t = t.cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def run_layer(ops, w, x, embed, *, dtype=torch.bfloat16, residual=True, x_len=None, T=None, **kw):
+    experts = ops.pack_experts(dev(w.W1), dev(w.b1), dev(w.W2), dev(w.b2))
+    xd, ed = dev(x, dtype), dev(embed, dtype)
+    return ops.moe_layer(xd, ed, dev(w.Wr), dev(w.br), experts, residual=xd if residual else None,
+                         x_len=dev(x_len), seq_len=T, return_routing=True, **kw)
+
+
+def check_against_oracle(oracle, res, ref, tol=BF16_REL_L2):
+    assert torch.equal(res.idx.cpu().long(), ref["idx"])                       # expert assignment: bit-exact
+    assert torch.equal(res.counts.cpu().long(), ref["counts"])                 # per-expert counts: bit-exact
+    assert torch.equal(res.mapping.cpu().long(), ref["mapping"].view(-1))      # scatter indices: bit-exact
+    torch.testing.assert_close(res.score.cpu(), ref["score"], rtol=2e-5, atol=1e-7)
+    out = res.out.float().cpu().view(ref["out"].shape)
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref["out"]) <= tol
+    return rel_l2(out, ref["out"])
+
+
+def test_golden_3m_top1(ops, oracle):
+    """The vectors produced by the reference's own Python (tests/golden/make_golden.py), through the CUDA path."""
+    g = load_golden("case_3m_top1.npz")
+
+    class W:
+        pass
+    w = W()
+    w.Wr, w.br, w.W1, w.b1, w.W2, w.b2 = g["Wr"], None, g["W1"], g["b1"], g["W2"], g["b2"]
+    res = run_layer(ops, w, g["x"], g["embed"], dtype=torch.float32, ff_scale=float(g["ff_scale"]))
+    assert torch.equal(res.idx.cpu().view(-1).long(), g["gate_idx"])
+    assert torch.equal(res.counts.cpu().long(), g["expert_count"])
+    torch.testing.assert_close(res.score.cpu().view(-1), g["gate_value"], rtol=2e-5, atol=1e-7)
+    assert rel_l2(res.out.cpu(), g["final"]) <= BF16_REL_L2
+    # the MoE contribution alone (residual removed), so the residual cannot mask an error
+    moe = (res.out.cpu() - g["x"]) / float(g["ff_scale"])
+    assert rel_l2(moe, g["weighted"]) <= 2 * BF16_REL_L2
+    # un-weighted, no residual == FMoEExpertPlugin's output
+    res2 = run_layer(ops, w, g["x"], g["embed"], dtype=torch.float32, residual=False, keep_expert_output=True)
+    assert rel_l2(res2.out.cpu(), g["expert_outputs"]) <= BF16_REL_L2
+
+
+def test_golden_naive_top2(ops, oracle):
+    g = load_golden("case_naive_top2.npz")
+
+    class W:
+        pass
+    w = W()
+    w.Wr, w.br, w.W1, w.b1, w.W2, w.b2 = g["Wr"], g["br"], g["W1"], g["b1"], g["W2"], g["b2"]
+    res = run_layer(ops, w, g["x"], None, dtype=torch.float32, residual=False, top_k=2, gate_mode=ops.GATE_NAIVE,
+                    act_type=ops.ACT_GELU)
+    assert torch.equal(torch.sort(res.idx.cpu().long(), 1).values, torch.sort(g["gate_idx"], 1).values)
+    assert torch.equal(res.counts.cpu().long(), g["expert_count"])
+    assert rel_l2(res.out.cpu(), g["out"]) <= BF16_REL_L2
+
+
+@pytest.mark.parametrize("S,dtype,random_bias", [
+    (50, torch.bfloat16, False),     # cfg1: batch 1 x 206 frames -> 50 tokens, reference init (zero biases)
+    (206, torch.bfloat16, True),     # cfg1, frames as tokens, biases exercised
+    (3200, torch.bfloat16, True),    # cfg3 per layer: batch 64 x 206 frames
+    (3200, torch.float32, True),     # fp32 activations at the boundary (the reference plugin's data_type 0)
+    (13184, torch.bfloat16, False),  # cfg3 with frames as tokens
+    (1, torch.bfloat16, True),
+])
+def test_layer_3m_repo_dims(ops, oracle, synth, S, dtype, random_bias):
+    E, D, H, Demb = 32, 512, 1024, 512
+    w = synth.make_weights(20260001, E, D, H, Demb, random_bias=random_bias)
+    x, embed = synth.make_activations(20260001 + S, S, D, Demb, w)
+    ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
+    res = run_layer(ops, w, x, embed, dtype=dtype, ff_scale=0.5)
+    err = check_against_oracle(oracle, res, ref)
+    # and the MoE term on its own
+    moe = (res.out.float().cpu() - x) / 0.5
+    assert rel_l2(moe, ref["moe"]) <= 3 * BF16_REL_L2, err
+
+
+def test_layer_padding_and_keep_output(ops, oracle, synth):
+    E, D, H, Demb, B, T = 32, 512, 1024, 512, 6, 60
+    w = synth.make_weights(31, E, D, H, Demb, random_bias=True)
+    x, embed = synth.make_activations(32, B * T, D, Demb, w)
+    x_len = torch.tensor([60, 33, 0, 1, 59, 24], dtype=torch.int32)
+    ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5, x_len=x_len, T=T,
+                             keep_expert_output=True)
+    res = run_layer(ops, w, x, embed, x_len=x_len, T=T, ff_scale=0.5, keep_expert_output=True)
+    check_against_oracle(oracle, res, ref)
+    pad = (torch.arange(B * T) % T) >= x_len.long().repeat_interleave(T)
+    assert torch.equal(res.out.float().cpu()[pad], x[pad])   # padded rows: output == residual, exactly
+
+
+@pytest.mark.parametrize("S,E,k,act", [(500, 32, 2, 2), (64, 8, 4, 1), (4000, 32, 2, 0)])
+def test_layer_naive_topk(ops, oracle, synth, S, E, k, act):
+    D, H = 512, 1024
+    w = synth.make_weights(41 + S, E, D, H, 0, router_bias=True, random_bias=True)
+    x, _ = synth.make_activations(42 + S, S, D, 0, w, top_k=k)
+    ref = oracle.moe_forward(x, None, w.Wr, w.br, w.W1, w.b1, w.W2, w.b2, top_k=k, gate_mode=oracle.GATE_NAIVE,
+                             act_type=act)
+    res = run_layer(ops, w, x, None, residual=False, top_k=k, gate_mode=ops.GATE_NAIVE, act_type=act)
+    check_against_oracle(oracle, res, ref)
+
+
+def test_layer_skewed_router(ops, oracle, synth):
+    """Zipf-like load through router_bias: a few experts take most tokens (several token tiles), many stay empty."""
+    E, D, H, Demb, S = 32, 512, 1024, 512, 6000
+    w = synth.make_weights(51, E, D, H, Demb, router_bias=True, random_bias=True)
+    w.br = (torch.arange(E, 0, -1).float() * 0.35).bfloat16().float()
+    x, embed = synth.make_activations(52, S, D, Demb, w)
+    ref = oracle.moe_forward(x, embed, w.Wr, w.br, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
+    assert int(ref["counts"].max()) > 1000 and int((ref["counts"] == 0).sum()) >= 1
+    res = run_layer(ops, w, x, embed, ff_scale=0.5)
+    check_against_oracle(oracle, res, ref)
+
+
+def test_layer_properties_at_large_size(ops, synth):
+    """cfg5-sized call (65 536 tokens) checked through size-independent properties: permuting the tokens permutes the
+    outputs bit-for-bit, counts sum to S, and doubling ff_scale doubles the MoE term."""
+    E, D, H, Demb, S = 32, 512, 1024, 512, 65536
+    w = synth.make_weights(61, E, D, H, Demb, random_bias=True)
+    g = torch.Generator().manual_seed(62)
+    x = torch.randn(S, D, generator=g).bfloat16()
+    embed = torch.randn(S, Demb, generator=g).bfloat16()
+    experts = ops.pack_experts(dev(w.W1), dev(w.b1), dev(w.W2), dev(w.b2))
+    Wr = dev(w.Wr)
+    xd, ed = x.cuda(), embed.cuda()
+    a = ops.moe_layer(xd, ed, Wr, None, experts, ff_scale=1.0, return_routing=True)
+    a_out, a_idx, a_counts = a.out.clone(), a.idx.clone(), a.counts.clone()
+    assert int(a_counts.sum()) == S
+    perm = torch.randperm(S, generator=g).cuda()
+    b = ops.moe_layer(xd[perm].contiguous(), ed[perm].contiguous(), Wr, None, experts, ff_scale=1.0,
+                      return_routing=True)
+    assert torch.equal(b.idx, a_idx[perm])
+    assert torch.equal(b.out, a_out[perm])
+    c = ops.moe_layer(xd, ed, Wr, None, experts, ff_scale=2.0)
+    torch.testing.assert_close(c.out.float(), 2.0 * a_out.float(), rtol=1e-2, atol=1e-3)
+    assert torch.isfinite(a_out.float()).all()
+
+
+def test_plugin_enqueue_matches_reference_contract(ops, oracle, synth):
+    """FMoEExpertPluginDynamic: six inputs, un-weighted output in token order (fmoe_expert_plugin.cpp:241-269)."""
+    plugin = pkg("plugin")
+    E, D, H, S = 32, 512, 1024, 206
+    w = synth.make_weights(71, E, D, H, 0, random_bias=True)
+    g = torch.Generator().manual_seed(72)
+    x = torch.randn(1, S, D, generator=g).bfloat16().float()
+    gate_idx = torch.randint(0, E, (1, S, 1), generator=g, dtype=torch.int32)
+    creator = plugin.PluginRegistry().get_plugin_creator("FMoEExpertPluginDynamic", "1", "")
+    p = creator.create_plugin("plugin", {"data_type": 0, "num_expert": E, "idim": D, "hidden_units": H})
+    out = p.enqueue([x.cuda(), gate_idx.cuda(), w.W1.cuda(), w.b1.cuda(), w.W2.cuda(), w.b2.cuda()])
+    assert out.shape == x.shape and out.dtype == torch.float32
+    prep = oracle.prepare(gate_idx.view(-1), E)
+    ybuf = oracle.expert_ffn(x.view(S, D)[prep["pos"]], prep["counts"], w.W1, w.b1, w.W2, w.b2, 0)
+    ref = ybuf[prep["mapping"]]
+    assert rel_l2(out.cpu().view(S, D), ref) <= BF16_REL_L2
+    # second enqueue re-uses the packed weights; a clone built from the serialised fields gives the same answer
+    out2 = p.enqueue([x.cuda(), gate_idx.cuda(), w.W1.cuda(), w.b1.cuda(), w.W2.cuda(), w.b2.cuda()])
+    q = creator.deserialize_plugin("plugin", p.serialize())
+    out3 = q.enqueue([x.cuda(), gate_idx.cuda(), w.W1.cuda(), w.b1.cuda(), w.W2.cuda(), w.b2.cuda()])
+    assert rel_l2(out2.cpu(), out.cpu()) < 1e-6 and torch.equal(out3, out2)
+
+
+def test_module_mirrors(ops, oracle, synth):
+    layer = pkg("layer")
+    fmoe = pkg("fmoe")
+    E, D, H, Demb, B, T = 32, 512, 1024, 512, 4, 50
+    w = synth.make_weights(81, E, D, H, Demb, random_bias=True)
+    x, embed = synth.make_activations(82, B * T, D, Demb, w)
+    m = layer.LocalFmoeCatEmbedFeedForward(D, Demb, num_experts=E, hidden_units=H, activation=layer.Swish())
+    m.load_state_dict({"router_weights": w.Wr, "experts.w_1.weight": w.W1, "experts.w_1.bias": w.b1,
+                       "experts.w_2.weight": w.W2, "experts.w_2.bias": w.b2})
+    m = m.cuda()
+    xin = x.view(B, T, D).cuda().bfloat16()
+    out = m(xin, embed.view(B, T, Demb).cuda().bfloat16(), None)
+    ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2)
+    assert rel_l2(out.float().cpu().view(B * T, D), ref["out"]) <= BF16_REL_L2
+    out_r = m(xin, embed.view(B, T, Demb).cuda().bfloat16(), None, residual=xin, ff_scale=0.5)
+    assert rel_l2(out_r.float().cpu().view(B * T, D), x + 0.5 * ref["out"]) <= BF16_REL_L2
+
+    w2 = synth.make_weights(83, 8, 256, 512, 0, router_bias=True, random_bias=True)
+    x2, _ = synth.make_activations(84, 300, 256, 0, w2, top_k=2)
+    mlp = fmoe.FMoETransformerMLP(num_expert=8, d_model=256, d_hidden=512, top_k=2)
+    mlp.load_state_dict({"gate.gate.weight": w2.Wr.t().contiguous(), "gate.gate.bias": w2.br,
+                         "experts.htoh4.weight": w2.W1, "experts.htoh4.bias": w2.b1,
+                         "experts.h4toh.weight": w2.W2, "experts.h4toh.bias": w2.b2})
+    mlp = mlp.cuda()
+    y = mlp(x2.view(3, 100, 256).cuda().bfloat16())
+    ref2 = oracle.moe_forward(x2, None, w2.Wr, w2.br, w2.W1, w2.b1, w2.W2, w2.b2, top_k=2,
+                              gate_mode=oracle.GATE_NAIVE, act_type=oracle.ACT_GELU)
+    assert tuple(y.shape) == (3, 100, 256)
+    assert rel_l2(y.float().cpu().view(300, 256), ref2["out"]) <= BF16_REL_L2
