@@ -73,7 +73,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -83,7 +83,7 @@ class ClockSampler(threading.Thread):
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                      0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 try:
                     r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -97,7 +97,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"sampler_error:{type(exc).__name__}")
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),

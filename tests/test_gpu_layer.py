@@ -83,10 +83,15 @@ def test_layer_3m_repo_dims(ops, oracle, synth, S, dtype, random_bias):
     x, embed = synth.make_activations(20260001 + S, S, D, Demb, w)
     ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
     res = run_layer(ops, w, x, embed, dtype=dtype, ff_scale=0.5)
-    err = check_against_oracle(oracle, res, ref)
-    # and the MoE term on its own
-    moe = (res.out.float().cpu() - x) / 0.5
-    assert rel_l2(moe, ref["moe"]) <= 3 * BF16_REL_L2, err
+    check_against_oracle(oracle, res, ref)
+    # The MoE term on its own (no residual), so the O(1) residual cannot mask an error in the O(1e-2) expert output.
+    # (With a bf16 residual stream the sum is rounded to 8 bits of mantissa, which is coarser than the MoE term for
+    # the reference's tiny xavier(gain=0.5) weights -- that is a property of bf16 storage, not of this kernel.)
+    res2 = run_layer(ops, w, x, embed, dtype=dtype, residual=False, ff_scale=0.5)
+    assert rel_l2(res2.out.float().cpu(), 0.5 * ref["moe"]) <= BF16_REL_L2
+    if dtype == torch.float32:
+        moe = (res.out.cpu() - x) / 0.5
+        assert rel_l2(moe, ref["moe"]) <= 2 * BF16_REL_L2
 
 
 def test_layer_padding_and_keep_output(ops, oracle, synth):
