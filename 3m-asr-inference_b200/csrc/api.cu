@@ -111,6 +111,11 @@ int b200moe_device_supported(int dev) {
   return major == 10 ? 1 : 0;
 }
 
+int b200moe_debug_ffn_trace(void* dev_buf, int records_per_cta) {
+  set_ffn_trace(dev_buf, records_per_cta);
+  return B200MOE_OK;
+}
+
 int b200moe_profile_enable(int on) {
   g_timer.enabled = on != 0;
   g_timer.used = 0;

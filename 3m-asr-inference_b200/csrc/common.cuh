@@ -124,6 +124,8 @@ struct FfnLaunch {
   int top_k;
 };
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
+// Debug timeline: every following ffn launch records per-CTA events into dev_buf (16 B records); null disables.
+void set_ffn_trace(void* dev_buf, int records_per_cta);
 
 // combine.cu
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,

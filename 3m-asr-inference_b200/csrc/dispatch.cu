@@ -135,23 +135,42 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   __shared__ int s_off[kMaxExperts + 1];      // global exclusive offsets
   __shared__ int s_scratch[kMaxExperts + 1];
   __shared__ int s_dst[kDispatchThreads];     // destination row of each entry of the current segment
+  constexpr int kMaxParts = 8;
+  __shared__ int s_part[kMaxParts * 2 * kMaxExperts];  // partial column sums (before / total) per part
   extern __shared__ int s_wcnt[];             // [kWarps][E] per-warp counts of the current segment
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // 1. column sums of the chunk histograms: totals and the part that precedes this chunk
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    int before = 0, total = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      const int v = chunk_hist[c * E + e];
-      if (c < static_cast<int>(blockIdx.x)) before += v;
-      total += v;
+  // 1. column sums of the chunk histograms: totals and the part that precedes this chunk.  All 256 threads take
+  //    part: thread (part, e) sums the chunks c = part, part + nparts, ... (independent loads, one latency), then
+  //    the partial sums are combined through shared memory.
+  {
+    const int nparts = max(1, min(kMaxParts, static_cast<int>(blockDim.x) / E));
+    const int e = threadIdx.x % E;
+    const int part = threadIdx.x / E;
+    if (part < nparts) {
+      int before = 0, total = 0;
+      for (int c = part; c < nchunks; c += nparts) {
+        const int v = chunk_hist[c * E + e];
+        if (c < static_cast<int>(blockIdx.x)) before += v;
+        total += v;
+      }
+      s_part[(part * 2) * kMaxExperts + e] = before;
+      s_part[(part * 2 + 1) * kMaxExperts + e] = total;
     }
-    s_cursor[e] = before;
-    s_total[e] = total;
+    for (int i = threadIdx.x; i < kWarps * E; i += blockDim.x) s_wcnt[i] = 0;
+    __syncthreads();
+    for (int ee = threadIdx.x; ee < E; ee += blockDim.x) {
+      int before = 0, total = 0;
+      for (int pt = 0; pt < nparts; ++pt) {
+        before += s_part[(pt * 2) * kMaxExperts + ee];
+        total += s_part[(pt * 2 + 1) * kMaxExperts + ee];
+      }
+      s_cursor[ee] = before;
+      s_total[ee] = total;
+    }
   }
-  for (int i = threadIdx.x; i < kWarps * E; i += blockDim.x) s_wcnt[i] = 0;
   __syncthreads();
   // 2. exclusive scan over experts (E <= 256: a serial scan by one thread is a few hundred cycles)
   if (threadIdx.x == 0) {

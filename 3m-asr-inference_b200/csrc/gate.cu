@@ -93,19 +93,27 @@ __device__ __forceinline__ void warp_select_store(float (&v)[NJ], int E, int top
   }
 }
 
+// 8 consecutive input elements as raw 128-bit words (1 word for 16-bit types, 2 for fp32) + conversion to fp32.
 template <typename InT>
-__device__ __forceinline__ void load8(const InT* __restrict__ p, float (&o)[8]);
+struct Raw8 {
+  static constexpr int kVec = sizeof(InT) == 4 ? 2 : 1;
+  uint4 v[kVec];
+  __device__ __forceinline__ void load(const InT* __restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+  }
+  __device__ __forceinline__ void to_f(float (&o)[8]) const;
+};
 template <>
-__device__ __forceinline__ void load8<float>(const float* __restrict__ p, float (&o)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+__device__ __forceinline__ void Raw8<float>::to_f(float (&o)[8]) const {
+  o[0] = __uint_as_float(v[0].x); o[1] = __uint_as_float(v[0].y);
+  o[2] = __uint_as_float(v[0].z); o[3] = __uint_as_float(v[0].w);
+  o[4] = __uint_as_float(v[1].x); o[5] = __uint_as_float(v[1].y);
+  o[6] = __uint_as_float(v[1].z); o[7] = __uint_as_float(v[1].w);
 }
 template <>
-__device__ __forceinline__ void load8<bf16>(const bf16* __restrict__ p, float (&o)[8]) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+__device__ __forceinline__ void Raw8<bf16>::to_f(float (&o)[8]) const {
+  const uint32_t w[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     o[2 * i] = __uint_as_float(w[i] << 16);
@@ -113,15 +121,23 @@ __device__ __forceinline__ void load8<bf16>(const bf16* __restrict__ p, float (&
   }
 }
 template <>
-__device__ __forceinline__ void load8<__half>(const __half* __restrict__ p, float (&o)[8]) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
+__device__ __forceinline__ void Raw8<__half>::to_f(float (&o)[8]) const {
+  const __half2* h = reinterpret_cast<const __half2*>(&v[0]);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 f = __half22float2(h[i]);
     o[2 * i] = f.x;
     o[2 * i + 1] = f.y;
   }
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- fast path ---------------------------------------------------------------------------------------------------
@@ -133,12 +149,23 @@ gate_smem_kernel(const InT* __restrict__ x, const InT* __restrict__ embed, const
   extern __shared__ __align__(16) float s_w[];  // [Rpad][32] fp32, 16-byte chunks XOR-swizzled by (k >> 3) & 7
   const int R = D + Demb;
   const int Rpad = (R + 127) / 128 * 128;
-  for (int i = threadIdx.x; i < Rpad * 32; i += kGateThreads) {
-    const int k = i >> 5;
-    const int e = i & 31;
-    const float val = (k < R && e < E) ? Wr[static_cast<size_t>(k) * E + e] : 0.0f;
-    const int pc = (e >> 2) ^ ((k >> 3) & 7);
-    s_w[k * 32 + pc * 4 + (e & 3)] = val;
+  if (E == 32) {
+    // rows are exactly 128 B: asynchronous 16-byte copies straight into the swizzled position (one latency in total)
+    for (int i = threadIdx.x; i < R * 8; i += kGateThreads) {
+      const int k = i >> 3;
+      const int c = i & 7;
+      cp_async_16(s_w + k * 32 + ((c ^ ((k >> 3) & 7)) << 2), Wr + static_cast<size_t>(k) * 32 + c * 4);
+    }
+    for (int i = R * 32 + threadIdx.x; i < Rpad * 32; i += kGateThreads) s_w[i] = 0.0f;
+    cp_async_wait_all();
+  } else {
+    for (int i = threadIdx.x; i < Rpad * 32; i += kGateThreads) {
+      const int k = i >> 5;
+      const int e = i & 31;
+      const float val = (k < R && e < E) ? Wr[static_cast<size_t>(k) * E + e] : 0.0f;
+      const int pc = (e >> 2) ^ ((k >> 3) & 7);
+      s_w[k * 32 + pc * 4 + (e & 3)] = val;
+    }
   }
   __syncthreads();
 
@@ -148,6 +175,10 @@ gate_smem_kernel(const InT* __restrict__ x, const InT* __restrict__ embed, const
   const int ks = lane >> 1;   // k-slot: 8 consecutive k per 128-wide iteration
   const int swz = ks & 7;
   const int n_tasks = (S + kTok - 1) / kTok;
+  const int nkb = Rpad / 128;
+  // register ring of prefetched activations: kPf iterations of 8 k per token are in flight at any time
+  constexpr int kVec = Raw8<InT>::kVec;
+  constexpr int kPf = (kTok * kVec >= 4) ? 2 : (kTok * kVec == 2 ? 4 : 8);
 
   for (int task = blockIdx.x * kGateWarps + warp; task < n_tasks; task += gridDim.x * kGateWarps) {
     const int t0 = task * kTok;
@@ -157,30 +188,51 @@ gate_smem_kernel(const InT* __restrict__ x, const InT* __restrict__ embed, const
 #pragma unroll
       for (int e = 0; e < 16; ++e) acc[t][e] = 0.0f;
 
-    for (int kb = 0; kb < Rpad; kb += 128) {
-      const int k0 = kb + ks * 8;
+    Raw8<InT> ring[kPf][kTok];
+    auto fetch = [&](Raw8<InT>(&dst)[kTok], int kb) {
+      const int k0 = kb * 128 + ks * 8;
       if (k0 < R) {
-        float xv[kTok][8];
 #pragma unroll
         for (int t = 0; t < kTok; ++t) {
           const int tok = min(t0 + t, S - 1);
           const InT* src = (k0 < Demb) ? embed + static_cast<size_t>(tok) * Demb + k0
                                        : x + static_cast<size_t>(tok) * D + (k0 - Demb);
-          load8<InT>(src, xv[t]);
+          dst[t].load(src);
         }
+      }
+    };
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4* row = reinterpret_cast<const float4*>(s_w + (k0 + j) * 32);
-          float w[16];
+    for (int s = 0; s < kPf; ++s)
+      if (s < nkb) fetch(ring[s], s);
+
+    for (int kb0 = 0; kb0 < nkb; kb0 += kPf) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 q = row[(hsel * 4 + c) ^ swz];
-            w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
+      for (int s = 0; s < kPf; ++s) {
+        const int kb = kb0 + s;
+        if (kb < nkb) {
+          const int k0 = kb * 128 + ks * 8;
+          float xv[kTok][8];
+          if (k0 < R) {
+#pragma unroll
+            for (int t = 0; t < kTok; ++t) ring[s][t].to_f(xv[t]);
           }
+          if (kb + kPf < nkb) fetch(ring[s], kb + kPf);
+          if (k0 < R) {
 #pragma unroll
-          for (int t = 0; t < kTok; ++t)
+            for (int j = 0; j < 8; ++j) {
+              const float4* row = reinterpret_cast<const float4*>(s_w + (k0 + j) * 32);
+              float w[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[t][e] = fmaf(xv[t][j], w[e], acc[t][e]);
+              for (int c = 0; c < 4; ++c) {
+                const float4 q = row[(hsel * 4 + c) ^ swz];
+                w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
+              }
+#pragma unroll
+              for (int t = 0; t < kTok; ++t)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[t][e] = fmaf(xv[t][j], w[e], acc[t][e]);
+            }
+          }
         }
       }
     }

@@ -89,6 +89,40 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Predicated global accesses as single straight-line instructions. With a C++ `if` around a store the compiler sinks
+// the whole computation of the stored value into the branch, one basic block per column, and the columns'
+// dependency chains can no longer interleave; a predicated instruction keeps the code branch-free.
+__device__ __forceinline__ void st_global_pred_b16(void* p, uint16_t v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b16 [%0], %1;\n\t}"
+      :
+      : "l"(p), "h"(v), "r"(static_cast<int>(pred))
+      : "memory");
+}
+__device__ __forceinline__ void st_global_pred_b32(void* p, uint32_t v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
+      :
+      : "l"(p), "r"(v), "r"(static_cast<int>(pred))
+      : "memory");
+}
+__device__ __forceinline__ uint16_t ld_global_pred_b16(const void* p, bool pred) {
+  uint16_t v;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.b16 %0, 0;\n\t@p ld.global.b16 %0, [%1];\n\t}"
+      : "=h"(v)
+      : "l"(p), "r"(static_cast<int>(pred)));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_global_pred_b32(const void* p, bool pred) {
+  uint32_t v;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.b32 %0, [%1];\n\t}"
+      : "=r"(v)
+      : "l"(p), "r"(static_cast<int>(pred)));
+  return v;
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

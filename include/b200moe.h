@@ -186,6 +186,11 @@ int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int
 int b200moe_profile_enable(int on);
 int b200moe_profile_read(float* stage_ms, int* stage_calls);
 
+/* Debug: while dev_buf is non-NULL every expert-FFN launch runs its tracing variant and writes a per-CTA timeline of
+ * 16-byte records {tile, event, globaltimer lo, hi}: 3 roles (TMA producer, MMA issuer, epilogue) x records_per_cta/3
+ * slots per CTA, CTA-major.  dev_buf must hold 148 * records_per_cta records.  See tools/ffn_trace.py. */
+int b200moe_debug_ffn_trace(void* dev_buf, int records_per_cta);
+
 /* Number of kernels this library launched on behalf of the calling process (for bench accounting). */
 unsigned long long b200moe_launch_count(void);
 

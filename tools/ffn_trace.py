@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Runs one fast_moe layer with the FFN kernel's debug tracer on and prints per-CTA timelines (GPU box only).
+
+usage: python tools/ffn_trace.py [S] [n_cta_to_print]     -> text on stdout, raw records in gpurun_out/ffn_trace_S.npy
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "3m-asr-inference_b200"
+EV = ["kernel_start", "prod_tile_start", "prod_dep_ok", "prod_issued", "mma_acc_free", "mma_first_data", "mma_issued",
+      "epi_acc_ready", "epi_acc_released", "epi_stored", "epi_published", "kernel_end"]
+
+
+def main():
+    S = int(sys.argv[1]) if len(sys.argv) > 1 else 3200
+    n_print = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    ops = importlib.import_module(PKG + ".ops")
+    lib = importlib.import_module(PKG + "._lib").load()
+    E, D, H, Demb = 32, 512, 1024, 512
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(1)
+    layers = []
+    for _ in range(4):  # cycle 4 weight sets so that weights are not L2 resident
+        W1 = ((torch.rand(E, H, D, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
+        W2 = ((torch.rand(E, D, H, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
+        Wr = ((torch.rand(Demb + D, E, generator=g, device=dev) * 2 - 1) * 0.04)
+        layers.append((Wr, ops.PackedExperts(W1, torch.zeros(E, H, device=dev), W2, torch.zeros(E, D, device=dev))))
+    x = torch.randn(S, D, generator=g, device=dev).bfloat16()
+    emb = torch.randn(S, Demb, generator=g, device=dev).bfloat16()
+    out = torch.empty_like(x)
+    for _ in range(3):
+        for Wr, ex in layers:
+            ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out)
+    torch.cuda.synchronize()
+    cap = 96  # records per CTA (3 roles x 32)
+    n_cta = 148
+    buf = torch.zeros(n_cta * cap, 4, dtype=torch.int32, device=dev)
+    lib.b200moe_debug_ffn_trace(buf.data_ptr(), cap)
+    Wr, ex = layers[0]
+    ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out)
+    torch.cuda.synchronize()
+    lib.b200moe_debug_ffn_trace(None, 0)
+    rec = buf.cpu().numpy().astype(np.int64).reshape(n_cta, 3, cap // 3, 4)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    np.save(os.path.join(ROOT, "gpurun_out", f"ffn_trace_{S}.npy"), rec)
+    t = (rec[..., 2] & 0xFFFFFFFF) | (rec[..., 3] << 32)
+    valid = t > 0
+    t0 = t[valid].min()
+    print(f"S={S}: kernel span {(t[valid].max() - t0) / 1e3:.2f} us over {int(valid.sum())} records")
+    # per-event statistics relative to kernel start
+    for ev in range(len(EV)):
+        m = valid & (rec[..., 1] == ev)
+        if m.any():
+            tt = (t[m] - t0) / 1e3
+            print(f"  {EV[ev]:18s} n={int(m.sum()):5d} first={tt.min():8.2f} median={np.median(tt):8.2f} last={tt.max():8.2f} us")
+    ctas = list(range(0, n_cta, max(1, n_cta // n_print)))[:n_print]
+    for c in ctas:
+        rows = []
+        for role in range(3):
+            for i in range(cap // 3):
+                if t[c, role, i] > 0:
+                    rows.append(((t[c, role, i] - t0) / 1e3, role, int(rec[c, role, i, 0]), int(rec[c, role, i, 1])))
+        rows.sort()
+        print(f"--- CTA {c}")
+        for ts, role, tile, ev in rows:
+            print(f"   {ts:8.2f} us  {'PME'[role]}  tile {tile:4d}  {EV[ev]}")
+
+
+if __name__ == "__main__":
+    main()
