@@ -22,7 +22,7 @@ class LayerArgs(C.Structure):
     """struct b200moe_layer_args"""
     _fields_ = [
         ("x", _vp), ("embed", _vp), ("residual", _vp), ("out", _vp), ("x_len", _vp),
-        ("Wr", _vp), ("br", _vp),
+        ("Wr", _vp), ("Wr_packed", _vp), ("br", _vp),
         ("W1", _vp), ("b1", _vp), ("W2", _vp), ("b2", _vp),
         ("B", _i), ("T", _i), ("D", _i), ("Demb", _i), ("E", _i), ("H", _i), ("top_k", _i),
         ("gate_mode", _i), ("act_type", _i), ("dtype", _i),
@@ -43,6 +43,9 @@ SIGNATURES = {
     "b200moe_pack_bf16": (_i, [_vp, _i, _vp, _sz, _vp]),
     "b200moe_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "b200moe_gate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b200moe_router_pack_bytes": (_sz, [_i]),
+    "b200moe_pack_router": (_i, [_vp, _i, _i, _vp, _vp]),
+    "b200moe_gate_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200moe_dispatch": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200moe_expert_ffn": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200moe_combine": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]),

@@ -172,6 +172,33 @@ int b200moe_gate(const void* x, const void* embed, const float* Wr, const float*
   return B200MOE_OK;
 }
 
+size_t b200moe_router_pack_bytes(int R) { return R > 0 ? router_pack_bytes(R) : 0; }
+
+int b200moe_pack_router(const float* Wr, int R, int E, void* packed, cudaStream_t stream) {
+  if (!Wr || !packed) return fail(B200MOE_ERR_ARG, "pack_router: null pointer");
+  if (E < 1 || E > 32 || R < 1) return fail(B200MOE_ERR_ARG, "pack_router: needs 1 <= E <= 32 (got E=%d, R=%d)", E, R);
+  cudaError_t e = launch_pack_router(Wr, R, E, packed, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pack_router");
+  return B200MOE_OK;
+}
+
+int b200moe_gate_tc(const void* x, const void* embed, const void* Wr_packed, const float* br, const int* x_len, int B,
+                    int T, int D, int Demb, int E, int top_k, int gate_mode, int* idx, float* score,
+                    cudaStream_t stream) {
+  if (B < 0 || T < 0 || D < 1) return fail(B200MOE_ERR_ARG, "gate_tc: bad shape");
+  if (B * T > 0 && (!x || !Wr_packed || !idx || !score)) return fail(B200MOE_ERR_ARG, "gate_tc: null pointer");
+  if (gate_mode != B200MOE_GATE_3M && gate_mode != B200MOE_GATE_NAIVE)
+    return fail(B200MOE_ERR_ARG, "gate_tc: bad gate_mode %d", gate_mode);
+  if (top_k < 1 || top_k > 8 || top_k > E) return fail(B200MOE_ERR_ARG, "gate_tc: top_k=%d unsupported", top_k);
+  if (gate_mode == B200MOE_GATE_3M && top_k != 1) return fail(B200MOE_ERR_ARG, "gate_tc: the 3M router is top-1");
+  if (!gate_tc_supported(D, embed ? Demb : 0, E, top_k, B200MOE_BF16))
+    return fail(B200MOE_ERR_ARG, "gate_tc: needs bf16 activations, E <= 32, D and Demb multiples of 64");
+  cudaError_t e = launch_gate_tc(x, embed, Wr_packed, br, x_len, B, T, D, embed ? Demb : 0, E, top_k, gate_mode, idx,
+                                 score, nullptr, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "gate_tc");
+  return B200MOE_OK;
+}
+
 int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int T, int E, int data_type, void* value,
                                  int* idx, cudaStream_t stream) {
   if (B * T > 0 && (!logits || !value || !idx)) return fail(B200MOE_ERR_ARG, "softmax_topk: null pointer");
@@ -192,7 +219,7 @@ int b200moe_dispatch(const void* x, const int* idx, int S, int D, int E, int top
   if (!ws || (S > 0 && (!x || !idx || !xbuf))) return fail(B200MOE_ERR_ARG, "dispatch: null pointer");
   RouteWs w = carve_workspace(ws, S, E, D, 0, top_k);
   cudaError_t e = launch_dispatch(x, idx, nullptr, S, D, E, top_k, dtype, choose_bn(S * top_k, E), w, counts, offsets,
-                                  mapping, static_cast<bf16*>(xbuf), nullptr, nullptr, stream);
+                                  mapping, static_cast<bf16*>(xbuf), nullptr, nullptr, nullptr, stream);
   if (e != cudaSuccess) return cuda_fail(e, "dispatch");
   return B200MOE_OK;
 }
@@ -265,7 +292,10 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
     return fail(B200MOE_ERR_ARG, "forward: the 3M router is top-1 (got top_k=%d)", a->top_k);
   if (a->act_type < 0 || a->act_type > 2) return fail(B200MOE_ERR_ARG, "forward: bad act_type %d", a->act_type);
   if (S == 0) return B200MOE_OK;
-  if (!a->x || !a->out || !a->Wr || !a->W1 || !a->W2 || !ws) return fail(B200MOE_ERR_ARG, "forward: null pointer");
+  if (!a->x || !a->out || (!a->Wr && !a->Wr_packed) || !a->W1 || !a->W2 || !ws)
+    return fail(B200MOE_ERR_ARG, "forward: null pointer");
+  if (!a->Wr && !gate_tc_supported(a->D, a->embed ? a->Demb : 0, a->E, a->top_k, a->dtype))
+    return fail(B200MOE_ERR_ARG, "forward: this shape/dtype needs the fp32 router (Wr), the packed one is not enough");
   const int Demb = a->embed ? a->Demb : 0;
   RouteWs w = carve_workspace(ws, S, a->E, a->D, a->H, a->top_k);
   if (ws_bytes < w.bytes)
@@ -275,10 +305,15 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   float* score = a->score_out ? a->score_out : w.score;
 
   cudaError_t e;
+  const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
   {
     StageScope t(0, stream);
-    e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k, a->gate_mode,
-                    a->dtype, idx, score, stream);
+    if (tc_gate)
+      e = launch_gate_tc(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
+                         a->gate_mode, idx, score, w.hist32, stream);
+    else
+      e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k, a->gate_mode,
+                      a->dtype, idx, score, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, "forward/gate");
 
@@ -289,7 +324,7 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
     StageScope t(1, stream);
     e = launch_dispatch(a->x, idx, a->keep_expert_output ? nullptr : score, S, a->D, a->E, a->top_k, a->dtype, bn, w,
                         a->counts_out, nullptr, a->mapping_out, w.xbuf, fused ? a->out : nullptr, a->residual,
-                        stream);
+                        tc_gate ? w.hist32 : nullptr, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, "forward/dispatch");
 
@@ -454,7 +489,7 @@ int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate
   const int bn = choose_bn(S, E);
   const int gmax = max_groups(S, E, bn);
   cudaError_t e = launch_dispatch(input, gate_idx, nullptr, S, D, E, 1, p->data_type, bn, w, nullptr, nullptr, nullptr,
-                                  w.xbuf, output, nullptr, stream);
+                                  w.xbuf, output, nullptr, nullptr, stream);
   if (e != cudaSuccess) return cuda_fail(e, "enqueue/dispatch");
   FfnLaunch f{};
   f.xbuf = w.xbuf;

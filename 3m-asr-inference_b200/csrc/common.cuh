@@ -27,7 +27,8 @@ struct GroupRec {
 
 // Device-side routing state produced by dispatch and consumed by the FFN kernel. Lives in the workspace.
 struct RouteWs {
-  int* chunk_hist;   // [kMaxChunks, E]
+  int* chunk_hist;   // [kMaxChunks, E] per-dispatch-chunk expert counts (count kernel)
+  int* hist32;       // [ceil(S/32), E] per-32-token expert counts (tensor-core gate)
   int* counts;       // [E]
   int* offsets;      // [E + 1]
   int* mapping;      // [Sk]   entry -> expert-order row (-1 = dropped)
@@ -60,6 +61,7 @@ inline RouteWs carve_workspace(void* base, int S, int E, int D, int H, int top_k
     return base ? static_cast<char*>(base) + o : static_cast<char*>(nullptr);
   };
   w.chunk_hist = reinterpret_cast<int*>(take(sizeof(int) * kMaxChunks * E));
+  w.hist32 = reinterpret_cast<int*>(take(sizeof(int) * ((static_cast<size_t>(S) + 31) / 32) * E));
   w.counts = reinterpret_cast<int*>(take(sizeof(int) * E));
   w.offsets = reinterpret_cast<int*>(take(sizeof(int) * (E + 1)));
   w.mapping = reinterpret_cast<int*>(take(sizeof(int) * Sk));
@@ -83,6 +85,13 @@ inline RouteWs carve_workspace(void* base, int S, int E, int D, int H, int top_k
 cudaError_t launch_gate(const void* x, const void* embed, const float* Wr, const float* br, const int* x_len, int B,
                         int T, int D, int Demb, int E, int top_k, int gate_mode, int dtype, int* idx, float* score,
                         cudaStream_t stream);
+// gate_tc.cu: tensor-core gate for bf16 activations and E <= 32 (router packed by launch_pack_router)
+bool gate_tc_supported(int D, int Demb, int E, int top_k, int dtype);
+size_t router_pack_bytes(int R);
+cudaError_t launch_pack_router(const float* Wr, int R, int E, void* packed, cudaStream_t stream);
+cudaError_t launch_gate_tc(const void* x, const void* embed, const void* wr_packed, const float* br, const int* x_len,
+                           int B, int T, int D, int Demb, int E, int top_k, int gate_mode, int* idx, float* score,
+                           int* hist32, cudaStream_t stream);
 cudaError_t launch_softmax_topk(const void* logits, const int* mask, int B, int T, int E, int dtype, void* value,
                                 int* idx, cudaStream_t stream);
 
@@ -91,10 +100,12 @@ cudaError_t launch_softmax_topk(const void* logits, const int* mask, int B, int 
 // drop_out (optional, `dtype`, [S, D], top_k == 1 only): rows of dropped tokens (idx < 0) are written here as
 // drop_residual[row] (or zeros), so that a fused FFN epilogue -- which only touches routed tokens -- leaves a
 // fully defined output.
+// hist32 (optional): per-32-token expert counts already produced by the tensor-core gate; the count kernel is skipped.
 cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
-                            cudaStream_t stream);
+                            const int* hist32, cudaStream_t stream);
+constexpr int kMaxHistRows = 512;  // above this many 32-token rows the scatter CTAs would re-read too much
 // Builds only the group table (+ zeroes the flags) from an existing offsets array.
 cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
                                 int gmax, cudaStream_t stream);

@@ -16,19 +16,22 @@ namespace b200moe {
 namespace {
 
 struct Chunking {
-  int chunk;    // entries per CTA (multiple of 32)
-  int nchunks;  // grid size (<= kMaxChunks)
+  int chunk_tok;  // tokens per CTA (multiple of 32)
+  int chunk;      // entries per CTA = chunk_tok * top_k
+  int nchunks;    // grid size (<= kMaxChunks)
 };
 
-Chunking make_chunking(int Sk) {
-  // ~2 CTAs per SM; a CTA's chunk is a multiple of 32 entries so that small batches still spread over many SMs
-  // (the row copy is latency bound: 3 200 tokens -> 100 CTAs x 32 rows, 4 rows per warp in flight at once).
+Chunking make_chunking(int S, int top_k) {
+  // ~2 CTAs per SM; a CTA's chunk is a multiple of 32 tokens so that small batches still spread over many SMs
+  // (the row copy is latency bound: 3 200 tokens -> 100 CTAs x 32 rows, 4 rows per warp in flight at once) and so
+  // that chunk boundaries coincide with the 32-token histogram rows the tensor-core gate emits.
   Chunking c;
-  int chunk = (Sk + 295) / 296;
+  int chunk = (S + 295) / 296;
   chunk = (chunk + 31) / 32 * 32;
   if (chunk < 32) chunk = 32;
-  c.chunk = chunk;
-  c.nchunks = (Sk + chunk - 1) / chunk;
+  c.chunk_tok = chunk;
+  c.chunk = chunk * top_k;
+  c.nchunks = (S + chunk - 1) / chunk;
   if (c.nchunks < 1) c.nchunks = 1;
   return c;
 }
@@ -123,7 +126,7 @@ template <typename InT>
 __global__ void __launch_bounds__(kDispatchThreads)
 dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, const float* __restrict__ score,
                         int Sk, int D, int E, int top_k, int chunk, int nchunks,
-                        const int* __restrict__ chunk_hist, int bn, int gmax, int* __restrict__ counts,
+                        const int* __restrict__ chunk_hist, int hist_rows, int rows_per_chunk, int bn, int gmax, int* __restrict__ counts,
                         int* __restrict__ offsets, int* __restrict__ mapping, int* __restrict__ pos,
                         float* __restrict__ row_score, bf16* __restrict__ xbuf, GroupRec* groups, int* n_groups,
                         int* h_ready, int* counts_out, int* offsets_out, int* mapping_out, InT* __restrict__ drop_out,
@@ -151,9 +154,11 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
     const int part = threadIdx.x / E;
     if (part < nparts) {
       int before = 0, total = 0;
-      for (int c = part; c < nchunks; c += nparts) {
+      // histogram rows are per dispatch chunk (count kernel) or per 32 tokens (tensor-core gate)
+      const int my_first_row = static_cast<int>(blockIdx.x) * rows_per_chunk;
+      for (int c = part; c < hist_rows; c += nparts) {
         const int v = chunk_hist[c * E + e];
-        if (c < static_cast<int>(blockIdx.x)) before += v;
+        if (c < my_first_row) before += v;
         total += v;
       }
       s_part[(part * 2) * kMaxExperts + e] = before;
@@ -297,7 +302,7 @@ int choose_bn(int Sk, int E) {
 cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
-                            cudaStream_t stream) {
+                            const int* hist32, cudaStream_t stream) {
   const int Sk = S * top_k;
   if (top_k != 1) drop_out = nullptr;
   if (E > kMaxExperts || E < 1 || D % 8 != 0) return cudaErrorInvalidValue;
@@ -312,15 +317,26 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
     if (offsets_out) cudaMemsetAsync(offsets_out, 0, sizeof(int) * (E + 1), stream);
     return cudaMemsetAsync(ws.n_groups, 0, sizeof(int), stream);
   }
-  const Chunking ck = make_chunking(Sk);
-  dispatch_count_kernel<<<ck.nchunks, kDispatchThreads, 0, stream>>>(idx, Sk, E, ck.chunk, ws.chunk_hist);
-  count_launch();
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return err;
+  const Chunking ck = make_chunking(S, top_k);
+  const int rows32 = (S + 31) / 32;
+  const int* hist = ws.chunk_hist;
+  int hist_rows = ck.nchunks;
+  int rows_per_chunk = 1;
+  if (hist32 != nullptr && rows32 <= kMaxHistRows) {
+    hist = hist32;  // counts came with the gate: no count kernel
+    hist_rows = rows32;
+    rows_per_chunk = ck.chunk_tok / 32;
+  } else {
+    dispatch_count_kernel<<<ck.nchunks, kDispatchThreads, 0, stream>>>(idx, Sk, E, ck.chunk, ws.chunk_hist);
+    count_launch();
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+  }
   const size_t dyn = sizeof(int) * (kDispatchThreads / 32) * E;
 #define B200MOE_SCATTER(T)                                                                                        \
   dispatch_scatter_kernel<T><<<ck.nchunks, kDispatchThreads, dyn, stream>>>(                                      \
-      static_cast<const T*>(x), idx, score, Sk, D, E, top_k, ck.chunk, ck.nchunks, ws.chunk_hist, bn, gmax,       \
+      static_cast<const T*>(x), idx, score, Sk, D, E, top_k, ck.chunk, ck.nchunks, hist, hist_rows,               \
+      rows_per_chunk, bn, gmax,                                                                                   \
       ws.counts, ws.offsets, ws.mapping, ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready,          \
       counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual))
   switch (dtype) {

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma_host.cuh"
 
 namespace b200moe {
 
@@ -523,38 +524,6 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
 // ------------------------------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-  });
-  return fn;
-}
-
-// 2-D bf16 row-major tensor [rows, cols]; box = [box_rows, 64 cols] with 128 B swizzle.
-bool make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return false;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * sizeof(bf16)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 void* g_trace_buf = nullptr;
 int g_trace_cap = 0;
 
@@ -566,17 +535,6 @@ int stages_for_bn(int bn) {
 size_t smem_bytes_for(int bn, int stages) {
   return 1024 + static_cast<size_t>(stages) * (kAStageBytes + bn * kBlockK * 2) + 8 * (2 * kMaxStages + 4) + 32 +
          kStagingBytes + 2 * 256 * 4;
-}
-
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
 }
 
 template <typename OutT>
@@ -618,9 +576,10 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   if (a.bn % 16 != 0 || a.bn < 16 || a.bn > 256) return cudaErrorInvalidValue;
   if (a.fused && a.top_k != 1) return cudaErrorInvalidValue;
   CUtensorMap tw1, tw2, tx, th;
-  if (!make_tmap_bf16(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM) ||
-      !make_tmap_bf16(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM) ||
-      !make_tmap_bf16(&tx, a.xbuf, a.n_rows, a.D, a.bn) || !make_tmap_bf16(&th, a.hbuf, a.n_rows, a.H, a.bn)) {
+  if (!make_tmap_bf16(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kBlockK) ||
+      !make_tmap_bf16(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM, kBlockK) ||
+      !make_tmap_bf16(&tx, a.xbuf, a.n_rows, a.D, a.bn, kBlockK) ||
+      !make_tmap_bf16(&th, a.hbuf, a.n_rows, a.H, a.bn, kBlockK)) {
     return cudaErrorInvalidValue;
   }
   FfnParams p;

@@ -1,0 +1,316 @@
+// Tensor-core gate (bf16 activations, E <= 32): router GEMM on tcgen05 + softmax / top-k + per-32-token histograms.
+//
+// Same reference behaviour as gate.cu (router MatMul + SoftmaxTopKPluginDynamic, NaiveGate); this kernel exists because
+// the SIMT version is FMA-bound at ~1/3 of the HBM roofline (32 FMAs per loaded activation element), while the router
+// GEMM [tokens, R] x [R, E] is a perfectly ordinary tensor-core problem:
+//   * A = activations, 128 tokens x 64 k per stage, TMA-loaded straight from `embed` (k < Demb) and `x` (k >= Demb):
+//     the reference's concat (positionwise_feed_forward.py:225) costs nothing;
+//   * B = the router matrix packed once as bf16 K-major [2*32, R]: rows 0..31 hold hi = bf16(Wr^T), rows 32..63 hold
+//     lo = bf16(Wr^T - hi).  bf16 x bf16 products are exact in the fp32 accumulator, so logits = acc_hi + acc_lo carry
+//     the fp32 router weights to ~2^-17 relative -- the arg-max agrees with an fp32/fp64 oracle whenever the top-1/2
+//     margin exceeds that, exactly like the SIMT kernel;
+//   * D = [128 tokens (TMEM lanes), 64 columns] fp32 in TMEM, double buffered; one epilogue thread per token reads its
+//     64 columns and does softmax / arg-max / top-k entirely in registers (no shuffles, no shared memory);
+//   * each epilogue warp (32 consecutive tokens) also emits the expert histogram of its tokens, which is what the
+//     dispatch kernel needs as per-chunk counts -- the separate count kernel disappears.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace b200moe {
+
+namespace {
+
+constexpr int kTokTile = 128;   // tokens per tile == UMMA M
+constexpr int kBlkK = 64;
+constexpr int kNCols = 64;      // UMMA N: 32 hi + 32 lo expert columns
+constexpr int kStagesG = 8;
+constexpr int kAStage = kTokTile * kBlkK * 2;  // 16 KiB
+constexpr int kBStage = kNCols * kBlkK * 2;    // 8 KiB
+constexpr int kThreadsG = 256;
+constexpr uint32_t kTmemColsG = 128;
+
+struct GateTcParams {
+  const float* br;
+  const int* x_len;
+  int* idx;
+  float* score;
+  int* hist32;  // [ceil(S/32), E] per-32-token expert counts, or null
+  int S, T, D, Demb, E, top_k, gate_mode;
+};
+
+__global__ void __launch_bounds__(kThreadsG, 1)
+gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_e,
+               const __grid_constant__ CUtensorMap tm_w, const GateTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + kStagesG * kAStage;
+  const uint32_t bar_base = smem_b + kStagesG * kBStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStagesG + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStagesG + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStagesG + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStagesG + 4);
+  const uint32_t misc_off = tmem_slot + 16u - ptx::smem_u32(smem_raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + misc_off - 16u);
+  float* s_br = reinterpret_cast<float*>(smem_raw + misc_off);            // [32]
+  int* s_hist = reinterpret_cast<int*>(smem_raw + misc_off + 32 * 4);     // [4][32]
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_x);
+    ptx::prefetch_tensormap(&tm_e);
+    ptx::prefetch_tensormap(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStagesG; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemColsG>(tmem_slot);
+  if (warp == 3) s_br[lane] = (p.br != nullptr && lane < p.E) ? p.br[lane] : 0.0f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n_tiles = (p.S + kTokTile - 1) / kTokTile;
+  const int kb_e = p.Demb / kBlkK;
+  const int nkb = (p.Demb + p.D) / kBlkK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), kAStage + kBStage);
+          if (kb < kb_e)
+            ptx::tma_load_2d(smem_a + stage * kAStage, &tm_e, full_bar(stage), kb * kBlkK, t * kTokTile,
+                             ptx::kEvictFirst);
+          else
+            ptx::tma_load_2d(smem_a + stage * kAStage, &tm_x, full_bar(stage), (kb - kb_e) * kBlkK, t * kTokTile,
+                             ptx::kEvictNormal);  // x is read again by the dispatch kernel
+          ptx::tma_load_2d(smem_b + stage * kBStage, &tm_w, full_bar(stage), kb * kBlkK, 0, ptx::kEvictLast);
+          if (++stage == kStagesG) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc(1u /*bf16*/, kTokTile, kNCols);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kNCols;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a + stage * kAStage);
+          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b + stage * kBStage);
+#pragma unroll
+          for (int k = 0; k < kBlkK / 16; ++k)
+            ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(empty_bar(stage));
+          if (kb == nkb - 1) ptx::umma_commit(tfull_bar(as));
+          if (++stage == kStagesG) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int tok = t * kTokTile + q * 32 + lane;
+      bool valid = tok < p.S;
+      if (valid && p.x_len != nullptr) valid = (tok % p.T) < p.x_len[tok / p.T];
+      s_hist[q * 32 + lane] = 0;
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kNCols;
+      uint32_t hi[32], lo[32];
+      ptx::tmem_ld_32x32b_x32(taddr, hi);
+      ptx::tmem_ld_32x32b_x32(taddr + 32, lo);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+
+      float l[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        l[e] = __uint_as_float(hi[e]) + __uint_as_float(lo[e]) + s_br[e];
+        if (e >= p.E) l[e] = -CUDART_INF_F;
+      }
+      const int kk = p.top_k;
+      float first = 0.0f;
+      float sel_v[8];
+      int sel_i[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        if (s < kk) {
+          float bv = l[0];
+          int bi = 0;
+#pragma unroll
+          for (int e = 1; e < 32; ++e) {
+            if (l[e] > bv) {  // strict: the lowest index wins exact ties
+              bv = l[e];
+              bi = e;
+            }
+          }
+          sel_v[s] = bv;
+          sel_i[s] = bi;
+          if (s == 0) first = bv;
+          if (s + 1 < kk) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e == bi) l[e] = -CUDART_INF_F;
+          }
+        }
+      }
+      float denom = 0.0f;
+      if (p.gate_mode == B200MOE_GATE_3M) {
+        // softmax over ALL experts relative to the maximum (kk == 1, so l[] is still intact)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) denom += expf(l[e] - first);  // exp(-inf) = 0 for the padded experts
+      } else {
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < kk) denom += expf(sel_v[s] - first);
+      }
+      if (tok < p.S) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < kk) {
+            p.idx[static_cast<size_t>(tok) * kk + s] = valid ? sel_i[s] : -1;
+            p.score[static_cast<size_t>(tok) * kk + s] = valid ? expf(sel_v[s] - first) / denom : 0.0f;
+          }
+        }
+      }
+      if (p.hist32 != nullptr) {
+        // expert histogram of this warp's 32 tokens (all top_k entries), for the dispatch kernel
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < kk) {
+            const int e = valid ? sel_i[s] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, e);
+            if (e >= 0 && lane == __ffs(peers) - 1) s_hist[q * 32 + e] += __popc(peers);
+            __syncwarp();
+          }
+        }
+        const int chunk = t * (kTokTile / 32) + q;
+        if (chunk * 32 < p.S && lane < p.E) p.hist32[static_cast<size_t>(chunk) * p.E + lane] = s_hist[q * 32 + lane];
+        __syncwarp();
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemColsG>(tmem_base);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_router_kernel(const float* __restrict__ Wr, int R, int E, bf16* __restrict__ packed) {
+  // packed [64, R]: row e = bf16(Wr[:, e]) (hi), row 32 + e = bf16(Wr[:, e] - hi) (lo); rows >= E are zero
+  const int n = 64 * R;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int row = i / R;
+    const int k = i - row * R;
+    const int e = row & 31;
+    float v = 0.0f;
+    if (e < E) {
+      const float w = Wr[static_cast<size_t>(k) * E + e];
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      v = row < 32 ? hi : (w - hi);
+    }
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace
+
+bool gate_tc_supported(int D, int Demb, int E, int top_k, int dtype) {
+  return dtype == B200MOE_BF16 && E <= 32 && top_k <= 8 && D % kBlkK == 0 && Demb % kBlkK == 0 && D > 0;
+}
+
+size_t router_pack_bytes(int R) { return static_cast<size_t>(64) * R * sizeof(bf16); }
+
+cudaError_t launch_pack_router(const float* Wr, int R, int E, void* packed, cudaStream_t stream) {
+  if (E > 32 || R < 1) return cudaErrorInvalidValue;
+  pack_router_kernel<<<64, 256, 0, stream>>>(Wr, R, E, static_cast<bf16*>(packed));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gate_tc(const void* x, const void* embed, const void* wr_packed, const float* br, const int* x_len,
+                           int B, int T, int D, int Demb, int E, int top_k, int gate_mode, int* idx, float* score,
+                           int* hist32, cudaStream_t stream) {
+  const int S = B * T;
+  if (S == 0) return cudaSuccess;
+  if (embed == nullptr) Demb = 0;
+  if (!gate_tc_supported(D, Demb, E, top_k, B200MOE_BF16)) return cudaErrorInvalidValue;
+  CUtensorMap tx, te, tw;
+  if (!make_tmap_bf16(&tx, x, S, D, kTokTile, kBlkK)) return cudaErrorInvalidValue;
+  if (Demb > 0) {
+    if (!make_tmap_bf16(&te, embed, S, Demb, kTokTile, kBlkK)) return cudaErrorInvalidValue;
+  } else {
+    te = tx;
+  }
+  if (!make_tmap_bf16(&tw, wr_packed, 64, static_cast<uint64_t>(D + Demb), kNCols, kBlkK)) return cudaErrorInvalidValue;
+  GateTcParams p;
+  p.br = br;
+  p.x_len = x_len;
+  p.idx = idx;
+  p.score = score;
+  p.hist32 = hist32;
+  p.S = S;
+  p.T = T;
+  p.D = D;
+  p.Demb = Demb;
+  p.E = E;
+  p.top_k = top_k;
+  p.gate_mode = gate_mode;
+  const size_t smem = 1024 + kStagesG * (kAStage + kBStage) + 8 * (2 * kStagesG + 4) + 16 + 32 * 4 + 4 * 32 * 4 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int n_tiles = (S + kTokTile - 1) / kTokTile;
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  gate_tc_kernel<<<grid, kThreadsG, smem, stream>>>(tx, te, tw, p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace b200moe

@@ -24,6 +24,16 @@ class NaiveGate(nn.Module):
         b = self.gate.bias
         return self._wr, (None if b is None else b.detach().float().contiguous())
 
+    def router_packed(self):
+        """bf16 hi/lo packing of the router for the tensor-core gate (None when E > 32)."""
+        Wr, _ = self.router_params()
+        if Wr.shape[1] > 32 or not Wr.is_cuda:
+            return None
+        if getattr(self, "_wrp_key", None) != self._wr_key:
+            self._wrp = ops.pack_router(Wr)
+            self._wrp_key = self._wr_key
+        return self._wrp
+
     def forward(self, inp):
         """Returns (gate_top_k_idx [N * top_k] int64, gate_score [N, 1, top_k], None).
         The reference also returns the dense logits (gates.py:66); they are not materialised here."""

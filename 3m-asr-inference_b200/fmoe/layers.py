@@ -105,7 +105,8 @@ class FMoE(nn.Module):
                                   top_k=self.top_k, gate_mode=ops.GATE_NAIVE, act_type=activation_code(act))
             return out.reshape(inp.shape)
         res = ops.moe_layer(x, None, Wr, br, packed, top_k=self.top_k, gate_mode=ops.GATE_NAIVE,
-                            act_type=activation_code(act), ff_scale=1.0, return_routing=self.gate_hook is not None)
+                            act_type=activation_code(act), ff_scale=1.0, return_routing=self.gate_hook is not None,
+                            Wr_packed=self.gate.router_packed() if hasattr(self.gate, "router_packed") else None)
         if self.gate_hook:
             self.gate_hook(res.idx.view(-1).long(), res.score.view(-1, 1, self.top_k), None)
         return res.out.reshape(inp.shape)

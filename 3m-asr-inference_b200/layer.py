@@ -71,6 +71,17 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
         br = None if self.router_bias is None else self.router_bias.detach().float().contiguous()
         return wr.contiguous(), br
 
+    def _router_packed(self, wr):
+        """bf16 hi/lo packing of the router for the tensor-core gate, refreshed when the parameter changes."""
+        if wr.shape[1] > 32 or not wr.is_cuda:
+            return None
+        w = self.router_weights
+        key = (w.data_ptr(), w._version, str(w.device))
+        if getattr(self, "_wrp_key", None) != key:
+            self._wrp = ops.pack_router(wr)
+            self._wrp_key = key
+        return self._wrp
+
     def forward(self, inputs: torch.Tensor, embed: Optional[torch.Tensor], mask: Optional[torch.Tensor] = None, *,
                 residual: Optional[torch.Tensor] = None, ff_scale: float = 1.0, return_routing: bool = False):
         """inputs [B, T, idim]; embed [B, T, embed_dim]; mask [B] int32 valid lengths (the plugin's `mask` input,
@@ -94,5 +105,6 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
             return out.view(B, T, D)
         res = ops.moe_layer(x, e, Wr, br, packed, residual=None if residual is None else residual.contiguous(),
                             x_len=x_len, top_k=1, gate_mode=ops.GATE_3M, act_type=act, ff_scale=ff_scale,
-                            keep_expert_output=self.keep_expert_output, return_routing=return_routing)
+                            keep_expert_output=self.keep_expert_output, return_routing=return_routing,
+                            Wr_packed=self._router_packed(Wr))
         return res if return_routing else res.out

@@ -116,6 +116,21 @@ def pack_experts(W1, b1, W2, b2) -> PackedExperts:
     return PackedExperts(pack_bf16(W1.detach().contiguous()), f32(b1), pack_bf16(W2.detach().contiguous()), f32(b2))
 
 
+def pack_router(Wr: torch.Tensor) -> torch.Tensor:
+    """fp32 router [R, E] (E <= 32) -> bf16 hi/lo K-major [64, R] for the tensor-core gate."""
+    _need_cuda(Wr)
+    R, E = Wr.shape
+    if Wr.dtype != torch.float32:
+        raise TypeError("router weights must be fp32")
+    out = torch.empty(64, R, dtype=torch.bfloat16, device=Wr.device)
+    _lib.check(_lib.load().b200moe_pack_router(_ptr(Wr), R, E, _ptr(out), _stream()), "b200moe_pack_router")
+    return out
+
+
+def gate_tc_usable(x_dtype, D: int, Demb: int, E: int, top_k: int) -> bool:
+    return x_dtype == torch.bfloat16 and E <= 32 and top_k <= 8 and D % 64 == 0 and Demb % 64 == 0
+
+
 # ---- stages ---------------------------------------------------------------------------------------------------------------
 def gate(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, br: Optional[torch.Tensor] = None,
          x_len: Optional[torch.Tensor] = None, *, top_k: int = 1, gate_mode: int = GATE_3M,
@@ -138,6 +153,27 @@ def gate(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, br: O
     lib = _lib.load()
     _lib.check(lib.b200moe_gate(_ptr(x), _ptr(embed), _ptr(Wr), _ptr(br), _ptr(x_len), B, T, D, Demb, E, top_k,
                                 gate_mode, dtype_code(x), _ptr(idx), _ptr(score), _stream()), "b200moe_gate")
+    return idx, score
+
+
+def gate_tc(x: torch.Tensor, embed: Optional[torch.Tensor], Wr_packed: torch.Tensor, num_expert: int,
+            br: Optional[torch.Tensor] = None, x_len: Optional[torch.Tensor] = None, *, top_k: int = 1,
+            gate_mode: int = GATE_3M, seq_len: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Tensor-core gate (bf16 activations, E <= 32). Same outputs as gate()."""
+    dev = _need_cuda(x, embed, Wr_packed, br, x_len)
+    if x.dim() == 3:
+        B, T, D = x.shape
+    else:
+        S, D = x.shape
+        T = seq_len if seq_len is not None else S
+        B = S // T if T else 0
+    S = B * T
+    Demb = 0 if embed is None else embed.shape[-1]
+    idx = torch.empty(S, top_k, dtype=torch.int32, device=dev)
+    score = torch.empty(S, top_k, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().b200moe_gate_tc(_ptr(x), _ptr(embed), _ptr(Wr_packed), _ptr(br), _ptr(x_len), B, T, D, Demb,
+                                           num_expert, top_k, gate_mode, _ptr(idx), _ptr(score), _stream()),
+               "b200moe_gate_tc")
     return idx, score
 
 
@@ -220,9 +256,11 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
               experts: PackedExperts, *, residual: Optional[torch.Tensor] = None, x_len: Optional[torch.Tensor] = None,
               seq_len: Optional[int] = None, top_k: int = 1, gate_mode: int = GATE_3M, act_type: int = ACT_SILU,
               ff_scale: float = 1.0, keep_expert_output: bool = False, out: Optional[torch.Tensor] = None,
-              return_routing: bool = False, ws: Optional[torch.Tensor] = None) -> LayerOut:
+              return_routing: bool = False, ws: Optional[torch.Tensor] = None,
+              Wr_packed: Optional[torch.Tensor] = None) -> LayerOut:
     """The fused layer: out = (residual) + ff_scale * sum_k score_k * FFN_{e_k}(x).  x [S, D] or [B, T, D]."""
-    dev = _need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out)
+    dev = _need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out,
+                     Wr_packed)
     shape = x.shape
     if x.dim() == 3:
         B, T, D = x.shape
@@ -245,7 +283,7 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
         mapping = torch.empty(S * top_k, dtype=torch.int32, device=dev)
     a = _lib.LayerArgs(
         x=_ptr(x), embed=_ptr(embed), residual=_ptr(residual), out=_ptr(out), x_len=_ptr(x_len),
-        Wr=_ptr(Wr), br=_ptr(br), W1=_ptr(experts.W1), b1=_ptr(experts.b1), W2=_ptr(experts.W2), b2=_ptr(experts.b2),
+        Wr=_ptr(Wr), Wr_packed=_ptr(Wr_packed), br=_ptr(br), W1=_ptr(experts.W1), b1=_ptr(experts.b1), W2=_ptr(experts.W2), b2=_ptr(experts.b2),
         B=B, T=T, D=D, Demb=Demb, E=E, H=H, top_k=top_k, gate_mode=gate_mode, act_type=act_type,
         dtype=dtype_code(x), keep_expert_output=int(keep_expert_output), ff_scale=float(ff_scale),
         idx_out=_ptr(idx), score_out=_ptr(score), counts_out=_ptr(counts), mapping_out=_ptr(mapping))

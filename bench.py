@@ -219,7 +219,7 @@ def main():
         b1 = torch.zeros(E_local, H, device=dev)
         b2 = torch.zeros(E_local, D, device=dev)
         Wr = xavier((DEMB + D, E), DEMB + D, E, gen_shared).bfloat16().float()
-        layers.append((Wr, ops.PackedExperts(W1, b1, W2, b2)))
+        layers.append((Wr, ops.PackedExperts(W1, b1, W2, b2), ops.pack_router(Wr)))
 
     # ---- synthetic activations: pinned host copies (for e2e) and device-resident copies (for value)
     g = torch.Generator().manual_seed(20260003 + rank)
@@ -234,14 +234,14 @@ def main():
 
     def step(x_in, e_in):
         cur = x_in
-        for li, (Wr, experts) in enumerate(layers):
+        for li, (Wr, experts, Wrp) in enumerate(layers):
             out = bufs[li & 1]
             if world > 1:
                 ep.ep_moe_layer(cur, e_in, Wr, None, experts, num_local_expert=E_local, group=None, top_k=1,
                                 gate_mode=ops.GATE_3M, act_type=ops.ACT_SILU, ff_scale=0.5, residual=cur, out=out)
             else:
                 ops.moe_layer(cur, e_in, Wr, None, experts, residual=cur, top_k=1, gate_mode=ops.GATE_3M,
-                              act_type=ops.ACT_SILU, ff_scale=0.5, out=out)
+                              act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=Wrp)
             cur = out
         return cur
 
@@ -358,7 +358,7 @@ def main():
         torch.set_num_threads(cores)
         n_sets = min(L, 2)
         cpu_layers = [dict(Wr=Wr.cpu(), W1=ex.W1.float().cpu(), b1=ex.b1.cpu(), W2=ex.W2.float().cpu(), b2=ex.b2.cpu())
-                      for (Wr, ex) in layers[:n_sets]]
+                      for (Wr, ex, _) in layers[:n_sets]]
         seq = [cpu_layers[i % n_sets] for i in range(L)]
         xc, ec = x_host.float(), e_host.float()
         with torch.no_grad():

@@ -96,6 +96,16 @@ int b200moe_gate(const void* x, const void* embed, const float* Wr, const float*
                  int D, int Demb, int E, int top_k, int gate_mode, int dtype, int* idx, float* score,
                  cudaStream_t stream);
 
+/* Tensor-core variant of the gate for bf16 activations and E <= 32 (D, Demb multiples of 64).  The router is packed
+ * once per checkpoint load into bf16 [64, Demb + D]: rows 0..31 = bf16(Wr^T), rows 32..63 = bf16(Wr^T - rows 0..31), so
+ * that the fp32 router weights survive to ~2^-17 and bf16 x bf16 products stay exact in the fp32 accumulator.
+ * Same outputs and tie rule as b200moe_gate. */
+size_t b200moe_router_pack_bytes(int R);
+int b200moe_pack_router(const float* Wr, int R, int E, void* packed, cudaStream_t stream);
+int b200moe_gate_tc(const void* x, const void* embed, const void* Wr_packed, const float* br, const int* x_len, int B,
+                    int T, int D, int Demb, int E, int top_k, int gate_mode, int* idx, float* score,
+                    cudaStream_t stream);
+
 /* ---- stage 2: dispatch -------------------------------------------------------------------------------------
  * Counts tokens per expert, exclusive-scans, and stably scatters token rows into expert-contiguous order:
  *   mapping[i] = offsets[idx[i]] + #{ j < i : idx[j] == idx[i] }   for entry i = s*top_k + j; -1 if idx[i] < 0
@@ -132,7 +142,8 @@ typedef struct b200moe_layer_args {
   void* out;            /* [B*T, D]                                                                    */
   const int* x_len;     /* [B] or NULL                                                                 */
   /* router */
-  const float* Wr;      /* [Demb + D, E] fp32                                                         */
+  const float* Wr;      /* [Demb + D, E] fp32 (may be NULL when Wr_packed is given and usable)        */
+  const void* Wr_packed;/* b200moe_pack_router(Wr) or NULL: enables the tensor-core gate for bf16 / E <= 32 */
   const float* br;      /* [E] fp32 or NULL                                                            */
   /* experts (bf16 packed weights, fp32 biases) */
   const void* W1;       /* [E, H, D] bf16                                                              */

@@ -16,11 +16,15 @@ def dev(t, dtype=None):
     return t.to(dtype) if dtype is not None else t
 
 
-def run_layer(ops, w, x, embed, *, dtype=torch.bfloat16, residual=True, x_len=None, T=None, **kw):
+def run_layer(ops, w, x, embed, *, dtype=torch.bfloat16, residual=True, x_len=None, T=None, tc_gate=True, **kw):
+    """tc_gate: hand the packed router to the layer so that bf16 / E <= 32 calls take the tensor-core gate (and the
+    gate-fused histograms); fp32 / fp16 activations and E > 32 use the SIMT gate either way."""
     experts = ops.pack_experts(dev(w.W1), dev(w.b1), dev(w.W2), dev(w.b2))
     xd, ed = dev(x, dtype), dev(embed, dtype)
-    return ops.moe_layer(xd, ed, dev(w.Wr), dev(w.br), experts, residual=xd if residual else None,
-                         x_len=dev(x_len), seq_len=T, return_routing=True, **kw)
+    Wr = dev(w.Wr)
+    packed = ops.pack_router(Wr) if (tc_gate and Wr.shape[1] <= 32) else None
+    return ops.moe_layer(xd, ed, Wr, dev(w.br), experts, residual=xd if residual else None,
+                         x_len=dev(x_len), seq_len=T, return_routing=True, Wr_packed=packed, **kw)
 
 
 def check_against_oracle(oracle, res, ref, tol=BF16_REL_L2):
@@ -69,25 +73,27 @@ def test_golden_naive_top2(ops, oracle):
     assert rel_l2(res.out.cpu(), g["out"]) <= BF16_REL_L2
 
 
+@pytest.mark.parametrize("tc_gate", [True, False])
 @pytest.mark.parametrize("S,dtype,random_bias", [
     (50, torch.bfloat16, False),     # cfg1: batch 1 x 206 frames -> 50 tokens, reference init (zero biases)
     (206, torch.bfloat16, True),     # cfg1, frames as tokens, biases exercised
     (3200, torch.bfloat16, True),    # cfg3 per layer: batch 64 x 206 frames
     (3200, torch.float32, True),     # fp32 activations at the boundary (the reference plugin's data_type 0)
     (13184, torch.bfloat16, False),  # cfg3 with frames as tokens
+    (20000, torch.bfloat16, False),  # > 512 histogram rows: falls back to the count kernel
     (1, torch.bfloat16, True),
 ])
-def test_layer_3m_repo_dims(ops, oracle, synth, S, dtype, random_bias):
+def test_layer_3m_repo_dims(ops, oracle, synth, S, dtype, random_bias, tc_gate):
     E, D, H, Demb = 32, 512, 1024, 512
     w = synth.make_weights(20260001, E, D, H, Demb, random_bias=random_bias)
     x, embed = synth.make_activations(20260001 + S, S, D, Demb, w)
     ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
-    res = run_layer(ops, w, x, embed, dtype=dtype, ff_scale=0.5)
+    res = run_layer(ops, w, x, embed, dtype=dtype, ff_scale=0.5, tc_gate=tc_gate)
     check_against_oracle(oracle, res, ref)
     # The MoE term on its own (no residual), so the O(1) residual cannot mask an error in the O(1e-2) expert output.
     # (With a bf16 residual stream the sum is rounded to 8 bits of mantissa, which is coarser than the MoE term for
     # the reference's tiny xavier(gain=0.5) weights -- that is a property of bf16 storage, not of this kernel.)
-    res2 = run_layer(ops, w, x, embed, dtype=dtype, residual=False, ff_scale=0.5)
+    res2 = run_layer(ops, w, x, embed, dtype=dtype, residual=False, ff_scale=0.5, tc_gate=tc_gate)
     assert rel_l2(res2.out.float().cpu(), 0.5 * ref["moe"]) <= BF16_REL_L2
     if dtype == torch.float32:
         moe = (res.out.cpu() - x) / 0.5

@@ -45,6 +45,54 @@ def test_gate_3m(ops, oracle, synth, S, E, D, Demb, dtype, bias):
     torch.testing.assert_close(score.cpu().view(-1), ref_val, rtol=SCORE_RTOL, atol=1e-7)
 
 
+@pytest.mark.parametrize("S,E,D,Demb,bias", [
+    (50, 32, 512, 512, False), (206, 32, 512, 512, True), (3200, 32, 512, 512, False), (20000, 32, 512, 512, True),
+    (129, 7, 128, 0, True), (1, 32, 512, 512, False), (128, 32, 64, 64, False), (4097, 20, 256, 128, True),
+])
+def test_gate_tc_3m(ops, oracle, synth, S, E, D, Demb, bias):
+    """Tensor-core gate: same bit-exact routing bar as the SIMT gate."""
+    w = synth.make_weights(600 + S, E, D, 128, Demb, router_bias=bias)
+    x, embed = synth.make_activations(700 + S, S, D, Demb, w)
+    ref_idx, ref_val, _ = oracle.gate_3m(x, embed, w.Wr, w.br)
+    packed = ops.pack_router(dev(w.Wr))
+    idx, score = ops.gate_tc(dev(x, torch.bfloat16), dev(embed, torch.bfloat16), packed, E, dev(w.br), top_k=1)
+    assert torch.equal(idx.cpu().view(-1).long(), ref_idx)
+    torch.testing.assert_close(score.cpu().view(-1), ref_val, rtol=SCORE_RTOL, atol=1e-7)
+    # and it agrees with the SIMT gate bit for bit on the routing
+    idx2, _ = ops.gate(dev(x, torch.bfloat16), dev(embed, torch.bfloat16), dev(w.Wr), dev(w.br), top_k=1)
+    assert torch.equal(idx, idx2)
+
+
+def test_gate_tc_router_off_the_bf16_grid(ops, oracle, synth):
+    """fp32 router weights that are NOT bf16-representable: the hi/lo split must keep the routing of the fp32 oracle."""
+    S, E, D, Demb = 5000, 32, 512, 512
+    w = synth.make_weights(801, E, D, 128, Demb)
+    g = torch.Generator().manual_seed(802)
+    w.Wr = (torch.rand(D + Demb, E, generator=g) * 2 - 1) * 0.04          # full fp32 mantissas
+    x, embed = synth.make_activations(803, S, D, Demb, w, margin=2e-4)
+    ref_idx, ref_val, _ = oracle.gate_3m(x, embed, w.Wr, None)
+    idx, score = ops.gate_tc(dev(x, torch.bfloat16), dev(embed, torch.bfloat16), ops.pack_router(dev(w.Wr)), E)
+    assert torch.equal(idx.cpu().view(-1).long(), ref_idx)
+    torch.testing.assert_close(score.cpu().view(-1), ref_val, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("S,E,D,k", [(29, 8, 128, 2), (1000, 32, 512, 2), (513, 16, 256, 4)])
+def test_gate_tc_naive_topk_and_padding(ops, oracle, synth, S, E, D, k):
+    w = synth.make_weights(900 + S, E, D, 128, 0, router_bias=True)
+    x, _ = synth.make_activations(950 + S, S, D, 0, w, top_k=k)
+    ref_idx, ref_score, _ = oracle.gate_naive(x, w.Wr, w.br, k)
+    packed = ops.pack_router(dev(w.Wr))
+    idx, score = ops.gate_tc(dev(x, torch.bfloat16), None, packed, E, dev(w.br), top_k=k, gate_mode=ops.GATE_NAIVE)
+    assert torch.equal(idx.cpu().long(), ref_idx)
+    torch.testing.assert_close(score.cpu(), ref_score, rtol=SCORE_RTOL, atol=1e-7)
+    # padding rows: idx -1, score 0
+    x_len = torch.tensor([S // 2], dtype=torch.int32)
+    idx, score = ops.gate_tc(dev(x, torch.bfloat16), None, packed, E, dev(w.br), dev(x_len), top_k=k,
+                             gate_mode=ops.GATE_NAIVE, seq_len=S)
+    assert torch.equal(idx.cpu().long()[: S // 2], ref_idx[: S // 2])
+    assert torch.all(idx.cpu()[S // 2:] == -1) and torch.all(score.cpu()[S // 2:] == 0)
+
+
 def _redraw_clear(oracle, x, embed, w, margin=1e-4):
     logits = oracle.router_logits(x, embed, w.Wr, w.br)
     top = torch.topk(logits, 2, dim=-1).values

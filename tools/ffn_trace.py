@@ -30,20 +30,20 @@ def main():
         W1 = ((torch.rand(E, H, D, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
         W2 = ((torch.rand(E, D, H, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
         Wr = ((torch.rand(Demb + D, E, generator=g, device=dev) * 2 - 1) * 0.04)
-        layers.append((Wr, ops.PackedExperts(W1, torch.zeros(E, H, device=dev), W2, torch.zeros(E, D, device=dev))))
+        layers.append((Wr, ops.PackedExperts(W1, torch.zeros(E, H, device=dev), W2, torch.zeros(E, D, device=dev)), ops.pack_router(Wr)))
     x = torch.randn(S, D, generator=g, device=dev).bfloat16()
     emb = torch.randn(S, Demb, generator=g, device=dev).bfloat16()
     out = torch.empty_like(x)
     for _ in range(3):
-        for Wr, ex in layers:
-            ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out)
+        for Wr, ex, wp in layers:
+            ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
     torch.cuda.synchronize()
     cap = 96  # records per CTA (3 roles x 32)
     n_cta = 148
     buf = torch.zeros(n_cta * cap, 4, dtype=torch.int32, device=dev)
     lib.b200moe_debug_ffn_trace(buf.data_ptr(), cap)
-    Wr, ex = layers[0]
-    ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out)
+    Wr, ex, wp = layers[0]
+    ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
     torch.cuda.synchronize()
     lib.b200moe_debug_ffn_trace(None, 0)
     rec = buf.cpu().numpy().astype(np.int64).reshape(n_cta, 3, cap // 3, 4)
