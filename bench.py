@@ -331,6 +331,13 @@ def main():
     # ---- roofline of the dominant kernel (expert FFN with the fused combine epilogue)
     hbm_peak, tf_peak, peak_kind = load_peaks()
     roofline = None
+    traffic = None   # DRAM bytes per launch of the same kernel from one `ncu --set full` capture (profiles/)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ffn_traffic.json")))
+        if args.workload == tr.get("workload"):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     if stage_calls.get("expert_ffn"):
         t_ffn = stage_ms["expert_ffn"] / stage_calls["expert_ffn"] * 1e-3      # seconds per launch
         w_bytes = 2 * E * D * H * 2 + (E * H + E * D) * 4                       # bf16 W1 + W2, fp32 biases
@@ -342,12 +349,12 @@ def main():
         if hbm_time >= tc_time:
             ach = alg_bytes / t_ffn / 1e9
             roofline = {"kernel": "ffn_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                        "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
                         "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": t_ffn * 1e6}
         else:
             ach = flops / t_ffn / 1e12
             roofline = {"kernel": "ffn_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": ach / tf_peak, "traffic": None, "peak_source": peak_kind,
+                        "frac": ach / tf_peak, "traffic": traffic, "peak_source": peak_kind,
                         "algorithmic_flops_per_launch": flops, "us_per_launch": t_ffn * 1e6}
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample (rank 0, N = 1 only)
