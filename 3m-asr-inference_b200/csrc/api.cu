@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -80,6 +81,28 @@ struct StageScope {
 }  // namespace
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+
+namespace {
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+}  // namespace
+
+int pdl_mask() {
+  static const int m = env_int("B200MOE_PDL", 0);
+  return m;
+}
+
+int pdl_trigger() {
+  static const int m = env_int("B200MOE_PDL_TRIG", 7);
+  return m;
+}
+
+int prefetch_mode() {
+  static const int m = env_int("B200MOE_PREFETCH", 0);
+  return m;
+}
 
 }  // namespace b200moe
 
@@ -194,7 +217,7 @@ int b200moe_gate_tc(const void* x, const void* embed, const void* Wr_packed, con
   if (!gate_tc_supported(D, embed ? Demb : 0, E, top_k, B200MOE_BF16))
     return fail(B200MOE_ERR_ARG, "gate_tc: needs bf16 activations, E <= 32, D and Demb multiples of 64");
   cudaError_t e = launch_gate_tc(x, embed, Wr_packed, br, x_len, B, T, D, embed ? Demb : 0, E, top_k, gate_mode, idx,
-                                 score, nullptr, stream);
+                                 score, nullptr, nullptr, 0, nullptr, 0, stream);
   if (e != cudaSuccess) return cuda_fail(e, "gate_tc");
   return B200MOE_OK;
 }
@@ -308,9 +331,14 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
   {
     StageScope t(0, stream);
-    if (tc_gate)
+    if (tc_gate) {
+      // small batches are bound by streaming the 2 * E * D * H weights: start pulling them into L2 now
+      const size_t wbytes = static_cast<size_t>(a->E) * a->H * a->D * sizeof(bf16);
+      const bool pf = Sk <= 32768;
       e = launch_gate_tc(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
-                         a->gate_mode, idx, score, w.hist32, stream);
+                         a->gate_mode, idx, score, w.hist32, pf ? a->W1 : nullptr, wbytes, pf ? a->W2 : nullptr, wbytes,
+                         stream);
+    }
     else
       e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k, a->gate_mode,
                       a->dtype, idx, score, stream);

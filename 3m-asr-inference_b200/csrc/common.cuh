@@ -7,6 +7,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/b200moe.h"
 
 namespace b200moe {
@@ -91,7 +93,8 @@ size_t router_pack_bytes(int R);
 cudaError_t launch_pack_router(const float* Wr, int R, int E, void* packed, cudaStream_t stream);
 cudaError_t launch_gate_tc(const void* x, const void* embed, const void* wr_packed, const float* br, const int* x_len,
                            int B, int T, int D, int Demb, int E, int top_k, int gate_mode, int* idx, float* score,
-                           int* hist32, cudaStream_t stream);
+                           int* hist32, const void* pf0, size_t pf0_bytes, const void* pf1, size_t pf1_bytes,
+                           cudaStream_t stream);
 cudaError_t launch_softmax_topk(const void* logits, const int* mask, int B, int T, int E, int dtype, void* value,
                                 int* idx, cudaStream_t stream);
 
@@ -144,6 +147,36 @@ cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* sc
 cudaError_t launch_pack_bf16(const void* src, int src_dtype, bf16* dst, size_t n, cudaStream_t stream);
 
 void count_launch(int n = 1);
+
+// Tunables read once from the environment (api.cu):
+//   B200MOE_PDL=m       bit mask of the kernels launched with programmatic dependent launch (1 gate, 2 dispatch,
+//                       4 expert FFN); 0 = ordinary stream ordering.  B200MOE_PDL_TRIG=m: which of them release their
+//                       dependents at their start (otherwise at exit)
+//   B200MOE_PREFETCH=0  no L2 prefetch of the layer's expert weights from the gate kernel; 1 (default) = issued before
+//                       the gate waits for the previous kernel; 2 = issued after that wait
+int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN: kernel launched with the PDL attribute
+int pdl_trigger();   // same bits: kernel executes griddepcontrol.launch_dependents at its start
+int prefetch_mode();
+constexpr int kPdlGate = 1, kPdlDispatch = 2, kPdlFfn = 4;
+
+// Kernel launch with the programmatic-stream-serialization attribute: the kernel may become resident as soon as every
+// CTA of the previous kernel in the stream has executed griddepcontrol.launch_dependents (or exited); everything it reads
+// or writes that an earlier kernel produces or still reads must come after its own griddepcontrol.wait.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int pdl_bit, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_bit & pdl_mask()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- small device helpers ------------------------------------------------------------------------------------
 template <typename T>

@@ -10,6 +10,7 @@
 // histograms, ranks its entries with warp match/ballot, and copies rows with 128-bit accesses, casting to bf16).
 // CTA 0 of the scatter kernel also emits counts / offsets / the FFN group table and clears the FFN flags.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace b200moe {
 
@@ -130,20 +131,26 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
                         int* __restrict__ offsets, int* __restrict__ mapping, int* __restrict__ pos,
                         float* __restrict__ row_score, bf16* __restrict__ xbuf, GroupRec* groups, int* n_groups,
                         int* h_ready, int* counts_out, int* offsets_out, int* mapping_out, InT* __restrict__ drop_out,
-                        const InT* __restrict__ drop_residual) {
+                        const InT* __restrict__ drop_residual, int early_trigger) {
   constexpr int kWarps = kDispatchThreads / 32;
   constexpr int kRowsPerBatch = 4;            // rows a warp keeps in flight during the copy
-  __shared__ int s_total[kMaxExperts];        // tokens per expert over all chunks
-  __shared__ int s_cursor[kMaxExperts];       // next expert-order row for this CTA's entries
-  __shared__ int s_off[kMaxExperts + 1];      // global exclusive offsets
-  __shared__ int s_scratch[kMaxExperts + 1];
-  __shared__ int s_dst[kDispatchThreads];     // destination row of each entry of the current segment
   constexpr int kMaxParts = 8;
-  __shared__ int s_part[kMaxParts * 2 * kMaxExperts];  // partial column sums (before / total) per part
-  extern __shared__ int s_wcnt[];             // [kWarps][E] per-warp counts of the current segment
+  // All shared memory is dynamic and sized by E (about 4.6 KB at E = 32), so that a CTA of the expert-FFN kernel
+  // (launched early under programmatic dependent launch, ~211 KB) fits on the same SM beside a dispatch CTA.
+  extern __shared__ int s_dyn[];
+  int* s_total = s_dyn;                       // [E]     tokens per expert over all chunks
+  int* s_cursor = s_total + E;                // [E]     next expert-order row for this CTA's entries
+  int* s_off = s_cursor + E;                  // [E + 1] global exclusive offsets
+  int* s_scratch = s_off + E + 1;             // [E + 1]
+  int* s_dst = s_scratch + E + 1;             // [kDispatchThreads] destination row of each entry of the segment
+  int* s_wcnt = s_dst + kDispatchThreads;     // [kWarps][E] per-warp counts of the current segment
+  int* s_part = s_wcnt + kWarps * E;          // [nparts][2][E] partial column sums (before / total)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (early_trigger) ptx::pdl_launch_dependents();  // the expert-FFN kernel may set itself up; it blocks in pdl_wait()
+  ptx::pdl_wait();               // idx / score / hist32 come from the gate; xbuf, pos, groups may still be read by
+                                 // the previous layer's FFN kernel
 
   // 1. column sums of the chunk histograms: totals and the part that precedes this chunk.  All 256 threads take
   //    part: thread (part, e) sums the chunks c = part, part + nparts, ... (independent loads, one latency), then
@@ -161,16 +168,16 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
         if (c < my_first_row) before += v;
         total += v;
       }
-      s_part[(part * 2) * kMaxExperts + e] = before;
-      s_part[(part * 2 + 1) * kMaxExperts + e] = total;
+      s_part[(part * 2) * E + e] = before;
+      s_part[(part * 2 + 1) * E + e] = total;
     }
     for (int i = threadIdx.x; i < kWarps * E; i += blockDim.x) s_wcnt[i] = 0;
     __syncthreads();
     for (int ee = threadIdx.x; ee < E; ee += blockDim.x) {
       int before = 0, total = 0;
       for (int pt = 0; pt < nparts; ++pt) {
-        before += s_part[(pt * 2) * kMaxExperts + ee];
-        total += s_part[(pt * 2 + 1) * kMaxExperts + ee];
+        before += s_part[(pt * 2) * E + ee];
+        total += s_part[(pt * 2 + 1) * E + ee];
       }
       s_cursor[ee] = before;
       s_total[ee] = total;
@@ -332,13 +339,18 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
   }
-  const size_t dyn = sizeof(int) * (kDispatchThreads / 32) * E;
+  const int nparts_max = 8;
+  const size_t dyn = sizeof(int) * (2 * E + 2 * (E + 1) + kDispatchThreads + (kDispatchThreads / 32) * E +
+                                    nparts_max * 2 * E);
+  cudaError_t lerr = cudaSuccess;
 #define B200MOE_SCATTER(T)                                                                                        \
-  dispatch_scatter_kernel<T><<<ck.nchunks, kDispatchThreads, dyn, stream>>>(                                      \
+  lerr = launch_kernel(dispatch_scatter_kernel<T>, dim3(ck.nchunks), dim3(kDispatchThreads), dyn, stream,          \
+      kPdlDispatch,                                                                                               \
       static_cast<const T*>(x), idx, score, Sk, D, E, top_k, ck.chunk, ck.nchunks, hist, hist_rows,               \
       rows_per_chunk, bn, gmax,                                                                                   \
       ws.counts, ws.offsets, ws.mapping, ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready,          \
-      counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual))
+      counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual),   \
+      (pdl_trigger() & kPdlDispatch) ? 1 : 0)
   switch (dtype) {
     case B200MOE_F32:
       B200MOE_SCATTER(float);
@@ -354,7 +366,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
   }
 #undef B200MOE_SCATTER
   count_launch();
-  return cudaGetLastError();
+  return lerr;
 }
 
 cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,

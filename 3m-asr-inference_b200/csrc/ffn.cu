@@ -20,6 +20,7 @@
 //  * warp roles: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, multi-stage mbarrier ring),
 //    warp 1 = single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, double buffered: 2 x 256 columns),
 //    warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/activation -> global).
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -35,12 +36,13 @@ constexpr int kBlockK = 64;                            // bf16 elements per k-bl
 constexpr int kUmmaK = 16;                             // K per tcgen05.mma for 16-bit inputs
 constexpr int kMaxStages = 10;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;    // 16 KiB
-constexpr int kStageBudget = 200 * 1024;
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kStageBudget = 192 * 1024;
+constexpr int kThreads = 384;                          // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;                       // two sets of four warps (one TMEM lane quarter each)
+constexpr int kSetThreads = 128;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kAccStride = 256;                        // TMEM columns per accumulator buffer
-constexpr int kStagingBytes = 32 * kBlockM * 4;        // epilogue transpose buffer: 32 columns x 128 features fp32
+constexpr int kStagingBytes = 32 * kBlockM * 4;        // per epilogue set: 32 columns x 128 features fp32 (or 2 x bf16)
 
 struct FfnParams {
   const GroupRec* groups;
@@ -58,6 +60,9 @@ struct FfnParams {
   int E, D, H, bn, act, fused;
   int stages;
   int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
+  int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
+  int dbg;          // timing experiments only (B200MOE_DBG): 1 = no phase-2 stores, 2 = no phase-1 stores, 4 = no residual
+  uint64_t w_policy;  // L2 eviction policy of the weight tiles: evict-first when every tile is read once
   // debug timeline (ffn_kernel<.., true> only): per CTA `trace_cap` records of {tile, event, globaltimer lo, hi}
   uint4* trace;
   int trace_cap;
@@ -66,7 +71,9 @@ struct FfnParams {
 enum TraceEvent : int {
   kEvKernelStart = 0, kEvProdTileStart = 1, kEvProdDepOk = 2, kEvProdIssued = 3, kEvMmaAccFree = 4,
   kEvMmaFirstData = 5, kEvMmaIssued = 6, kEvEpiAccReady = 7, kEvEpiAccReleased = 8, kEvEpiStored = 9,
-  kEvEpiPublished = 10, kEvKernelEnd = 11
+  kEvEpiPublished = 10, kEvKernelEnd = 11, kEvEpiChunkLd = 12, kEvEpiChunkStaged = 13, kEvEpiChunkDone = 14,
+  kEvClock = 15,        // time fields = %globaltimer (ns) ...
+  kEvClockCycles = 16   // ... and clock64 read right after it
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -75,7 +82,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// One slot counter per role (0 producer, 1 mma, 2 epilogue) so the three recording threads never collide.
+// One slot counter per role (0 producer, 1 mma, 2 epilogue, 3 publisher) so the recording threads never collide.
 template <bool kTrace>
 struct Tracer {
   uint4* base;
@@ -83,17 +90,32 @@ struct Tracer {
   __device__ __forceinline__ Tracer(const FfnParams& p, int role) : base(nullptr), cap(0), n(0) {
     if constexpr (kTrace) {
       if (p.trace != nullptr) {
-        cap = p.trace_cap / 3;
-        base = p.trace + (static_cast<size_t>(blockIdx.x) * 3 + role) * cap;
+        cap = p.trace_cap / 4;
+        base = p.trace + (static_cast<size_t>(blockIdx.x) * 4 + role) * cap;
       }
     }
   }
+  // Events carry the SM's cycle counter (a register read); reading %globaltimer costs a few hundred ns and would
+  // distort what is being measured.  sync() records one (globaltimer, clock64) pair so that the host can put every
+  // CTA's cycle counts on the common ns time base.
   __device__ __forceinline__ void rec(int tile, int ev) {
     if constexpr (kTrace) {
       if (base != nullptr && n < cap) {
-        const unsigned long long t = global_ns();
+        const unsigned long long t = static_cast<unsigned long long>(clock64());
         base[n++] = make_uint4(static_cast<uint32_t>(tile), static_cast<uint32_t>(ev), static_cast<uint32_t>(t),
                                static_cast<uint32_t>(t >> 32));
+      }
+    }
+  }
+  __device__ __forceinline__ void sync() {
+    if constexpr (kTrace) {
+      if (base != nullptr && n + 1 < cap) {
+        const unsigned long long g = global_ns();
+        const unsigned long long c = static_cast<unsigned long long>(clock64());
+        base[n++] = make_uint4(0u, static_cast<uint32_t>(kEvClock), static_cast<uint32_t>(g),
+                               static_cast<uint32_t>(g >> 32));
+        base[n++] = make_uint4(0u, static_cast<uint32_t>(kEvClockCycles), static_cast<uint32_t>(c),
+                               static_cast<uint32_t>(c >> 32));
       }
     }
   }
@@ -150,6 +172,61 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
   }
 }
+
+// sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5, so SiLU costs ONE special-function op (tanh.approx) instead of ex2 + rcp: the
+// epilogue of the first GEMM is otherwise bound by the 16 MUFU results per clock of an SM.  tanh.approx is good to
+// ~2^-11 relative, the result is rounded to bf16 (2^-9) right after.
+__device__ __forceinline__ float silu_fast(float v) {
+  const float hv = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hv));
+  return fmaf(hv, t, hv);
+}
+
+__device__ __forceinline__ float apply_act_fast(float v, int act) {
+  if (act == B200MOE_ACT_SILU) return silu_fast(v);
+  if (act == B200MOE_ACT_RELU) return fmaxf(v, 0.0f);
+  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+}
+
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<const uint16_t*>(&b);
+}
+
+// One boundary element per lane, predicated (direct epilogue: a warp instruction covers 32 consecutive features).
+template <typename T>
+struct ScalarIo;
+template <>
+struct ScalarIo<float> {
+  using raw_t = uint32_t;
+  static __device__ __forceinline__ raw_t load(const float* p, bool pred) { return ptx::ld_global_pred_b32(p, pred); }
+  static __device__ __forceinline__ float to_f(raw_t r) { return __uint_as_float(r); }
+  static __device__ __forceinline__ void store(float* p, float v, bool pred) {
+    ptx::st_global_pred_b32(p, __float_as_uint(v), pred);
+  }
+};
+template <>
+struct ScalarIo<bf16> {
+  using raw_t = uint16_t;
+  static __device__ __forceinline__ raw_t load(const bf16* p, bool pred) { return ptx::ld_global_pred_b16(p, pred); }
+  static __device__ __forceinline__ float to_f(raw_t r) { return __uint_as_float(static_cast<uint32_t>(r) << 16); }
+  static __device__ __forceinline__ void store(bf16* p, float v, bool pred) {
+    ptx::st_global_pred_b16(p, bf16_bits(v), pred);
+  }
+};
+template <>
+struct ScalarIo<__half> {
+  using raw_t = uint16_t;
+  static __device__ __forceinline__ raw_t load(const __half* p, bool pred) { return ptx::ld_global_pred_b16(p, pred); }
+  static __device__ __forceinline__ float to_f(raw_t r) {
+    return __half2float(*reinterpret_cast<const __half*>(&r));
+  }
+  static __device__ __forceinline__ void store(__half* p, float v, bool pred) {
+    const __half h = __float2half_rn(v);
+    ptx::st_global_pred_b16(p, *reinterpret_cast<const uint16_t*>(&h), pred);
+  }
+};
 
 // Four consecutive boundary elements as one vector access (8 B for 16-bit types, 16 B for fp32), predicated so that
 // the code stays branch-free (a C++ `if` around a store makes the compiler sink the value's whole computation into a
@@ -236,8 +313,9 @@ template <typename OutT, bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
            const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const FfnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -250,16 +328,18 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };   // epilogue -> publisher
+  auto pempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + s); };  // publisher -> epilogue
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 8);
   // epilogue staging: one chunk of 32 token columns x 128 features (fp32, or bf16 for h) + per-column routing tables
   const uint32_t stage_off = ((tmem_slot + 16u + 15u) & ~15u) - ptx::smem_u32(smem_raw);
-  float* stg_f = reinterpret_cast<float*>(smem_raw + stage_off);
-  int* s_tok = reinterpret_cast<int*>(smem_raw + stage_off + kStagingBytes);
-  float* s_sc = reinterpret_cast<float*>(smem_raw + stage_off + kStagingBytes + 256 * 4);
+  int* s_tok = reinterpret_cast<int*>(smem_raw + stage_off + 2 * kStagingBytes);
+  float* s_sc = reinterpret_cast<float*>(smem_raw + stage_off + 2 * kStagingBytes + 256 * 4);
   // generic pointer to the tmem slot for reading it back
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
+  if (p.pdl_trigger) ptx::pdl_launch_dependents();  // the next kernel's prologue may overlap this whole kernel
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_w1);
     ptx::prefetch_tensormap(&tm_w2);
@@ -274,6 +354,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
       ptx::mbar_init(tempty_bar(s), kEpiThreads / 32);
+      ptx::mbar_init(pfull_bar(s), kEpiThreads / 32);
+      ptx::mbar_init(pempty_bar(s), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -285,6 +367,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Everything above touched only kernel parameters and on-chip state, so under programmatic dependent launch it
+  // overlaps the tail of the dispatch kernel.  The routing tables, xbuf and every output come after this wait.
+  ptx::pdl_wait();
   const int ng = *p.n_groups;
   const int m1 = p.H / kBlockM;
   const int m2 = p.D / kBlockM;
@@ -300,6 +385,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       uint32_t phase = 0;
       const uint32_t tx_bytes = kAStageBytes + b_stage_bytes;
       Tracer<kTrace> tr(p, 0);
+      tr.sync();
       tr.rec(-1, kEvKernelStart);
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
@@ -309,17 +395,38 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         const CUtensorMap* tm_b = tl.phase == 1 ? &tm_x : &tm_h;
         const int a_row = gr.expert * (tl.phase == 1 ? p.H : p.D) + tl.mb * kBlockM;
         const int nkb = tl.phase == 1 ? kb1 : kb2;
+        int pre = 0;
         if (tl.phase == 2) {
-          // wait until every phase-1 tile of this group has published its slice of h
-          while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1) __nanosleep(40);
+          // The W2 tiles do not depend on h: fill the ring with them first, then wait until every phase-1 tile of this
+          // group has published its slice of h and add the h tiles to the same stages (one full barrier per stage
+          // expects both).
+          pre = nkb < stages ? nkb : stages;
+          const int stage0 = stage;
+          for (int kb = 0; kb < pre; ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+            ptx::tma_load_2d(smem_a + stage * kAStageBytes, tm_a, full_bar(stage), kb * kBlockK, a_row,
+                             p.w_policy);
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1) __nanosleep(32);
           ptx::fence_proxy_async_all();  // generic-proxy writes of h -> async-proxy (TMA) reads
+          int s2 = stage0;
+          for (int kb = 0; kb < pre; ++kb) {
+            ptx::tma_load_2d(smem_b + s2 * b_stage_bytes, tm_b, full_bar(s2), kb * kBlockK, gr.row0,
+                             ptx::kEvictLast);
+            if (++s2 == stages) s2 = 0;
+          }
         }
         tr.rec(t, kEvProdDepOk);
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = pre; kb < nkb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           ptx::tma_load_2d(smem_a + stage * kAStageBytes, tm_a, full_bar(stage), kb * kBlockK, a_row,
-                           ptx::kEvictNormal);
+                           p.w_policy);
           ptx::tma_load_2d(smem_b + stage * b_stage_bytes, tm_b, full_bar(stage), kb * kBlockK, gr.row0,
                            ptx::kEvictLast);
           if (++stage == stages) {
@@ -330,6 +437,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         tr.rec(t, kEvProdIssued);
       }
       tr.rec(-1, kEvKernelEnd);
+      tr.sync();
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (one thread) ============================
@@ -369,21 +477,48 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         tr.rec(t, kEvMmaIssued);
       }
     }
+  } else if (warp == 3) {
+    // ============================ publisher (one thread) ============================
+    // Releasing a phase-1 tile's slice of h at gpu scope waits until the tile's stores have drained to L2, which under
+    // full memory load takes 1-2 us.  It runs here so that the epilogue warps can start on their next tile at once.
+    if (lane == 0) {
+      Tracer<kTrace> tr(p, 3);
+      int k = 0;  // phase-1 tiles of this CTA so far
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(t, ng, lag, m1, m2);
+        if (tl.phase != 1) continue;
+        const int slot = k & 1;
+        ptx::mbar_wait(pfull_bar(slot), (k >> 1) & 1);  // acquire.cta: the four epilogue warps' h stores
+        ptx::fence_proxy_async_all();                   // generic-proxy writes -> the consumers' TMA reads
+        ptx::red_release_gpu_add(p.h_ready + tl.g, 1);
+        ptx::mbar_arrive(pempty_bar(slot));
+        tr.rec(t, kEvEpiPublished);
+        ++k;
+      }
+    }
   } else if (warp >= 4) {
-    // ============================ epilogue (4 warps, one TMEM lane quarter each) ============================
-    // tcgen05.ld gives thread (q, lane) ONE feature and 32 token columns; global memory wants whole token rows.
-    // Each chunk of 32 columns is therefore transposed through shared memory: the feature-major values are written
-    // column by column (conflict-free), then warp q turns columns 8q..8q+7 into row segments of 128 features with
-    // 8/16-byte vector accesses (256 / 512 contiguous bytes per warp instruction).  All global loads of a chunk
-    // (residual rows) are issued before anything depends on them; routing records come from a table filled before
-    // the accumulator wait.  Global memory latency under full HBM load is 1-2 us, so no dependent load chains.
-    const int q = warp & 3;  // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
-    const int et = threadIdx.x - (kThreads - kEpiThreads);
-    const int feat_l = q * 32 + lane;  // feature within the tile owned in the column phase
+    // ============================ epilogue (8 warps = 2 sets x 4 TMEM lane quarters) ============================
+    // tcgen05.ld gives thread (q, lane) ONE feature and 32 token columns, while global memory holds token rows, so each
+    // chunk of 32 columns is transposed through shared memory: the feature-major values are written column by column
+    // (conflict-free, immediate offsets), then warp q of the set turns columns 8q..8q+7 into row segments of 128 features
+    // with 16/8-byte vector accesses.  Set s owns the chunks c with c % 2 == s and has its own staging buffer and named
+    // barrier, so the two sets never wait for each other inside a tile.
+    //
+    // What bounds this code is the instruction issue rate of the four schedulers (a warp-wide FP32 op occupies a
+    // 16-lane pipe for two cycles; measured: ~2.5 cycles per SASS instruction with one warp per scheduler), not memory:
+    // switching every store and residual load off did not change its duration.  Hence: as few instructions per
+    // element as possible (SiLU = fma, tanh, fma), two warps per scheduler, and no per-element address arithmetic.
+    const int q = warp & 3;                 // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
+    const int set = (warp - 4) >> 2;        // 0 or 1
+    const int et = threadIdx.x - 128;       // 0 .. 255
+    const int feat_l = q * 32 + lane;       // feature within the tile owned in the column phase
+    const uint32_t set_bar = 1u + set;
+    uint8_t* stg_raw = smem_raw + stage_off + set * kStagingBytes;
+    float* stg_f = reinterpret_cast<float*>(stg_raw);
     int it = 0;
+    int k1 = 0;  // phase-1 tiles so far (publisher hand-off ring)
     Tracer<kTrace> tr(p, 2);
     const bool tracer_thread = et == 0;
-    bf16* stg_h = reinterpret_cast<bf16*>(stg_f);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const Tile tl = decode_tile(t, ng, lag, m1, m2);
       const GroupRec gr = p.groups[tl.g];
@@ -394,63 +529,76 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       const int nrows = gr.nrows;
       if (tl.phase == 1) {
         const float bias = p.b1 ? p.b1[static_cast<size_t>(gr.expert) * p.H + feat0 + feat_l] : 0.0f;
+        const float hbias = 0.5f * bias;
+        const int act = p.act;
+        const int nst = (p.dbg & 2) ? 0 : nrows;
         ptx::mbar_wait(tfull_bar(as), aphase);
         ptx::tc_fence_after();
         if (tracer_thread) tr.rec(t, kEvEpiAccReady);
-        for (int c0 = 0; c0 < nrows; c0 += 32) {
+        int ci = 0;
+#pragma unroll 1
+        for (int c0 = set * 32; c0 < nrows; c0 += 64, ++ci) {
+          bf16* sb = reinterpret_cast<bf16*>(stg_raw) + (ci & 1) * (32 * kBlockM);  // two 8 KB buffers per set
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + c0, r);
           ptx::tmem_ld_wait();
-          if (c0 + 32 >= nrows) {  // last chunk is in registers: hand the accumulator back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-            if (tracer_thread) tr.rec(t, kEvEpiAccReleased);
-          }
-          if (p.act == B200MOE_ACT_SILU) {
+          if (act == B200MOE_ACT_SILU) {
+            // silu(a + b) with h = (a + b) / 2:  h * tanh(h) + h
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float hv = fmaf(__uint_as_float(r[j]), 0.5f, hbias);
+              float th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hv));
+              sb[j * kBlockM + feat_l] = __float2bfloat16_rn(fmaf(hv, th, hv));
+            }
+          } else if (act == B200MOE_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              stg_h[j * kBlockM + feat_l] =
-                  __float2bfloat16_rn(apply_act(__uint_as_float(r[j]) + bias, B200MOE_ACT_SILU));
-          } else if (p.act == B200MOE_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              stg_h[j * kBlockM + feat_l] =
-                  __float2bfloat16_rn(apply_act(__uint_as_float(r[j]) + bias, B200MOE_ACT_RELU));
+              sb[j * kBlockM + feat_l] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias, 0.0f));
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              stg_h[j * kBlockM + feat_l] =
-                  __float2bfloat16_rn(apply_act(__uint_as_float(r[j]) + bias, B200MOE_ACT_GELU));
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]) + bias;
+              sb[j * kBlockM + feat_l] = __float2bfloat16_rn(0.5f * v * (1.0f + erff(v * 0.70710678118654752f)));
+            }
           }
-          ptx::named_bar_sync(1, kEpiThreads);
+          ptx::named_bar_sync(set_bar, kSetThreads);  // this chunk is staged; the other buffer's readers are done
+          if (tracer_thread) tr.rec(t, kEvEpiChunkStaged);
           // row phase: warp q owns columns 8q .. 8q+7; a half-warp writes one 256-byte row segment of h
           {
             const int half = lane >> 4;
             const int l16 = lane & 15;
+            bf16* hrow = p.hbuf + static_cast<size_t>(gr.row0 + c0 + q * 8 + half) * p.H + feat0 + l16 * 8;
+            const size_t step = 2 * static_cast<size_t>(p.H);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int j = q * 8 + 2 * i + half;
-              const uint4 val = *reinterpret_cast<const uint4*>(stg_h + j * kBlockM + l16 * 8);
-              bf16* dst = p.hbuf + static_cast<size_t>(gr.row0 + c0 + j) * p.H + feat0 + l16 * 8;
-              st_pred_v4(dst, val, c0 + j < nrows);
+              const uint4 val = *reinterpret_cast<const uint4*>(sb + j * kBlockM + l16 * 8);
+              st_pred_v4(hrow + i * step, val, c0 + j < nst);
             }
           }
-          ptx::named_bar_sync(1, kEpiThreads);  // staging buffer free again; all h stores of the chunk issued
         }
-        // publish: every epilogue thread's stores precede the barrier above; one thread releases them at gpu scope
+        // every column this warp owns has left TMEM: hand the accumulator back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
         if (tracer_thread) tr.rec(t, kEvEpiStored);
-        if (et == 0) {
-          ptx::fence_proxy_async_all();
-          ptx::red_release_gpu_add(p.h_ready + tl.g, 1);
-          tr.rec(t, kEvEpiPublished);
+        // hand the tile to the publisher: this warp's stores are ordered before lane 0's arrive (release.cta)
+        if (lane == 0) {
+          const int slot = k1 & 1;
+          ptx::mbar_wait(pempty_bar(slot), ((k1 >> 1) & 1) ^ 1u);
+          ptx::mbar_arrive(pfull_bar(slot));
         }
+        ++k1;
+        ptx::named_bar_sync(set_bar, kSetThreads);  // staging buffers free before the next tile reuses them
       } else {
         const float bias = p.b2 ? p.b2[static_cast<size_t>(gr.expert) * p.D + feat0 + feat_l] : 0.0f;
         OutT* out = static_cast<OutT*>(p.out);
         const OutT* res = static_cast<const OutT*>(p.residual);
-        const bool with_res = p.fused && res != nullptr;
+        const bool with_res = p.fused && res != nullptr && !(p.dbg & 4);
+        const bool st2 = !(p.dbg & 1);
         // routing table of the tile's columns: output row and scale (filled while the MMAs are still running)
+        ptx::named_bar_sync(3, kEpiThreads);  // every warp is done with the previous table
         for (int i = et; i < nrows; i += kEpiThreads) {
           const int row = gr.row0 + i;
           int tok = row;
@@ -462,52 +610,84 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           s_tok[i] = tok;
           s_sc[i] = sc;
         }
+        ptx::named_bar_sync(3, kEpiThreads);  // routing table visible to all epilogue warps
+        using Io = Vec4Io<OutT>;
+        const size_t fo = static_cast<size_t>(feat0 + lane * 4);
+        // Residual rows of this set's first two chunks are requested now, while the MMAs of the tile still run (a global
+        // load under full HBM load takes 1-2 us); the rows of chunk k+2 are requested as soon as chunk k is done.
+        typename Io::raw_t rres[2][8];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int col = (2 * cc + set) * 32 + q * 8 + i;
+            const bool v = col < nrows;
+            const int tok = v ? s_tok[col] : 0;
+            rres[cc][i] = Io::load(res + static_cast<size_t>(tok) * p.D + fo, v && with_res);
+          }
+        }
         ptx::mbar_wait(tfull_bar(as), aphase);
         ptx::tc_fence_after();
         if (tracer_thread) tr.rec(t, kEvEpiAccReady);
-        using Io = Vec4Io<OutT>;
-        for (int c0 = 0; c0 < nrows; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
-          ptx::tmem_ld_wait();
-          if (c0 + 32 >= nrows) {
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-            if (tracer_thread) tr.rec(t, kEvEpiAccReleased);
-          }
+#pragma unroll 1
+        for (int cb = set * 32; cb < nrows; cb += 128) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg_f[j * kBlockM + feat_l] = __uint_as_float(r[j]) + bias;
-          ptx::named_bar_sync(1, kEpiThreads);  // staging (and, for the first chunk, the routing table) complete
-          {
-            // row phase: warp q owns columns 8q .. 8q+7, lane l the 4 features 4l .. 4l+3 of each
-            typename Io::raw_t rres[8];
-            size_t off[8];
-            bool valid[8];
+          for (int cs = 0; cs < 2; ++cs) {  // spelled out twice: the residual registers need static indices
+            const int c0 = cb + cs * 64;
+            if (c0 < nrows) {               // uniform over the set
+              {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+                ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int col = c0 + q * 8 + i;
-              valid[i] = col < nrows;
-              const int tok = valid[i] ? s_tok[col] : 0;
-              off[i] = static_cast<size_t>(tok) * p.D + feat0 + lane * 4;
-              rres[i] = Io::load(res + off[i], valid[i] && with_res);
+                for (int j = 0; j < 32; ++j) stg_f[j * kBlockM + feat_l] = __uint_as_float(r[j]) + bias;
+              }
+              if (tracer_thread) tr.rec(t, kEvEpiChunkLd);
+              ptx::named_bar_sync(set_bar, kSetThreads);  // staging complete
+              if (tracer_thread) tr.rec(t, kEvEpiChunkStaged);
+              // row phase: warp q owns columns 8q .. 8q+7, lane l the 4 features 4l .. 4l+3 of each
+              float4 a[8];
+              float sc[8];
+              size_t ofs[8];
+              bool vv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int j = q * 8 + i;
+                const int col = c0 + j;
+                vv[i] = col < nrows;
+                const int tok = vv[i] ? s_tok[col] : 0;
+                sc[i] = vv[i] ? s_sc[col] : 0.0f;
+                a[i] = *reinterpret_cast<const float4*>(stg_f + j * kBlockM + lane * 4);
+                ofs[i] = static_cast<size_t>(tok) * p.D + fo;
+              }
+              ptx::named_bar_sync(set_bar, kSetThreads);  // staging buffer free again (values are in registers)
+              float o[8][4];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float rv[4];
+                Io::to_f(rres[cs][i], rv);
+                o[i][0] = fmaf(sc[i], a[i].x, rv[0]);
+                o[i][1] = fmaf(sc[i], a[i].y, rv[1]);
+                o[i][2] = fmaf(sc[i], a[i].z, rv[2]);
+                o[i][3] = fmaf(sc[i], a[i].w, rv[3]);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) Io::store(out + ofs[i], o[i], vv[i] && st2);
+              // residual rows of the chunk two steps ahead
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int col = c0 + 128 + q * 8 + i;
+                const bool v = col < nrows;
+                const int tok = v ? s_tok[col] : 0;
+                rres[cs][i] = Io::load(res + static_cast<size_t>(tok) * p.D + fo, v && with_res);
+              }
+              if (tracer_thread) tr.rec(t, kEvEpiChunkDone);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = q * 8 + i;
-              const float4 a = *reinterpret_cast<const float4*>(stg_f + j * kBlockM + lane * 4);
-              const float sc = valid[i] ? s_sc[c0 + j] : 0.0f;
-              float rv[4], o[4];
-              Io::to_f(rres[i], rv);
-              o[0] = fmaf(sc, a.x, rv[0]);
-              o[1] = fmaf(sc, a.y, rv[1]);
-              o[2] = fmaf(sc, a.z, rv[2]);
-              o[3] = fmaf(sc, a.w, rv[3]);
-              Io::store(out + off[i], o, valid[i]);
-            }
           }
-          ptx::named_bar_sync(1, kEpiThreads);  // staging buffer (and routing table) free again
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
         if (tracer_thread) tr.rec(t, kEvEpiStored);
       }
     }
@@ -533,8 +713,8 @@ int stages_for_bn(int bn) {
 }
 
 size_t smem_bytes_for(int bn, int stages) {
-  return 1024 + static_cast<size_t>(stages) * (kAStageBytes + bn * kBlockK * 2) + 8 * (2 * kMaxStages + 4) + 32 +
-         kStagingBytes + 2 * 256 * 4;
+  return static_cast<size_t>(stages) * (kAStageBytes + bn * kBlockK * 2) + 8 * (2 * kMaxStages + 8) + 32 +
+         2 * kStagingBytes + 2 * 256 * 4;
 }
 
 template <typename OutT>
@@ -555,12 +735,13 @@ cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUten
   int grid = num_sms();
   if (tiles_ub < grid) grid = static_cast<int>(tiles_ub);
   if (grid < 1) grid = 1;
+  cudaError_t e;
   if (p.trace != nullptr)
-    ffn_kernel<OutT, true><<<grid, kThreads, smem, stream>>>(tw1, tw2, tx, th, p);
+    e = launch_kernel(ffn_kernel<OutT, true>, dim3(grid), dim3(kThreads), smem, stream, kPdlFfn, tw1, tw2, tx, th, p);
   else
-    ffn_kernel<OutT, false><<<grid, kThreads, smem, stream>>>(tw1, tw2, tx, th, p);
+    e = launch_kernel(ffn_kernel<OutT, false>, dim3(grid), dim3(kThreads), smem, stream, kPdlFfn, tw1, tw2, tx, th, p);
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace
@@ -602,6 +783,17 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   p.act = a.act;
   p.fused = a.fused;
   p.stages = stages_for_bn(a.bn);
+  {
+    static const int dbg = [] {
+      const char* v = std::getenv("B200MOE_DBG");
+      return (v && *v) ? std::atoi(v) : 0;
+    }();
+    p.dbg = dbg;
+    p.pdl_trigger = (pdl_trigger() & kPdlFfn) ? 1 : 0;
+  }
+  // about one token tile per expert: every weight tile is read exactly once, so it can leave L2 right after
+  p.w_policy = (static_cast<long long>(a.n_rows) <= static_cast<long long>(a.E) * a.bn) ? ptx::kEvictFirst
+                                                                                      : ptx::kEvictNormal;
   p.trace = static_cast<uint4*>(g_trace_buf);
   p.trace_cap = g_trace_cap;
   // phase-2 tiles trail their group's phase-1 tiles by ~3 waves of the grid

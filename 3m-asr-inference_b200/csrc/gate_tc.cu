@@ -39,7 +39,31 @@ struct GateTcParams {
   float* score;
   int* hist32;  // [ceil(S/32), E] per-32-token expert counts, or null
   int S, T, D, Demb, E, top_k, gate_mode;
+  // optional DRAM -> L2 prefetch of the layer's expert weights, spread over all CTAs (the gate itself moves ~2 KiB per
+  // token, so HBM is otherwise idle while the gate and the dispatch run)
+  const uint8_t* pf_ptr[2];
+  unsigned long long pf_bytes[2];
+  int pdl_trigger;
+  int pf_mode;  // 0 off, 1 before the dependency wait (weights are constants), 2 after it
 };
+
+constexpr unsigned kPfChunk = 16384;
+
+__device__ __forceinline__ void prefetch_weights(const GateTcParams& p, int lane) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const unsigned long long n = p.pf_bytes[r];
+    if (p.pf_ptr[r] == nullptr || n == 0) continue;
+    const unsigned long long nchunks = (n + kPfChunk - 1) / kPfChunk;
+    for (unsigned long long c = static_cast<unsigned long long>(blockIdx.x) * 32 + lane; c < nchunks;
+         c += static_cast<unsigned long long>(gridDim.x) * 32) {
+      const unsigned long long off = c * kPfChunk;
+      const unsigned long long left = n - off;
+      const unsigned bytes = left < kPfChunk ? static_cast<unsigned>(left & ~15ull) : kPfChunk;
+      if (bytes) ptx::prefetch_l2_bulk(p.pf_ptr[r] + off, bytes);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreadsG, 1)
 gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_e,
@@ -61,11 +85,13 @@ gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   float* s_br = reinterpret_cast<float*>(smem_raw + misc_off);            // [32]
   int* s_hist = reinterpret_cast<int*>(smem_raw + misc_off + 32 * 4);     // [4][32]
 
+  if (p.pdl_trigger) ptx::pdl_launch_dependents();  // dispatch may start its prologue; it blocks in its pdl_wait()
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_x);
     ptx::prefetch_tensormap(&tm_e);
     ptx::prefetch_tensormap(&tm_w);
   }
+  if (warp == 3 && p.pf_mode == 1) prefetch_weights(p, lane);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStagesG; ++s) {
       ptx::mbar_init(full_bar(s), 1);
@@ -88,10 +114,15 @@ gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const int kb_e = p.Demb / kBlkK;
   const int nkb = (p.Demb + p.D) / kBlkK;
 
+  if (warp == 3 && p.pf_mode == 2) {
+    ptx::pdl_wait();
+    prefetch_weights(p, lane);
+  }
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      ptx::pdl_wait();  // x is the previous layer's output; idx / score / hist32 may still be read by its kernels
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -142,6 +173,7 @@ gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   } else if (warp >= 4) {
     const int q = warp & 3;
     int it = 0;
+    ptx::pdl_wait();
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -273,7 +305,8 @@ cudaError_t launch_pack_router(const float* Wr, int R, int E, void* packed, cuda
 
 cudaError_t launch_gate_tc(const void* x, const void* embed, const void* wr_packed, const float* br, const int* x_len,
                            int B, int T, int D, int Demb, int E, int top_k, int gate_mode, int* idx, float* score,
-                           int* hist32, cudaStream_t stream) {
+                           int* hist32, const void* pf0, size_t pf0_bytes, const void* pf1, size_t pf1_bytes,
+                           cudaStream_t stream) {
   const int S = B * T;
   if (S == 0) return cudaSuccess;
   if (embed == nullptr) Demb = 0;
@@ -307,10 +340,22 @@ cudaError_t launch_gate_tc(const void* x, const void* embed, const void* wr_pack
     attr_set = true;
   }
   const int n_tiles = (S + kTokTile - 1) / kTokTile;
-  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-  gate_tc_kernel<<<grid, kThreadsG, smem, stream>>>(tx, te, tw, p);
+  int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  p.pf_mode = 0;
+  p.pdl_trigger = (pdl_trigger() & kPdlGate) ? 1 : 0;
+  p.pf_ptr[0] = p.pf_ptr[1] = nullptr;
+  p.pf_bytes[0] = p.pf_bytes[1] = 0;
+  if (prefetch_mode() != 0 && (pf0 != nullptr || pf1 != nullptr)) {
+    p.pf_mode = prefetch_mode() == 2 ? 2 : 1;
+    p.pf_ptr[0] = static_cast<const uint8_t*>(pf0);
+    p.pf_bytes[0] = pf0 ? pf0_bytes : 0;
+    p.pf_ptr[1] = static_cast<const uint8_t*>(pf1);
+    p.pf_bytes[1] = pf1 ? pf1_bytes : 0;
+    grid = num_sms();  // CTAs without a token tile only prefetch
+  }
+  cudaError_t e = launch_kernel(gate_tc_kernel, dim3(grid), dim3(kThreadsG), smem, stream, kPdlGate, tx, te, tw, p);
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace b200moe
