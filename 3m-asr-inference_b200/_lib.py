@@ -50,6 +50,18 @@ SIGNATURES = {
     "b200moe_expert_ffn": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200moe_combine": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]),
     "b200moe_forward": (_i, [C.POINTER(LayerArgs), _vp, _sz, _vp]),
+    "b200moe_ep_buffer_bytes": (_sz, [_i, _i, _i, _i]),
+    "b200moe_ep_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "b200moe_ep_free": (_i, [_vp]),
+    "b200moe_ep_ipc_export": (_i, [_vp, _vp]),
+    "b200moe_ep_ipc_open": (_i, [_vp, C.POINTER(_vp)]),
+    "b200moe_ep_ipc_close": (_i, [_vp]),
+    "b200moe_ep_create": (_vp, [_i, _i, _i, _i, _i, C.POINTER(_vp), _i]),
+    "b200moe_ep_destroy": (None, [_vp]),
+    "b200moe_ep_workspace_bytes": (_sz, [_vp, _i]),
+    "b200moe_ep_forward": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _vp]),
+    "b200moe_ep_forward_stages": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _i, _vp]),
+    "b200moe_ep_status": (_i, [_vp, C.POINTER(_i)]),
     "b200moe_plugin_create": (_vp, [_i, _i, _i, _i, _i]),
     "b200moe_plugin_clone": (_vp, [_vp]),
     "b200moe_plugin_serialization_size": (_sz, [_vp]),

@@ -400,6 +400,201 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   return B200MOE_OK;
 }
 
+// ---- expert parallelism over peer-mapped memory ------------------------------------------------------------------
+
+struct b200moe_ep_ctx {
+  EpPeers peers;
+};
+
+size_t b200moe_ep_buffer_bytes(int world, int E_local, int D, int cap) {
+  if (world < 1 || world > kMaxEpWorld || E_local < 1 || D < 1 || cap < 1) return 0;
+  return ep_layout(world, E_local, D, cap).bytes;
+}
+
+int b200moe_ep_alloc(size_t bytes, void** dev_ptr) {
+  if (!dev_ptr || bytes == 0) return fail(B200MOE_ERR_ARG, "ep_alloc: bad argument");
+  // cudaMalloc (not a pool or VMM allocation) so that the buffer can be exported with cudaIpcGetMemHandle
+  cudaError_t e = cudaMalloc(dev_ptr, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "ep_alloc/cudaMalloc");
+  e = cudaMemset(*dev_ptr, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cuda_fail(e, "ep_alloc/cudaMemset");
+  return B200MOE_OK;
+}
+
+int b200moe_ep_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "ep_free");
+  return B200MOE_OK;
+}
+
+int b200moe_ep_ipc_export(void* dev_ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  if (!dev_ptr || !handle64) return fail(B200MOE_ERR_ARG, "ep_ipc_export: null pointer");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, dev_ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "ep_ipc_export");
+  std::memcpy(handle64, &h, sizeof(h));
+  return B200MOE_OK;
+}
+
+int b200moe_ep_ipc_open(const void* handle64, void** peer_ptr) {
+  if (!handle64 || !peer_ptr) return fail(B200MOE_ERR_ARG, "ep_ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "ep_ipc_open");
+  return B200MOE_OK;
+}
+
+int b200moe_ep_ipc_close(void* peer_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "ep_ipc_close");
+  return B200MOE_OK;
+}
+
+b200moe_ep_ctx* b200moe_ep_create(int rank, int world, int E_local, int D, int cap, void* const* bufs,
+                                  int timeout_ms) {
+  if (world < 1 || world > kMaxEpWorld || rank < 0 || rank >= world || E_local < 1 ||
+      E_local * world > kMaxExperts || D < 8 || D % 8 != 0 || cap < 1 || !bufs) {
+    fail(B200MOE_ERR_ARG, "ep_create: bad argument (world <= %d, E_local * world <= %d)", kMaxEpWorld, kMaxExperts);
+    return nullptr;
+  }
+  for (int r = 0; r < world; ++r)
+    if (!bufs[r]) {
+      fail(B200MOE_ERR_ARG, "ep_create: null buffer for rank %d", r);
+      return nullptr;
+    }
+  b200moe_ep_ctx* c = new (std::nothrow) b200moe_ep_ctx();
+  if (!c) return nullptr;
+  std::memset(&c->peers, 0, sizeof(c->peers));
+  c->peers.rank = rank;
+  c->peers.world = world;
+  c->peers.E_local = E_local;
+  c->peers.cap = cap;
+  c->peers.D = D;
+  c->peers.timeout_ms = timeout_ms > 0 ? timeout_ms : 2000;
+  c->peers.lay = ep_layout(world, E_local, D, cap);
+  for (int r = 0; r < world; ++r) c->peers.base[r] = static_cast<uint8_t*>(bufs[r]);
+  return c;
+}
+
+void b200moe_ep_destroy(b200moe_ep_ctx* c) { delete c; }
+
+size_t b200moe_ep_workspace_bytes(const b200moe_ep_ctx* c, int H) {
+  if (!c || H < 0) return 0;
+  const EpPeers& p = c->peers;
+  return carve_workspace(nullptr, p.world * p.cap, p.E_local * p.world, p.D, H, 1).bytes;
+}
+
+int b200moe_ep_status(const b200moe_ep_ctx* c, int* host_status) {
+  if (!c || !host_status) return fail(B200MOE_ERR_ARG, "ep_status: null pointer");
+  const EpPeers& p = c->peers;
+  int ctrl[4];
+  cudaError_t e = cudaMemcpy(ctrl, p.base[p.rank] + p.lay.ctrl, sizeof(ctrl), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "ep_status");
+  *host_status = ctrl[3];
+  return B200MOE_OK;
+}
+
+int b200moe_ep_forward(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes,
+                       cudaStream_t stream) {
+  return b200moe_ep_forward_stages(c, a, ws, ws_bytes, 7, stream);
+}
+
+int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes, int stages,
+                              cudaStream_t stream) {
+  if (!c || !a) return fail(B200MOE_ERR_ARG, "ep_forward: null argument");
+  const EpPeers& ep = c->peers;
+  const int S = a->B * a->T;
+  const int E_total = ep.E_local * ep.world;
+  if (a->B < 0 || a->T < 0) return fail(B200MOE_ERR_ARG, "ep_forward: bad B/T");
+  if (a->E != E_total) return fail(B200MOE_ERR_ARG, "ep_forward: router has E=%d, context has %d x %d", a->E, ep.E_local, ep.world);
+  if (a->D != ep.D) return fail(B200MOE_ERR_ARG, "ep_forward: D=%d, context has %d", a->D, ep.D);
+  if (a->D % 128 != 0 || a->H % 128 != 0)
+    return fail(B200MOE_ERR_ARG, "ep_forward: D=%d and H=%d must be multiples of 128", a->D, a->H);
+  if (a->dtype != B200MOE_BF16) return fail(B200MOE_ERR_ARG, "ep_forward: activations must be bf16");
+  if (a->top_k < 1 || a->top_k > 8 || a->top_k > a->E) return fail(B200MOE_ERR_ARG, "ep_forward: bad top_k %d", a->top_k);
+  if (a->gate_mode == B200MOE_GATE_3M && a->top_k != 1) return fail(B200MOE_ERR_ARG, "ep_forward: the 3M router is top-1");
+  if (a->act_type < 0 || a->act_type > 2) return fail(B200MOE_ERR_ARG, "ep_forward: bad act_type %d", a->act_type);
+  const int Sk = S * a->top_k;
+  if (Sk > ep.cap) return fail(B200MOE_ERR_ARG, "ep_forward: %d entries exceed the context capacity %d", Sk, ep.cap);
+  if ((S > 0 && (!a->x || !a->out)) || (!a->Wr && !a->Wr_packed) || !a->W1 || !a->W2 || !ws)
+    return fail(B200MOE_ERR_ARG, "ep_forward: null pointer");
+  const int Demb = a->embed ? a->Demb : 0;
+  if (!a->Wr && !gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype))
+    return fail(B200MOE_ERR_ARG, "ep_forward: this shape needs the fp32 router (Wr)");
+  const int rows_cap = ep.world * ep.cap;
+  RouteWs w = carve_workspace(ws, rows_cap, E_total, a->D, a->H, 1);
+  if (ws_bytes < w.bytes)
+    return fail(B200MOE_ERR_WORKSPACE, "ep_forward: workspace %zu B < required %zu B", ws_bytes, w.bytes);
+  int* idx = a->idx_out ? a->idx_out : w.idx;
+  float* score = a->score_out ? a->score_out : w.score;
+
+  cudaError_t e = cudaSuccess;
+  const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
+  if (S > 0 && (stages & 1)) {
+    StageScope t(0, stream);
+    if (tc_gate)
+      e = launch_gate_tc(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
+                         a->gate_mode, idx, score, w.hist32, nullptr, 0, nullptr, 0, stream);
+    else
+      e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k, a->gate_mode,
+                      a->dtype, idx, score, stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/gate");
+
+  const int bn = choose_bn(Sk, E_total);
+  const int gmax = max_groups(rows_cap, E_total, bn);
+  if (stages & 1) {
+    StageScope t(1, stream);
+    e = launch_dispatch(a->x, idx, nullptr, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
+                        a->mapping_out, w.xbuf, nullptr, nullptr, tc_gate && S > 0 ? w.hist32 : nullptr, stream, &ep);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/dispatch");
+  if (stages & 2) {
+    StageScope t(1, stream);
+    e = launch_ep_wait_build(ep, bn, w.groups, w.n_groups, w.h_ready, gmax, stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/wait_build");
+
+  FfnLaunch f{};
+  f.xbuf = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.recv_x);
+  f.hbuf = static_cast<bf16*>(w.hbuf);
+  f.W1 = static_cast<const bf16*>(a->W1);
+  f.W2 = static_cast<const bf16*>(a->W2);
+  f.b1 = a->b1;
+  f.b2 = a->b2;
+  f.groups = w.groups;
+  f.n_groups = w.n_groups;
+  f.h_ready = w.h_ready;
+  f.n_rows = rows_cap;
+  f.E = ep.E_local;
+  f.D = a->D;
+  f.H = a->H;
+  f.bn = bn;
+  f.act = a->act_type;
+  f.gmax = gmax;
+  f.fused = 0;
+  f.out_dtype = B200MOE_BF16;
+  f.out = ep.base[ep.rank] + ep.lay.ret_y;
+  f.top_k = 1;
+  f.ff_scale = 1.0f;
+  f.ep = &ep;
+  if (stages & 2) {
+    StageScope t(2, stream);
+    e = launch_ffn(f, stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/expert_ffn");
+  if (stages & 4) {
+    StageScope t(3, stream);
+    e = launch_ep_combine(ep, w.mapping, a->keep_expert_output ? nullptr : score, a->residual, a->ff_scale, S, a->D,
+                          a->top_k, a->out, stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/combine");
+  return B200MOE_OK;
+}
+
 // ---- plugin mirror ----------------------------------------------------------------------------------------------
 
 b200moe_plugin* b200moe_plugin_create(int data_type, int num_expert, int idim, int hidden_units, int act_type) {

@@ -19,12 +19,57 @@ constexpr int kMaxExperts = 256;      // smem tables in gate/dispatch are sized 
 constexpr int kDispatchThreads = 256;  // 8 warps per dispatch CTA
 constexpr int kMaxChunks = 296;        // 2 x 148 dispatch chunks at most (make_chunking divides by this)
 
-// One GEMM "group" = one expert x one tile of <= BN of its tokens. {expert, first row, rows, unused}
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// One GEMM "group" = one expert x one tile of <= BN of its tokens.
 struct GroupRec {
-  int expert;
-  int row0;
-  int nrows;
-  int pad;
+  int expert;  // (local) expert whose weights the group uses
+  int row0;    // first row of the group in xbuf / hbuf
+  int nrows;   // 1 .. BN
+  int src;     // expert parallelism: rank the rows came from (selects the output buffer); else 0
+  int orow0;   // expert parallelism: first output row in the source rank's return buffer; else == row0
+  int pad[3];
+};
+
+// ---- expert parallelism over peer-mapped memory (ep.cu) -------------------------------------------------------
+constexpr int kMaxEpWorld = 8;
+
+// Byte offsets inside the symmetric buffer every rank allocates (identical on all ranks).
+struct EpLayout {
+  size_t ctrl;       // int32[16]: [0] seq (layer calls so far), [1] dispatch CTAs done, [2] FFN CTAs done, [3] error
+  size_t disp_flag;  // int32[kMaxEpWorld]: disp_flag[s] = seq of the last dispatch whose rows from rank s have landed
+  size_t ret_flag;   // int32[kMaxEpWorld]: ret_flag[r] = seq of the last layer whose results from expert rank r landed
+  size_t recv_cnt;   // int32[kMaxEpWorld][E_local + 1]: rows per local expert from rank s; [E_local] = first row of
+                     //   this rank's segment in rank s's expert-ordered entries
+  size_t recv_x;     // bf16 [world][cap][D]: rows from rank s, ordered by local expert (stable inside an expert)
+  size_t ret_y;      // bf16 [cap][D]: expert outputs for this rank's own entries, in its expert order
+  size_t bytes;
+};
+
+inline EpLayout ep_layout(int world, int E_local, int D, int cap) {
+  EpLayout l;
+  size_t off = 0;
+  auto take = [&](size_t b) {
+    size_t o = off;
+    off = align_up(off + b, 1024);
+    return o;
+  };
+  l.ctrl = take(sizeof(int) * 16);
+  l.disp_flag = take(sizeof(int) * kMaxEpWorld);
+  l.ret_flag = take(sizeof(int) * kMaxEpWorld);
+  l.recv_cnt = take(sizeof(int) * kMaxEpWorld * (E_local + 1));
+  l.recv_x = take(sizeof(bf16) * static_cast<size_t>(world) * cap * D);
+  l.ret_y = take(sizeof(bf16) * static_cast<size_t>(cap) * D);
+  l.bytes = off;
+  return l;
+}
+
+// Passed by value to the kernels: where every rank's symmetric buffer is mapped in THIS process.
+struct EpPeers {
+  int rank, world, E_local, cap, D;
+  int timeout_ms;            // spins on remote flags give up after this long and raise ctrl[3]
+  uint8_t* base[kMaxEpWorld];  // base[rank] is the local buffer
+  EpLayout lay;
 };
 
 // Device-side routing state produced by dispatch and consumed by the FFN kernel. Lives in the workspace.
@@ -46,8 +91,6 @@ struct RouteWs {
   void* ybuf;        // [Sk, D]  staging for the un-fused combine (top_k > 1)
   size_t bytes;
 };
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 inline int max_groups(int Sk, int E, int bn) { return (Sk + bn - 1) / bn + E; }
 
@@ -107,7 +150,7 @@ cudaError_t launch_softmax_topk(const void* logits, const int* mask, int B, int 
 cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
-                            const int* hist32, cudaStream_t stream);
+                            const int* hist32, cudaStream_t stream, const EpPeers* ep = nullptr);
 constexpr int kMaxHistRows = 512;  // above this many 32-token rows the scatter CTAs would re-read too much
 // Builds only the group table (+ zeroes the flags) from an existing offsets array.
 cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
@@ -136,10 +179,20 @@ struct FfnLaunch {
   const float* row_score;  // null => 1
   float ff_scale;
   int top_k;
+  const EpPeers* ep;  // expert parallelism (un-fused only): rows of group g go to rank g.src's return buffer
 };
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
 // Debug timeline: every following ffn launch records per-CTA events into dev_buf (16 B records); null disables.
 void set_ffn_trace(void* dev_buf, int records_per_cta);
+
+// ep.cu
+// Waits until every rank's rows of the current layer call have landed, then builds the FFN group table over the receive
+// buffer (expert-major, source rank inside an expert) and clears the h flags.
+cudaError_t launch_ep_wait_build(const EpPeers& ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax,
+                                 cudaStream_t stream);
+// Waits until every expert rank has returned this rank's rows, then out = residual + ff_scale * sum_k score * ret_y[mapping].
+cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float* score, const void* residual,
+                              float ff_scale, int S, int D, int top_k, void* out, cudaStream_t stream);
 
 // combine.cu
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,

@@ -116,14 +116,21 @@ __device__ void build_groups_block(const int* offsets_sm /*[E+1] in smem or glob
       r.expert = e;
       r.row0 = offsets_sm[e] + j * bn;
       r.nrows = min(bn, c - j * bn);
-      r.pad = 0;
+      r.src = 0;
+      r.orow0 = r.row0;
+      r.pad[0] = r.pad[1] = r.pad[2] = 0;
       groups[g0 + j] = r;
     }
   }
   for (int g = threadIdx.x; g < gmax; g += blockDim.x) h_ready[g] = 0;
 }
 
-template <typename InT>
+// kEp: expert parallelism.  Rows are pushed straight into the destination rank's receive buffer over peer-mapped
+// memory (NVLink): expert e lives on rank e / E_local, and this rank's rows for that rank land, ordered by local expert,
+// at recv_x[my rank][mapping - offsets[first expert of that rank]].  The last CTA to finish then writes the per-expert
+// counts into every peer and raises its arrival flag with a system-scope release (the reference does this with two
+// NCCL all-to-alls and a host round trip: trainer_3m_fix/fmoe/functions.py:37-50,74-80).
+template <typename InT, bool kEp>
 __global__ void __launch_bounds__(kDispatchThreads)
 dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, const float* __restrict__ score,
                         int Sk, int D, int E, int top_k, int chunk, int nchunks,
@@ -131,7 +138,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
                         int* __restrict__ offsets, int* __restrict__ mapping, int* __restrict__ pos,
                         float* __restrict__ row_score, bf16* __restrict__ xbuf, GroupRec* groups, int* n_groups,
                         int* h_ready, int* counts_out, int* offsets_out, int* mapping_out, InT* __restrict__ drop_out,
-                        const InT* __restrict__ drop_residual, int early_trigger) {
+                        const InT* __restrict__ drop_residual, int early_trigger, const EpPeers ep) {
   constexpr int kWarps = kDispatchThreads / 32;
   constexpr int kRowsPerBatch = 4;            // rows a warp keeps in flight during the copy
   constexpr int kMaxParts = 8;
@@ -145,6 +152,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   int* s_dst = s_scratch + E + 1;             // [kDispatchThreads] destination row of each entry of the segment
   int* s_wcnt = s_dst + kDispatchThreads;     // [kWarps][E] per-warp counts of the current segment
   int* s_part = s_wcnt + kWarps * E;          // [nparts][2][E] partial column sums (before / total)
+  int* s_exp = s_part + kMaxParts * 2 * E;    // [kDispatchThreads] expert of each entry of the segment (kEp)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -218,6 +226,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
       dst = base + __popc(peers & ((1u << lane) - 1u));
     }
     s_dst[threadIdx.x] = dst;
+    if (kEp) s_exp[threadIdx.x] = e;
     if (static_cast<int>(threadIdx.x) < n) {
       mapping[i] = dst;
       if (mapping_out) mapping_out[i] = dst;
@@ -245,6 +254,18 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
         d[r] = j < n ? s_dst[j] : -1;
         src[r] = x + static_cast<size_t>((seg + (j < n ? j : 0)) / top_k) * D;
       }
+      bf16* drow[kRowsPerBatch];
+#pragma unroll
+      for (int r = 0; r < kRowsPerBatch; ++r) {
+        drow[r] = xbuf + static_cast<size_t>(d[r] < 0 ? 0 : d[r]) * D;
+        if (kEp && d[r] >= 0) {
+          const int j = j0 + r * kWarps;
+          const int dest = s_exp[j] / ep.E_local;
+          const int slot = d[r] - s_off[dest * ep.E_local];
+          drow[r] = reinterpret_cast<bf16*>(ep.base[dest] + ep.lay.recv_x) +
+                    (static_cast<size_t>(ep.rank) * ep.cap + slot) * D;
+        }
+      }
       for (int v = lane; v < D / 8; v += 32) {
         uint4 regs[kRowsPerBatch];
 #pragma unroll
@@ -252,7 +273,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
           if (d[r] >= 0) regs[r] = load8_as_bf16<InT>(src[r] + v * 8);
 #pragma unroll
         for (int r = 0; r < kRowsPerBatch; ++r)
-          if (d[r] >= 0) reinterpret_cast<uint4*>(xbuf + static_cast<size_t>(d[r]) * D)[v] = regs[r];
+          if (d[r] >= 0) reinterpret_cast<uint4*>(drow[r])[v] = regs[r];
       }
       if (drop_out != nullptr) {
         // dropped tokens (padding / invalid expert): output row = residual row (or zero)
@@ -280,7 +301,42 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
       offsets[e] = s_off[e];
       if (offsets_out) offsets_out[e] = s_off[e];
     }
-    build_groups_block(s_off, E, bn, groups, n_groups, h_ready, gmax, s_scratch);
+    if (!kEp) build_groups_block(s_off, E, bn, groups, n_groups, h_ready, gmax, s_scratch);
+  }
+
+  if (kEp) {
+    // Completion: every CTA makes its pushed rows visible system-wide, the last one tells the peers.
+    __syncthreads();
+    __shared__ int s_last;
+    int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
+    if (threadIdx.x == 0) {
+      ptx::fence_acq_rel_sys();
+      const int prev = atomicAdd(&ctrl[1], 1);
+      s_last = prev == static_cast<int>(gridDim.x) - 1;
+      if (s_last) ptx::fence_acq_rel_sys();  // acquire side: the other CTAs' pushes happen-before the flags below
+    }
+    __syncthreads();
+    if (s_last) {
+      const int seq = ctrl[0] + 1;
+      const int El = ep.E_local;
+      // counts (and the base row of the destination's segment) into every peer's recv_cnt[my rank][...]
+      for (int i = threadIdx.x; i < ep.world * (El + 1); i += blockDim.x) {
+        const int dest = i / (El + 1);
+        const int k = i - dest * (El + 1);
+        int* rc = reinterpret_cast<int*>(ep.base[dest] + ep.lay.recv_cnt) + ep.rank * (El + 1);
+        rc[k] = k < El ? s_total[dest * El + k] : s_off[dest * El];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ptx::fence_acq_rel_sys();
+        ctrl[1] = 0;
+        ctrl[0] = seq;
+        ptx::fence_acq_rel_sys();
+      }
+      __syncthreads();
+      if (threadIdx.x < ep.world)
+        ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, seq);
+    }
   }
 }
 
@@ -309,12 +365,13 @@ int choose_bn(int Sk, int E) {
 cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
-                            const int* hist32, cudaStream_t stream) {
+                            const int* hist32, cudaStream_t stream, const EpPeers* ep) {
   const int Sk = S * top_k;
-  if (top_k != 1) drop_out = nullptr;
+  if (top_k != 1 || ep != nullptr) drop_out = nullptr;
+  if (ep != nullptr && (ep->world * ep->E_local != E || Sk > ep->cap || ep->D != D)) return cudaErrorInvalidValue;
   if (E > kMaxExperts || E < 1 || D % 8 != 0) return cudaErrorInvalidValue;
   const int gmax = max_groups(Sk, E, bn);
-  if (Sk == 0) {
+  if (Sk == 0 && ep == nullptr) {
     // nothing to route: still publish zero counts / offsets and an empty group table
     cudaError_t e = cudaMemsetAsync(ws.counts, 0, sizeof(int) * E, stream);
     if (e != cudaSuccess) return e;
@@ -341,16 +398,23 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
   }
   const int nparts_max = 8;
   const size_t dyn = sizeof(int) * (2 * E + 2 * (E + 1) + kDispatchThreads + (kDispatchThreads / 32) * E +
-                                    nparts_max * 2 * E);
+                                    nparts_max * 2 * E + kDispatchThreads);
   cudaError_t lerr = cudaSuccess;
-#define B200MOE_SCATTER(T)                                                                                        \
-  lerr = launch_kernel(dispatch_scatter_kernel<T>, dim3(ck.nchunks), dim3(kDispatchThreads), dyn, stream,          \
+  EpPeers epv{};
+  if (ep) epv = *ep;
+#define B200MOE_SCATTER_K(T, EP)                                                                                  \
+  lerr = launch_kernel(dispatch_scatter_kernel<T, EP>, dim3(ck.nchunks), dim3(kDispatchThreads), dyn, stream,     \
       kPdlDispatch,                                                                                               \
       static_cast<const T*>(x), idx, score, Sk, D, E, top_k, ck.chunk, ck.nchunks, hist, hist_rows,               \
       rows_per_chunk, bn, gmax,                                                                                   \
       ws.counts, ws.offsets, ws.mapping, ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready,          \
-      counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual),   \
-      (pdl_trigger() & kPdlDispatch) ? 1 : 0)
+      counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual),      \
+      (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv)
+#define B200MOE_SCATTER(T)          \
+  if (ep)                           \
+    B200MOE_SCATTER_K(T, true);     \
+  else                              \
+    B200MOE_SCATTER_K(T, false)
   switch (dtype) {
     case B200MOE_F32:
       B200MOE_SCATTER(float);
@@ -365,6 +429,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
       return cudaErrorInvalidValue;
   }
 #undef B200MOE_SCATTER
+#undef B200MOE_SCATTER_K
   count_launch();
   return lerr;
 }

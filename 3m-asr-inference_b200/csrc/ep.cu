@@ -1,0 +1,174 @@
+// Expert parallelism over peer-mapped memory: experts are partitioned contiguously over the GPUs of one NVLink / NVSwitch
+// domain (expert e on rank e / E_local, the reference's layout: trainer_3m_fix/model/..._hier.py:259-273), tokens stay
+// data-parallel, and rows travel by plain stores into the destination GPU's memory.
+//
+// Reference behaviour replaced (trainer_3m_fix/fmoe/functions.py):
+//   :37-44   fmoe_cuda.expert_exchange   all-to-all of per-expert counts      -> counts stored into the peers by the
+//                                                                               dispatch kernel's last CTA
+//   :48-50   .cpu() of the counts        host synchronisation                 -> none: counts are only read on the device
+//   :74-80   fmoe_cuda.global_scatter    all-to-all-v of token rows           -> dispatch_scatter_kernel<.., kEp = true>
+//                                                                               pushes rows into recv_x of the owner rank
+//   :185-191 fmoe_cuda.global_gather     all-to-all-v of expert outputs       -> the FFN kernel's second-GEMM epilogue
+//                                                                               stores rows into ret_y of the source rank
+// Per layer and rank: gate -> dispatch (push) -> ep_wait_build -> expert FFN (push back) -> ep_combine.  Every wait is a
+// spin on a flag in LOCAL memory that a peer raises with st.release.sys after its data; flags carry the layer sequence
+// number, so nothing is ever reset across ranks.  One receive buffer suffices: a rank can only start pushing layer L+1
+// after its combine of layer L, which needed every peer's "rows are back" flag, which a peer raises at the very end of
+// its FFN kernel, i.e. after its last read of the receive buffer.
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200moe {
+
+namespace {
+
+constexpr int kErrDispatchTimeout = 1;
+constexpr int kErrReturnTimeout = 2;
+
+// Spin until *flag >= want (acquire, system scope) or the deadline passes. Returns false on timeout.
+__device__ __forceinline__ bool wait_flag_sys(const int* flag, int want, unsigned long long deadline_ns) {
+  while (ptx::ld_acquire_sys(flag) < want) {
+    __nanosleep(64);
+    if (ptx::globaltimer_ns() > deadline_ns) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+ep_wait_build_kernel(const EpPeers ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax) {
+  __shared__ int s_cnt[kMaxEpWorld][kMaxExperts + 1];
+  __shared__ int s_g0[kMaxExperts * kMaxEpWorld + 1];  // first group of (expert, source), expert-major
+  int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
+  const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.disp_flag);
+  const int W = ep.world, El = ep.E_local;
+  const int seq = ctrl[0];  // set by this rank's own dispatch kernel, which precedes this kernel in the stream
+  if (threadIdx.x < W) {
+    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
+    if (!wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kErrDispatchTimeout);
+  }
+  __syncthreads();
+  const int* rc = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.recv_cnt);
+  for (int i = threadIdx.x; i < W * (El + 1); i += blockDim.x) s_cnt[i / (El + 1)][i % (El + 1)] = rc[i];
+  __syncthreads();
+  if (ctrl[3] != 0) {  // a peer never showed up: run the rest of the layer over nothing rather than over garbage
+    for (int i = threadIdx.x; i < W * (El + 1); i += blockDim.x) s_cnt[i / (El + 1)][i % (El + 1)] = 0;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < El; ++e)
+      for (int s = 0; s < W; ++s) {
+        s_g0[e * W + s] = acc;
+        acc += (s_cnt[s][e] + bn - 1) / bn;
+      }
+    s_g0[El * W] = acc;
+    n_groups[0] = acc < gmax ? acc : gmax;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < El * W; i += blockDim.x) {
+    const int e = i / W, s = i - e * W;
+    const int c = s_cnt[s][e];
+    int off = 0;  // rows of source s that precede expert e in its segment
+    for (int k = 0; k < e; ++k) off += s_cnt[s][k];
+    const int nt = (c + bn - 1) / bn;
+    const int g0 = s_g0[i];
+    for (int j = 0; j < nt && g0 + j < gmax; ++j) {
+      GroupRec r;
+      r.expert = e;
+      r.row0 = s * ep.cap + off + j * bn;
+      r.nrows = min(bn, c - j * bn);
+      r.src = s;
+      r.orow0 = s_cnt[s][El] + off + j * bn;  // row in rank s's own expert-ordered entries
+      r.pad[0] = r.pad[1] = r.pad[2] = 0;
+      groups[g0 + j] = r;
+    }
+  }
+  for (int g = threadIdx.x; g < gmax; g += blockDim.x) h_ready[g] = 0;
+}
+
+__device__ __forceinline__ void bf16x8_to_f(const uint4& v, float (&o)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = __uint_as_float(w[i] << 16);
+    o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// One warp per token row.  ret_y was written by other GPUs during this kernel's lifetime at the latest, so it is read
+// with ordinary (L2-coherent) loads after the acquire, never through the read-only path.
+__global__ void __launch_bounds__(256)
+ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float* __restrict__ score,
+                  const bf16* __restrict__ residual, float ff_scale, int S, int D, int top_k, bf16* __restrict__ out) {
+  int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
+  const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ret_flag);
+  if (threadIdx.x < ep.world) {
+    const int seq = ctrl[0];
+    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
+    if (!wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kErrReturnTimeout);
+  }
+  __syncthreads();
+  const bf16* ret_y = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.ret_y);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x / 32;
+  for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
+    for (int v = lane; v < D / 8; v += 32) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+      for (int j = 0; j < top_k; ++j) {
+        const int row = mapping[s * top_k + j];
+        if (row < 0) continue;
+        const float w = score ? score[s * top_k + j] : 1.0f;
+        const uint4 y = *reinterpret_cast<const uint4*>(ret_y + static_cast<size_t>(row) * D + v * 8);
+        float f[8];
+        bf16x8_to_f(y, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+      }
+      float o[8];
+      if (residual) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(residual + static_cast<size_t>(s) * D + v * 8));
+        bf16x8_to_f(r, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(ff_scale, acc[i], o[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = ff_scale * acc[i];
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 pk = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&pk);
+      }
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(s) * D + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_ep_wait_build(const EpPeers& ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax,
+                                 cudaStream_t stream) {
+  if (ep.E_local > kMaxExperts || ep.world > kMaxEpWorld) return cudaErrorInvalidValue;
+  ep_wait_build_kernel<<<1, 256, 0, stream>>>(ep, bn, groups, n_groups, h_ready, gmax);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float* score, const void* residual,
+                              float ff_scale, int S, int D, int top_k, void* out, cudaStream_t stream) {
+  if (D % 8 != 0) return cudaErrorInvalidValue;
+  int blocks = (S + 7) / 8;
+  if (blocks < 1) blocks = 1;  // the wait on the return flags must happen even for a rank without tokens
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  ep_combine_kernel<<<blocks, 256, 0, stream>>>(ep, mapping, score, static_cast<const bf16*>(residual), ff_scale, S, D,
+                                                top_k, static_cast<bf16*>(out));
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace b200moe

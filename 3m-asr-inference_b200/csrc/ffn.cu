@@ -61,6 +61,12 @@ struct FfnParams {
   int stages;
   int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
   int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
+  // expert parallelism: results go to the source rank's return buffer over peer-mapped memory (NVLink)
+  int ep;                           // 0 = off
+  int ep_world, ep_rank;
+  uint8_t* ep_out[kMaxEpWorld];     // ret_y of every rank
+  int* ep_ret_flag[kMaxEpWorld];    // &ret_flag[my rank] in every rank's buffer
+  int* ep_ctrl;                     // local control block
   int dbg;          // timing experiments only (B200MOE_DBG): 1 = no phase-2 stores, 2 = no phase-1 stores, 4 = no residual
   uint64_t w_policy;  // L2 eviction policy of the weight tiles: evict-first when every tile is read once
   // debug timeline (ffn_kernel<.., true> only): per CTA `trace_cap` records of {tile, event, globaltimer lo, hi}
@@ -593,7 +599,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         ptx::named_bar_sync(set_bar, kSetThreads);  // staging buffers free before the next tile reuses them
       } else {
         const float bias = p.b2 ? p.b2[static_cast<size_t>(gr.expert) * p.D + feat0 + feat_l] : 0.0f;
-        OutT* out = static_cast<OutT*>(p.out);
+        OutT* out = p.ep ? reinterpret_cast<OutT*>(p.ep_out[gr.src]) : static_cast<OutT*>(p.out);
         const OutT* res = static_cast<const OutT*>(p.residual);
         const bool with_res = p.fused && res != nullptr && !(p.dbg & 4);
         const bool st2 = !(p.dbg & 1);
@@ -601,7 +607,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         ptx::named_bar_sync(3, kEpiThreads);  // every warp is done with the previous table
         for (int i = et; i < nrows; i += kEpiThreads) {
           const int row = gr.row0 + i;
-          int tok = row;
+          int tok = gr.orow0 + i;  // un-fused: same row of the output buffer (the source rank's under EP)
           float sc = 1.0f;
           if (p.fused) {
             tok = p.pos[row] / p.top_k;
@@ -699,6 +705,18 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     ptx::tc_fence_after();
     ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
+  if (p.ep && threadIdx.x == 0) {
+    // Every store of this CTA into the peers' return buffers precedes the barrier above.  The last CTA of the grid to
+    // get here tells every source rank that its rows are back (functions.py:185-191's all-to-all, without the host).
+    ptx::fence_acq_rel_sys();
+    const int prev = atomicAdd(&p.ep_ctrl[2], 1);
+    if (prev == static_cast<int>(gridDim.x) - 1) {
+      ptx::fence_acq_rel_sys();
+      p.ep_ctrl[2] = 0;
+      const int seq = p.ep_ctrl[0];
+      for (int r = 0; r < p.ep_world; ++r) ptx::st_release_sys(p.ep_ret_flag[r], seq);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -764,6 +782,24 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
     return cudaErrorInvalidValue;
   }
   FfnParams p;
+  p.ep = 0;
+  p.ep_world = p.ep_rank = 0;
+  p.ep_ctrl = nullptr;
+  for (int r = 0; r < kMaxEpWorld; ++r) {
+    p.ep_out[r] = nullptr;
+    p.ep_ret_flag[r] = nullptr;
+  }
+  if (a.ep != nullptr) {
+    if (a.fused || a.out_dtype != B200MOE_BF16) return cudaErrorInvalidValue;
+    p.ep = 1;
+    p.ep_world = a.ep->world;
+    p.ep_rank = a.ep->rank;
+    p.ep_ctrl = reinterpret_cast<int*>(a.ep->base[a.ep->rank] + a.ep->lay.ctrl);
+    for (int r = 0; r < a.ep->world; ++r) {
+      p.ep_out[r] = a.ep->base[r] + a.ep->lay.ret_y;
+      p.ep_ret_flag[r] = reinterpret_cast<int*>(a.ep->base[r] + a.ep->lay.ret_flag) + a.ep->rank;
+    }
+  }
   p.groups = a.groups;
   p.n_groups = a.n_groups;
   p.h_ready = a.h_ready;

@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--ep", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: peer-memory kernels (product) or NCCL all-to-all (comparison)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -175,7 +177,9 @@ def workload_config(args, wl, S_total):
             "utterances": wl["utts"] * max(args.gpus, 1), "experts": E, "idim": D, "hidden_units": H, "embed_dim": DEMB,
             "top_k": 1, "gate": "3m softmax->max", "activation": "silu", "ff_scale": 0.5,
             "cache": "inputs larger than L2 (18 x 64 MiB weight sets cycle through a 126 MB L2)",
-            "parallelism": "single GPU" if args.gpus == 1 else f"ep{args.gpus} (32/{args.gpus} experts per GPU)"}
+            "parallelism": "single GPU" if args.gpus == 1 else
+            f"ep{args.gpus} (32/{args.gpus} experts per GPU), exchange: " +
+            ("peer-memory stores fused into dispatch / FFN kernels" if args.ep == "p2p" else "NCCL all-to-all")}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -197,7 +201,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    ep = importlib.import_module(PKG + ".ep") if world > 1 else None
+    ep = importlib.import_module(PKG + (".ep" if args.ep == "nccl" else ".ep_p2p")) if world > 1 else None
 
     wl = WORKLOADS[args.workload]
     L = wl["layers"]
@@ -232,13 +236,21 @@ def main():
     e_stage = torch.empty_like(e_dev)
     bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
 
+    ep_ctx = None
+    if world > 1 and args.ep == "p2p":
+        ep_ctx = ep.EpContext.from_process_group(E_local, D, cap=S, timeout_ms=20000)
+
     def step(x_in, e_in):
         cur = x_in
         for li, (Wr, experts, Wrp) in enumerate(layers):
             out = bufs[li & 1]
-            if world > 1:
+            if ep_ctx is not None:
+                ep_ctx.forward(cur, e_in, Wr, None, experts, residual=cur, top_k=1, gate_mode=ops.GATE_3M,
+                               act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=Wrp)
+            elif world > 1:
                 ep.ep_moe_layer(cur, e_in, Wr, None, experts, num_local_expert=E_local, group=None, top_k=1,
-                                gate_mode=ops.GATE_3M, act_type=ops.ACT_SILU, ff_scale=0.5, residual=cur, out=out)
+                                gate_mode=ops.GATE_3M, act_type=ops.ACT_SILU, ff_scale=0.5, residual=cur, out=out,
+                                Wr_packed=Wrp)
             else:
                 ops.moe_layer(cur, e_in, Wr, None, experts, residual=cur, top_k=1, gate_mode=ops.GATE_3M,
                               act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=Wrp)
@@ -261,7 +273,8 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = ops.launch_count() - n0
 
-    use_graph = (world == 1) and not args.no_graph
+    # the peer-memory EP path has no host synchronisation either, so the whole step is captured on every rank
+    use_graph = (world == 1 or ep_ctx is not None) and not args.no_graph
     graph = None
     if use_graph:
         graph = torch.cuda.CUDAGraph()
@@ -327,6 +340,12 @@ def main():
     ms_e2e = timed(e2e_step, K) / K
     e2e_value = tokens_per_step / (ms_e2e * 1e-3)
     clocks = sampler.stop()
+    if ep_ctx is not None:
+        status = ep_ctx.status()
+        if status != 0:   # a kernel gave up waiting for a peer: whatever was timed is not the workload
+            print(f"rank {rank}: expert-parallel flag wait timed out (status {status}); no result", file=sys.stderr,
+                  flush=True)
+            sys.exit(3)
 
     # ---- roofline of the dominant kernel (expert FFN with the fused combine epilogue)
     hbm_peak, tf_peak, peak_kind = load_peaks()
@@ -401,6 +420,9 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if ep_ctx is not None:
+        dist.barrier()
+        ep_ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

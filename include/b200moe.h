@@ -164,6 +164,48 @@ typedef struct b200moe_layer_args {
 
 int b200moe_forward(const b200moe_layer_args* args, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+/* ---- expert parallelism over peer-mapped memory (NVLink / NVSwitch) ---------------------------------------------
+ * The reference's only multi-GPU mode of this path: experts are partitioned contiguously over the GPUs of one node
+ * (expert e on rank e / E_local; `num_expert` is per worker: trainer_3m_fix/model/..._hier.py:259-273), tokens stay
+ * data-parallel, and fmoe_cuda exchanges counts and rows with all-to-alls around the expert computation
+ * (trainer_3m_fix/fmoe/functions.py:37-50 expert_exchange + .cpu(), :74-80 global_scatter, :185-191 global_gather).
+ * Here the exchange is fused into the kernels on either side of it: the dispatch kernel stores token rows straight
+ * into the owner GPU's receive buffer, the expert-FFN kernel's second GEMM stores its result rows straight into the
+ * source GPU's return buffer, and arrival is signalled with system-scope release/acquire flags -- no collective call,
+ * no host synchronisation, CUDA-graph capturable.  One process per GPU; the buffers are exchanged once at set-up:
+ *
+ *   every rank:  b200moe_ep_alloc(b200moe_ep_buffer_bytes(world, E_local, D, cap), &buf);   (cudaMalloc, zeroed)
+ *                b200moe_ep_ipc_export(buf, handle);   all-gather the 64-byte handles by any means (host side)
+ *                b200moe_ep_ipc_open(handle_of_rank_r, &bufs[r]) for r != rank;  bufs[rank] = buf
+ *                ctx = b200moe_ep_create(rank, world, E_local, D, cap, bufs, timeout_ms);
+ *   per layer:   b200moe_ep_forward(ctx, &args, ws, ws_bytes, stream);
+ *
+ * cap = the largest B*T*top_k any rank will ever pass.  args->E is the TOTAL number of experts (router width),
+ * args->W1/b1/W2/b2 hold this rank's E_local experts.  Activations must be bf16.  Every rank must call
+ * b200moe_ep_forward the same number of times (ranks without tokens pass B*T = 0).  A peer that does not show up
+ * within timeout_ms makes the waiting kernels give up and sets the status word (b200moe_ep_status != 0). */
+typedef struct b200moe_ep_ctx b200moe_ep_ctx;
+size_t b200moe_ep_buffer_bytes(int world, int E_local, int D, int cap);
+int b200moe_ep_alloc(size_t bytes, void** dev_ptr);
+int b200moe_ep_free(void* dev_ptr);
+int b200moe_ep_ipc_export(void* dev_ptr, void* handle64 /* host, 64 bytes */);
+int b200moe_ep_ipc_open(const void* handle64 /* host */, void** peer_ptr);
+int b200moe_ep_ipc_close(void* peer_ptr);
+b200moe_ep_ctx* b200moe_ep_create(int rank, int world, int E_local, int D, int cap, void* const* bufs /* host [world] */,
+                                  int timeout_ms);
+void b200moe_ep_destroy(b200moe_ep_ctx* ctx);
+size_t b200moe_ep_workspace_bytes(const b200moe_ep_ctx* ctx, int H);
+int b200moe_ep_forward(b200moe_ep_ctx* ctx, const b200moe_layer_args* args, void* ws, size_t ws_bytes,
+                       cudaStream_t stream);
+/* Same, restricted to some of its stages (bit 0: gate + dispatch/push, bit 1: wait for the peers' rows + expert FFN
+ * + push back, bit 2: wait for the returned rows + combine).  Lets one process drive several ranks on ONE GPU stage
+ * by stage (tests): kernels that wait on one another must never be queued on the same GPU in the wrong order. */
+int b200moe_ep_forward_stages(b200moe_ep_ctx* ctx, const b200moe_layer_args* args, void* ws, size_t ws_bytes,
+                              int stages, cudaStream_t stream);
+/* Reads the context's device status word (synchronous copy): 0 ok, 1 a peer's rows did not arrive, 2 returned rows did
+ * not arrive. */
+int b200moe_ep_status(const b200moe_ep_ctx* ctx, int* host_status);
+
 /* ---- plugin object: mirror of FMoEExpertPlugin / FMoEExpertPluginCreator --------------------------------------
  * Fields are the creator's (fmoe_expert_plugin.cpp:325-366): data_type (0 fp32, 1 fp16; anything else fails like
  * the reference creator, except 2 = bf16 which is new), num_expert, idim, hidden_units, act_type. */
@@ -198,8 +240,8 @@ int b200moe_profile_enable(int on);
 int b200moe_profile_read(float* stage_ms, int* stage_calls);
 
 /* Debug: while dev_buf is non-NULL every expert-FFN launch runs its tracing variant and writes a per-CTA timeline of
- * 16-byte records {tile, event, globaltimer lo, hi}: 3 roles (TMA producer, MMA issuer, epilogue) x records_per_cta/3
- * slots per CTA, CTA-major.  dev_buf must hold 148 * records_per_cta records.  See tools/ffn_trace.py. */
+ * 16-byte records {tile, event, clock64 lo, hi}: 4 roles (TMA producer, MMA issuer, epilogue, publisher) x
+ * records_per_cta/4 slots per CTA, CTA-major.  dev_buf must hold 148 * records_per_cta records.  See tools/ffn_trace.py. */
 int b200moe_debug_ffn_trace(void* dev_buf, int records_per_cta);
 
 /* Number of kernels this library launched on behalf of the calling process (for bench accounting). */

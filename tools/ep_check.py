@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Multi-GPU parity of the expert-parallel path (run under torchrun on a multi-GPU box):
+"""Multi-GPU parity of the expert-parallel paths (run under torchrun on a multi-GPU box):
 the W-rank result on each rank's tokens must equal the single-GPU fused layer on the same tokens with all experts --
-routing bit-exact, outputs within bf16 round-off.
+routing bit-exact, outputs within bf16 round-off.  Checks the peer-memory path (ep_p2p.EpContext, the product) and the
+NCCL formulation (ep.ep_moe_layer).
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ep_check.py
 """
 import importlib
@@ -25,39 +26,74 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ops = importlib.import_module(PKG + ".ops")
     ep = importlib.import_module(PKG + ".ep")
+    ep_p2p = importlib.import_module(PKG + ".ep_p2p")
     synth = importlib.import_module(PKG + ".synth")
     E, D, H, Demb = 32, 512, 1024, 512
     E_local = E // world
     w = synth.make_weights(777, E, D, H, Demb, random_bias=True)
+    sizes = (50 + 13 * rank, 3200, 1 if rank else 0)
+    ctx = ep_p2p.EpContext.from_process_group(E_local, D, cap=4096, timeout_ms=5000)
     ok = True
-    for S in (50 + 13 * rank, 3200, 1):
+    Wr = w.Wr.to(dev)
+    Wrp = ops.pack_router(Wr)
+    full = ops.pack_experts(w.W1.to(dev), w.b1.to(dev), w.W2.to(dev), w.b2.to(dev))
+    sl = slice(rank * E_local, (rank + 1) * E_local)
+    mine = ops.PackedExperts(full.W1[sl].contiguous(), full.b1[sl].contiguous(), full.W2[sl].contiguous(),
+                             full.b2[sl].contiguous())
+    for S in sizes:
         x, embed = synth.make_activations(1000 * S + rank, S, D, Demb, w)
         xd, ed = x.to(dev).bfloat16(), embed.to(dev).bfloat16()
-        Wr = w.Wr.to(dev)
-        full = ops.pack_experts(w.W1.to(dev), w.b1.to(dev), w.W2.to(dev), w.b2.to(dev))
-        sl = slice(rank * E_local, (rank + 1) * E_local)
-        mine = ops.PackedExperts(full.W1[sl].contiguous(), full.b1[sl].contiguous(), full.W2[sl].contiguous(),
-                                 full.b2[sl].contiguous())
-        ref = ops.moe_layer(xd, ed, Wr, None, full, residual=xd, ff_scale=0.5, return_routing=True,
-                            Wr_packed=ops.pack_router(Wr))
-        out, idx, score, counts, mapping = ep.ep_moe_layer(
-            xd, ed, Wr, None, mine, num_local_expert=E_local, top_k=1, gate_mode=ops.GATE_3M, act_type=ops.ACT_SILU,
-            ff_scale=0.5, residual=xd, Wr_packed=ops.pack_router(Wr), return_routing=True)
-        torch.cuda.synchronize()
-        same_idx = torch.equal(idx, ref.idx)
-        same_map = torch.equal(mapping, ref.mapping)
-        err = float((out.float() - ref.out.float()).norm() / ref.out.float().norm())
-        # MoE term alone
-        out2 = ep.ep_moe_layer(xd, ed, Wr, None, mine, num_local_expert=E_local, ff_scale=1.0, residual=None,
-                               Wr_packed=ops.pack_router(Wr))
-        ref2 = ops.moe_layer(xd, ed, Wr, None, full, residual=None, ff_scale=1.0)
-        err2 = float((out2.float() - ref2.out.float()).norm() / ref2.out.float().norm().clamp_min(1e-20))
-        good = same_idx and same_map and err < 5e-3 and err2 < 1e-2
-        ok = ok and good
-        print(f"rank {rank} S={S}: routing {'bit-exact' if same_idx and same_map else 'DIFFERS'}, out rel-L2 {err:.2e}, "
-              f"moe-term rel-L2 {err2:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+        if S > 0:
+            ref = ops.moe_layer(xd, ed, Wr, None, full, residual=xd, ff_scale=0.5, return_routing=True, Wr_packed=Wrp)
+            ref2 = ops.moe_layer(xd, ed, Wr, None, full, residual=None, ff_scale=1.0, Wr_packed=Wrp)
+        for name in ("p2p", "nccl"):
+            if name == "p2p":
+                out, idx, score, counts, mapping = ctx.forward(xd, ed, Wr, None, mine, residual=xd, ff_scale=0.5,
+                                                               Wr_packed=Wrp, return_routing=True)
+                out2 = ctx.forward(xd, ed, Wr, None, mine, residual=None, ff_scale=1.0, Wr_packed=Wrp)
+            else:
+                out, idx, score, counts, mapping = ep.ep_moe_layer(
+                    xd, ed, Wr, None, mine, num_local_expert=E_local, top_k=1, gate_mode=ops.GATE_3M,
+                    act_type=ops.ACT_SILU, ff_scale=0.5, residual=xd, Wr_packed=Wrp, return_routing=True)
+                out2 = ep.ep_moe_layer(xd, ed, Wr, None, mine, num_local_expert=E_local, ff_scale=1.0, residual=None,
+                                       Wr_packed=Wrp)
+            torch.cuda.synchronize()
+            if S == 0:
+                print(f"rank {rank} {name} S=0: participated", flush=True)
+                continue
+            same_idx = torch.equal(idx, ref.idx)
+            same_map = torch.equal(mapping, ref.mapping)
+            err = float((out.float() - ref.out.float()).norm() / ref.out.float().norm())
+            err2 = float((out2.float() - ref2.out.float()).norm() / ref2.out.float().norm().clamp_min(1e-20))
+            good = same_idx and same_map and err < 5e-3 and err2 < 1e-2
+            ok = ok and good
+            print(f"rank {rank} {name} S={S}: routing {'bit-exact' if same_idx and same_map else 'DIFFERS'}, "
+                  f"out rel-L2 {err:.2e}, moe-term rel-L2 {err2:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+    st = ctx.status()
+    if st != 0:
+        print(f"rank {rank}: peer-flag wait timed out, status {st}", flush=True)
+        ok = False
+    # many layers back to back without any host synchronisation (flag sequence numbers, buffer reuse)
+    S = 3200
+    x, embed = synth.make_activations(5 + rank, S, D, Demb, w)
+    xd, ed = x.to(dev).bfloat16(), embed.to(dev).bfloat16()
+    bufs = [torch.empty_like(xd), torch.empty_like(xd)]
+    cur = xd
+    ref_cur = xd
+    for li in range(12):
+        cur = ctx.forward(cur, ed, Wr, None, mine, residual=cur, ff_scale=0.5, Wr_packed=Wrp, out=bufs[li & 1])
+    for li in range(12):
+        ref_cur = ops.moe_layer(ref_cur, ed, Wr, None, full, residual=ref_cur, ff_scale=0.5, Wr_packed=Wrp).out
+    torch.cuda.synchronize()
+    err = float((cur.float() - ref_cur.float()).norm() / ref_cur.float().norm())
+    good = err < 2e-2 and ctx.status() == 0
+    ok = ok and good
+    print(f"rank {rank} p2p 12 layers back to back: rel-L2 vs single-GPU chain {err:.2e}, status {ctx.status()} -> "
+          f"{'ok' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    ctx.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
