@@ -546,13 +546,16 @@ int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, vo
 
   const int bn = choose_bn(Sk, E_total);
   const int gmax = max_groups(rows_cap, E_total, bn);
+  // all stages in one call: the dispatch kernel's last CTA also waits for the peers and builds the group table
+  const bool fold_wait = (stages & 3) == 3;
   if (stages & 1) {
     StageScope t(1, stream);
     e = launch_dispatch(a->x, idx, nullptr, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
-                        a->mapping_out, w.xbuf, nullptr, nullptr, tc_gate && S > 0 ? w.hist32 : nullptr, stream, &ep);
+                        a->mapping_out, w.xbuf, nullptr, nullptr, tc_gate && S > 0 ? w.hist32 : nullptr, stream, &ep,
+                        fold_wait);
   }
   if (e != cudaSuccess) return cuda_fail(e, "ep_forward/dispatch");
-  if (stages & 2) {
+  if ((stages & 2) && !fold_wait) {
     StageScope t(1, stream);
     e = launch_ep_wait_build(ep, bn, w.groups, w.n_groups, w.h_ready, gmax, stream);
   }

@@ -150,7 +150,8 @@ cudaError_t launch_softmax_topk(const void* logits, const int* mask, int B, int 
 cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
-                            const int* hist32, cudaStream_t stream, const EpPeers* ep = nullptr);
+                            const int* hist32, cudaStream_t stream, const EpPeers* ep = nullptr,
+                            bool ep_fold_wait = false);
 constexpr int kMaxHistRows = 512;  // above this many 32-token rows the scatter CTAs would re-read too much
 // Builds only the group table (+ zeroes the flags) from an existing offsets array.
 cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,

@@ -10,6 +10,7 @@
 // histograms, ranks its entries with warp match/ballot, and copies rows with 128-bit accesses, casting to bf16).
 // CTA 0 of the scatter kernel also emits counts / offsets / the FFN group table and clears the FFN flags.
 #include "common.cuh"
+#include "ep_device.cuh"
 #include "ptx.cuh"
 
 namespace b200moe {
@@ -138,7 +139,8 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
                         int* __restrict__ offsets, int* __restrict__ mapping, int* __restrict__ pos,
                         float* __restrict__ row_score, bf16* __restrict__ xbuf, GroupRec* groups, int* n_groups,
                         int* h_ready, int* counts_out, int* offsets_out, int* mapping_out, InT* __restrict__ drop_out,
-                        const InT* __restrict__ drop_residual, int early_trigger, const EpPeers ep) {
+                        const InT* __restrict__ drop_residual, int early_trigger, const EpPeers ep,
+                        int ep_fold_wait) {
   constexpr int kWarps = kDispatchThreads / 32;
   constexpr int kRowsPerBatch = 4;            // rows a warp keeps in flight during the copy
   constexpr int kMaxParts = 8;
@@ -310,10 +312,13 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
     __shared__ int s_last;
     int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
     if (threadIdx.x == 0) {
+      // (one NVLink round trip: the fence returns once this CTA's pushes have been performed at the peers)
       ptx::fence_acq_rel_sys();
       const int prev = atomicAdd(&ctrl[1], 1);
       s_last = prev == static_cast<int>(gridDim.x) - 1;
-      if (s_last) ptx::fence_acq_rel_sys();  // acquire side: the other CTAs' pushes happen-before the flags below
+      // acquire side: every other CTA fenced its pushes system-wide before its increment, so observing the increments
+      // at gpu scope is enough to order them before the flags below
+      if (s_last) ptx::fence_acq_rel_gpu();
     }
     __syncthreads();
     if (s_last) {
@@ -326,16 +331,23 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
         int* rc = reinterpret_cast<int*>(ep.base[dest] + ep.lay.recv_cnt) + ep.rank * (El + 1);
         rc[k] = k < El ? s_total[dest * El + k] : s_off[dest * El];
       }
-      __syncthreads();
       if (threadIdx.x == 0) {
-        ptx::fence_acq_rel_sys();
         ctrl[1] = 0;
         ctrl[0] = seq;
-        ptx::fence_acq_rel_sys();
       }
       __syncthreads();
+      // one release per peer (second round trip): covers the counts above through the barrier
       if (threadIdx.x < ep.world)
         ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, seq);
+      if (ep_fold_wait) {
+        // Same CTA goes on to wait for the peers' rows and to build the FFN group table, which saves a kernel launch
+        // per layer (the standalone ep_wait_build_kernel exists for drivers that run the stages separately).
+        // s_part (8 * 2 * E ints) is free by now and large enough for both scratch arrays.
+        __syncthreads();
+        int* s_cnt2 = s_part;
+        int* s_g02 = s_part + ep.world * (El + 1);
+        ep_wait_and_build_groups(ep, seq, bn, groups, n_groups, h_ready, gmax, s_cnt2, s_g02);
+      }
     }
   }
 }
@@ -365,7 +377,7 @@ int choose_bn(int Sk, int E) {
 cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
-                            const int* hist32, cudaStream_t stream, const EpPeers* ep) {
+                            const int* hist32, cudaStream_t stream, const EpPeers* ep, bool ep_fold_wait) {
   const int Sk = S * top_k;
   if (top_k != 1 || ep != nullptr) drop_out = nullptr;
   if (ep != nullptr && (ep->world * ep->E_local != E || Sk > ep->cap || ep->D != D)) return cudaErrorInvalidValue;
@@ -409,7 +421,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
       rows_per_chunk, bn, gmax,                                                                                   \
       ws.counts, ws.offsets, ws.mapping, ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready,          \
       counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual),      \
-      (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv)
+      (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, ep_fold_wait ? 1 : 0)
 #define B200MOE_SCATTER(T)          \
   if (ep)                           \
     B200MOE_SCATTER_K(T, true);     \

@@ -18,74 +18,20 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "ep_device.cuh"
 #include "ptx.cuh"
 
 namespace b200moe {
 
 namespace {
 
-constexpr int kErrDispatchTimeout = 1;
-constexpr int kErrReturnTimeout = 2;
-
-// Spin until *flag >= want (acquire, system scope) or the deadline passes. Returns false on timeout.
-__device__ __forceinline__ bool wait_flag_sys(const int* flag, int want, unsigned long long deadline_ns) {
-  while (ptx::ld_acquire_sys(flag) < want) {
-    __nanosleep(64);
-    if (ptx::globaltimer_ns() > deadline_ns) return false;
-  }
-  return true;
-}
-
 __global__ void __launch_bounds__(256)
 ep_wait_build_kernel(const EpPeers ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax) {
-  __shared__ int s_cnt[kMaxEpWorld][kMaxExperts + 1];
-  __shared__ int s_g0[kMaxExperts * kMaxEpWorld + 1];  // first group of (expert, source), expert-major
-  int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
-  const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.disp_flag);
-  const int W = ep.world, El = ep.E_local;
+  __shared__ int s_cnt[kMaxEpWorld * (kMaxExperts + 1)];
+  __shared__ int s_g0[kMaxExperts + 1];  // E_local * world <= kMaxExperts
+  const int* ctrl = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ctrl);
   const int seq = ctrl[0];  // set by this rank's own dispatch kernel, which precedes this kernel in the stream
-  if (threadIdx.x < W) {
-    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
-    if (!wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kErrDispatchTimeout);
-  }
-  __syncthreads();
-  const int* rc = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.recv_cnt);
-  for (int i = threadIdx.x; i < W * (El + 1); i += blockDim.x) s_cnt[i / (El + 1)][i % (El + 1)] = rc[i];
-  __syncthreads();
-  if (ctrl[3] != 0) {  // a peer never showed up: run the rest of the layer over nothing rather than over garbage
-    for (int i = threadIdx.x; i < W * (El + 1); i += blockDim.x) s_cnt[i / (El + 1)][i % (El + 1)] = 0;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int e = 0; e < El; ++e)
-      for (int s = 0; s < W; ++s) {
-        s_g0[e * W + s] = acc;
-        acc += (s_cnt[s][e] + bn - 1) / bn;
-      }
-    s_g0[El * W] = acc;
-    n_groups[0] = acc < gmax ? acc : gmax;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < El * W; i += blockDim.x) {
-    const int e = i / W, s = i - e * W;
-    const int c = s_cnt[s][e];
-    int off = 0;  // rows of source s that precede expert e in its segment
-    for (int k = 0; k < e; ++k) off += s_cnt[s][k];
-    const int nt = (c + bn - 1) / bn;
-    const int g0 = s_g0[i];
-    for (int j = 0; j < nt && g0 + j < gmax; ++j) {
-      GroupRec r;
-      r.expert = e;
-      r.row0 = s * ep.cap + off + j * bn;
-      r.nrows = min(bn, c - j * bn);
-      r.src = s;
-      r.orow0 = s_cnt[s][El] + off + j * bn;  // row in rank s's own expert-ordered entries
-      r.pad[0] = r.pad[1] = r.pad[2] = 0;
-      groups[g0 + j] = r;
-    }
-  }
-  for (int g = threadIdx.x; g < gmax; g += blockDim.x) h_ready[g] = 0;
+  ep_wait_and_build_groups(ep, seq, bn, groups, n_groups, h_ready, gmax, s_cnt, s_g0);
 }
 
 __device__ __forceinline__ void bf16x8_to_f(const uint4& v, float (&o)[8]) {
@@ -107,7 +53,7 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
   if (threadIdx.x < ep.world) {
     const int seq = ctrl[0];
     const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
-    if (!wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kErrReturnTimeout);
+    if (!ep_wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kEpErrReturnTimeout);
   }
   __syncthreads();
   const bf16* ret_y = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.ret_y);

@@ -93,11 +93,12 @@ template <bool kTrace>
 struct Tracer {
   uint4* base;
   int cap, n;
-  __device__ __forceinline__ Tracer(const FfnParams& p, int role) : base(nullptr), cap(0), n(0) {
+  __device__ __forceinline__ Tracer(const FfnParams& p, int role, int tail_slots = 0) : base(nullptr), cap(0), n(0) {
     if constexpr (kTrace) {
       if (p.trace != nullptr) {
         cap = p.trace_cap / 4;
         base = p.trace + (static_cast<size_t>(blockIdx.x) * 4 + role) * cap;
+        if (tail_slots > 0) n = cap - tail_slots;  // a second recorder of the same role writes the last slots
       }
     }
   }
@@ -708,10 +709,14 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   if (p.ep && threadIdx.x == 0) {
     // Every store of this CTA into the peers' return buffers precedes the barrier above.  The last CTA of the grid to
     // get here tells every source rank that its rows are back (functions.py:185-191's all-to-all, without the host).
+    Tracer<kTrace> tr(p, 3, 4);
+    tr.rec(-2, kEvEpiChunkLd);
     ptx::fence_acq_rel_sys();
+    tr.rec(-2, kEvEpiChunkStaged);
     const int prev = atomicAdd(&p.ep_ctrl[2], 1);
+    tr.rec(-2, kEvEpiChunkDone);
     if (prev == static_cast<int>(gridDim.x) - 1) {
-      ptx::fence_acq_rel_sys();
+      ptx::fence_acq_rel_gpu();  // the other CTAs' system-wide fences precede their increments
       p.ep_ctrl[2] = 0;
       const int seq = p.ep_ctrl[0];
       for (int r = 0; r < p.ep_world; ++r) ptx::st_release_sys(p.ep_ret_flag[r], seq);

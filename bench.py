@@ -314,7 +314,7 @@ def main():
     # ---- eager device time (no graph) and per-stage CUDA-event timing of the same steps (roofline input)
     ms_eager = timed(lambda: step(x_dev, e_dev), K) / K
     stage_ms, stage_calls = {}, {}
-    if world == 1:
+    if world == 1 or ep_ctx is not None:
         ops.profile_enable(True)
         kprof = min(K, 400)
         for _ in range(kprof):

@@ -18,7 +18,7 @@ E, D, H, DEMB = 32, 512, 1024, 512
 
 
 def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=None, random_bias=True, seed=4242,
-              layers=1, keep_expert_output=False):
+              layers=1, keep_expert_output=False, stage_seq=(1, 2, 4)):
     gate_mode = ops.GATE_3M if gate_mode is None else gate_mode
     dev = torch.device("cuda")
     E_local = E // world
@@ -48,12 +48,12 @@ def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=No
                   torch.empty(sizes[r] * top_k, dtype=torch.int32, device=dev)) for r in range(world)]
         # the MoE term alone first (no residual, ff_scale 1): the O(1) residual must not be able to mask an error in it
         moes = [torch.empty_like(c) for c in cur]
-        for stage in (1, 2, 4):
+        for stage in stage_seq:
             for r in range(world):
                 ctxs[r].forward(cur[r], emb[r], Wr, br, mine[r], residual=None, top_k=top_k, gate_mode=gate_mode,
                                 ff_scale=1.0, out=moes[r], Wr_packed=packed, return_routing=True, stages=stage,
                                 routing_bufs=rbufs[r], keep_expert_output=keep_expert_output)
-        for stage in (1, 2, 4):
+        for stage in stage_seq:
             for r in range(world):
                 ctxs[r].forward(cur[r], emb[r], Wr, br, mine[r], residual=cur[r], top_k=top_k, gate_mode=gate_mode,
                                 ff_scale=0.5, out=outs[r], Wr_packed=packed, return_routing=True, stages=stage,
@@ -115,3 +115,10 @@ def test_ep_naive_top2(ops, ep_mod, synth, oracle):
 
 def test_ep_keep_expert_output(ops, ep_mod, synth, oracle):
     run_world(ops, ep_mod, synth, oracle, 2, [77, 50], keep_expert_output=True)
+
+
+@pytest.mark.parametrize("S", [50, 3200])
+def test_ep_whole_layer_in_one_call(ops, ep_mod, synth, oracle, S):
+    """stages = 7, the call a multi-process rank makes: the dispatch kernel's last CTA itself waits for the arrival
+    flags and builds the group table (no separate wait kernel).  With one rank every flag it waits for is its own."""
+    run_world(ops, ep_mod, synth, oracle, 1, [S], layers=2, stage_seq=(7,))

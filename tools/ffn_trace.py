@@ -18,36 +18,7 @@ EV = ["kernel_start", "prod_tile_start", "prod_dep_ok", "prod_issued", "mma_acc_
       "epi_chunk_done", "clock"]
 
 
-def main():
-    S = int(sys.argv[1]) if len(sys.argv) > 1 else 3200
-    n_print = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    ops = importlib.import_module(PKG + ".ops")
-    lib = importlib.import_module(PKG + "._lib").load()
-    E, D, H, Demb = 32, 512, 1024, 512
-    dev = torch.device("cuda")
-    g = torch.Generator(device=dev).manual_seed(1)
-    layers = []
-    for _ in range(4):  # cycle 4 weight sets so that weights are not L2 resident
-        W1 = ((torch.rand(E, H, D, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
-        W2 = ((torch.rand(E, D, H, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
-        Wr = ((torch.rand(Demb + D, E, generator=g, device=dev) * 2 - 1) * 0.04)
-        layers.append((Wr, ops.PackedExperts(W1, torch.zeros(E, H, device=dev), W2, torch.zeros(E, D, device=dev)), ops.pack_router(Wr)))
-    x = torch.randn(S, D, generator=g, device=dev).bfloat16()
-    emb = torch.randn(S, Demb, generator=g, device=dev).bfloat16()
-    out = torch.empty_like(x)
-    for _ in range(3):
-        for Wr, ex, wp in layers:
-            ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
-    torch.cuda.synchronize()
-    cap = 256  # records per CTA (4 roles x 64)
-    n_cta = 148
-    buf = torch.zeros(n_cta * cap, 4, dtype=torch.int32, device=dev)
-    lib.b200moe_debug_ffn_trace(buf.data_ptr(), cap)
-    Wr, ex, wp = layers[0]
-    ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
-    torch.cuda.synchronize()
-    lib.b200moe_debug_ffn_trace(None, 0)
-    rec = buf.cpu().numpy().astype(np.int64).reshape(n_cta, 4, cap // 4, 4)
+def analyze(rec, cap, n_cta, S, n_print):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.save(os.path.join(ROOT, "gpurun_out", f"ffn_trace_{S}.npy"), rec)
     raw = (rec[..., 2] & 0xFFFFFFFF) | (rec[..., 3] << 32)     # clock64 for events, ns for sync records
@@ -87,6 +58,40 @@ def main():
         print(f"--- CTA {c}")
         for ts, role, tile, ev in rows:
             print(f"   {ts:8.2f} us  {'PMEU'[role]}  tile {tile:4d}  {EV[ev]}")
+
+
+
+def main():
+    S = int(sys.argv[1]) if len(sys.argv) > 1 else 3200
+    n_print = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    ops = importlib.import_module(PKG + ".ops")
+    lib = importlib.import_module(PKG + "._lib").load()
+    E, D, H, Demb = 32, 512, 1024, 512
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(1)
+    layers = []
+    for _ in range(4):  # cycle 4 weight sets so that weights are not L2 resident
+        W1 = ((torch.rand(E, H, D, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
+        W2 = ((torch.rand(E, D, H, generator=g, device=dev) * 2 - 1) * 0.05).bfloat16()
+        Wr = ((torch.rand(Demb + D, E, generator=g, device=dev) * 2 - 1) * 0.04)
+        layers.append((Wr, ops.PackedExperts(W1, torch.zeros(E, H, device=dev), W2, torch.zeros(E, D, device=dev)), ops.pack_router(Wr)))
+    x = torch.randn(S, D, generator=g, device=dev).bfloat16()
+    emb = torch.randn(S, Demb, generator=g, device=dev).bfloat16()
+    out = torch.empty_like(x)
+    for _ in range(3):
+        for Wr, ex, wp in layers:
+            ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
+    torch.cuda.synchronize()
+    cap = 256  # records per CTA (4 roles x 64)
+    n_cta = 148
+    buf = torch.zeros(n_cta * cap, 4, dtype=torch.int32, device=dev)
+    lib.b200moe_debug_ffn_trace(buf.data_ptr(), cap)
+    Wr, ex, wp = layers[0]
+    ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
+    torch.cuda.synchronize()
+    lib.b200moe_debug_ffn_trace(None, 0)
+    rec = buf.cpu().numpy().astype(np.int64).reshape(n_cta, 4, cap // 4, 4)
+    analyze(rec, cap, n_cta, S, n_print)
 
 
 if __name__ == "__main__":
