@@ -287,13 +287,15 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    def timed(fn, iters):
+    def timed(fn, iters, finish=None):
         barrier()
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(iters):
             fn()
+        if finish is not None:
+            finish()
         ev1.record(stream)
         ev1.synchronize()
         barrier()
@@ -323,21 +325,54 @@ def main():
         stage_ms, stage_calls = ops.profile_read()
         ops.profile_enable(False)
 
-    # ---- e2e: host buffers in, host buffer out, every step
+    # ---- e2e: host buffers in, host buffer out, EVERY step, through the public API.  The copies run on their own
+    # streams so that step i+1's upload and step i's download overlap step i's / i+1's compute, the way a serving loop
+    # would feed the layer; every step still uploads its own inputs from pinned memory and downloads its own result.
+    h2d_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
+    st_x = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    st_e = [torch.empty_like(e_dev), torch.empty_like(e_dev)]
+    st_o = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+    ev_up = [torch.cuda.Event(), torch.cuda.Event()]        # upload of slot b finished
+    ev_used = [torch.cuda.Event(), torch.cuda.Event()]      # compute has consumed staging slot b
+    ev_out = [torch.cuda.Event(), torch.cuda.Event()]       # result of slot b is in st_o[b]
+    ev_down = [torch.cuda.Event(), torch.cuda.Event()]      # download of slot b finished
+    e2e_i = [0]
+
     def e2e_step():
+        b = e2e_i[0] & 1
+        e2e_i[0] += 1
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(ev_used[b])
+            st_x[b].copy_(x_host, non_blocking=True)
+            st_e[b].copy_(e_host, non_blocking=True)
+            ev_up[b].record(h2d_stream)
+        stream.wait_event(ev_up[b])
         if use_graph:   # the graph reads x_dev / e_dev and leaves the result in `final`
-            x_dev.copy_(x_host, non_blocking=True)
-            e_dev.copy_(e_host, non_blocking=True)
+            x_dev.copy_(st_x[b], non_blocking=True)
+            e_dev.copy_(st_e[b], non_blocking=True)
+            ev_used[b].record(stream)
             graph.replay()
-            out_host.copy_(final, non_blocking=True)
+            res = final
         else:
-            x_stage.copy_(x_host, non_blocking=True)
-            e_stage.copy_(e_host, non_blocking=True)
-            out_host.copy_(step(x_stage, e_stage), non_blocking=True)
+            res = step(st_x[b], st_e[b])
+            ev_used[b].record(stream)
+        stream.wait_event(ev_down[b])
+        st_o[b].copy_(res, non_blocking=True)
+        ev_out[b].record(stream)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ev_out[b])
+            out_hosts[b].copy_(st_o[b], non_blocking=True)
+            ev_down[b].record(d2h_stream)
+
+    def e2e_finish():   # the last downloads belong to the timed region
+        stream.wait_stream(d2h_stream)
 
     for _ in range(3):
         e2e_step()
-    ms_e2e = timed(e2e_step, K) / K
+    e2e_finish()
+    ms_e2e = timed(e2e_step, K, e2e_finish) / K
     e2e_value = tokens_per_step / (ms_e2e * 1e-3)
     clocks = sampler.stop()
     if ep_ctx is not None:
@@ -353,13 +388,13 @@ def main():
     traffic = None   # DRAM bytes per launch of the same kernel from one `ncu --set full` capture (profiles/)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ffn_traffic.json")))
-        if args.workload == tr.get("workload"):
+        if args.workload == tr.get("workload") and world == 1:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
+    w_bytes = 2 * E_local * D * H * 2 + (E_local * H + E_local * D) * 4         # bf16 W1 + W2, fp32 biases (this rank)
     if stage_calls.get("expert_ffn"):
         t_ffn = stage_ms["expert_ffn"] / stage_calls["expert_ffn"] * 1e-3      # seconds per launch
-        w_bytes = 2 * E * D * H * 2 + (E * H + E * D) * 4                       # bf16 W1 + W2, fp32 biases
         act_bytes = S * (2 * D + 2 * D + 2 * D + 8)                             # xbuf read, residual read, out write, pos+score
         alg_bytes = w_bytes + act_bytes
         flops = S * 4 * D * H
@@ -375,6 +410,16 @@ def main():
             roofline = {"kernel": "ffn_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
                         "frac": ach / tf_peak, "traffic": traffic, "peak_source": peak_kind,
                         "algorithmic_flops_per_launch": flops, "us_per_launch": t_ffn * 1e6}
+    # the whole layer (gate + dispatch + expert FFN with the fused combine) against the same peaks: SURVEY section 8(d)'s
+    # 9 236 B per token (bf16, top-1) + the expert weights once, over the time a layer takes inside the timed region
+    layer_bytes = w_bytes + S * 9236
+    layer_flops = S * (4 * D * H + 2 * (D + DEMB) * E)
+    t_layer = ms_step * 1e-3 / L
+    layer_roofline = {
+        "bound": "hbm" if layer_bytes / (hbm_peak * 1e9) >= layer_flops / (tf_peak * 1e12) else "tensor",
+        "hbm_GBps": layer_bytes / t_layer / 1e9, "hbm_frac": layer_bytes / t_layer / 1e9 / hbm_peak,
+        "tensor_TFLOPs": layer_flops / t_layer / 1e12, "tensor_frac": layer_flops / t_layer / 1e12 / tf_peak,
+        "algorithmic_bytes_per_layer": layer_bytes, "us_per_layer": t_layer * 1e6}
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample (rank 0, N = 1 only)
     cpu_baseline = None
@@ -411,6 +456,7 @@ def main():
             "stage_us_per_layer": {k: (stage_ms[k] / stage_calls[k] * 1e3 if stage_calls.get(k) else None)
                                    for k in stage_ms},
             "roofline": roofline,
+            "layer_roofline": layer_roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 2 + e_host.numel() * 2,
