@@ -89,20 +89,25 @@ int env_int(const char* name, int dflt) {
 }
 }  // namespace
 
-int pdl_mask() {
-  static const int m = env_int("B200MOE_PDL", 0);
-  return m;
+// Tunables: environment default, overridable at run time through b200moe_config() (tests flip them per case).
+namespace {
+std::atomic<int> g_pdl{-1}, g_pdl_trig{-1}, g_prefetch{-1}, g_route{-1};
+int knob(std::atomic<int>& v, const char* env, int dflt) {
+  int cur = v.load(std::memory_order_relaxed);
+  if (cur < 0) {
+    cur = env_int(env, dflt);
+    if (cur < 0) cur = dflt;
+    v.store(cur, std::memory_order_relaxed);
+  }
+  return cur;
 }
+}  // namespace
 
-int pdl_trigger() {
-  static const int m = env_int("B200MOE_PDL_TRIG", 7);
-  return m;
-}
+int pdl_mask() { return knob(g_pdl, "B200MOE_PDL", 0); }
+int pdl_trigger() { return knob(g_pdl_trig, "B200MOE_PDL_TRIG", 7); }
+int route_mode() { return knob(g_route, "B200MOE_ROUTE", 1); }
 
-int prefetch_mode() {
-  static const int m = env_int("B200MOE_PREFETCH", 0);
-  return m;
-}
+int prefetch_mode() { return knob(g_prefetch, "B200MOE_PREFETCH", 0); }
 
 }  // namespace b200moe
 
@@ -134,8 +139,24 @@ int b200moe_device_supported(int dev) {
   return major == 10 ? 1 : 0;
 }
 
+int b200moe_debug_route_trace(void* dev_buf) {
+  set_route_trace(dev_buf);
+  return B200MOE_OK;
+}
+
 int b200moe_debug_ffn_trace(void* dev_buf, int records_per_cta) {
   set_ffn_trace(dev_buf, records_per_cta);
+  return B200MOE_OK;
+}
+
+int b200moe_config(const char* key, int value) {
+  if (!key || value < 0) return fail(B200MOE_ERR_ARG, "config: bad argument");
+  const std::string k(key);
+  if (k == "route") g_route.store(value);
+  else if (k == "pdl") g_pdl.store(value);
+  else if (k == "pdl_trig") g_pdl_trig.store(value);
+  else if (k == "prefetch") g_prefetch.store(value);
+  else return fail(B200MOE_ERR_ARG, "config: unknown key '%s'", key);
   return B200MOE_OK;
 }
 
@@ -329,6 +350,18 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
 
   cudaError_t e;
   const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
+  const int bn = choose_bn(Sk, a->E);
+  const int gmax = max_groups(Sk, a->E, bn);
+  const bool fused = a->top_k == 1;
+  const bool route = tc_gate && route_supported(S, a->D, Demb, a->E, a->top_k, a->dtype);
+  if (route) {
+    // small batch: gate and dispatch as one kernel (grid barrier instead of a kernel boundary)
+    StageScope t(0, stream);
+    e = launch_route(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->gate_mode,
+                     a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf,
+                     fused ? a->out : nullptr, a->residual, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "forward/route");
+  } else {
   {
     StageScope t(0, stream);
     if (tc_gate) {
@@ -344,10 +377,6 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
                       a->dtype, idx, score, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, "forward/gate");
-
-  const int bn = choose_bn(Sk, a->E);
-  const int gmax = max_groups(Sk, a->E, bn);
-  const bool fused = a->top_k == 1;
   {
     StageScope t(1, stream);
     e = launch_dispatch(a->x, idx, a->keep_expert_output ? nullptr : score, S, a->D, a->E, a->top_k, a->dtype, bn, w,
@@ -355,6 +384,7 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
                         tc_gate ? w.hist32 : nullptr, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, "forward/dispatch");
+  }
 
   FfnLaunch f{};
   f.xbuf = w.xbuf;
@@ -376,6 +406,10 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   f.out_dtype = a->dtype;
   f.top_k = a->top_k;
   f.ff_scale = a->ff_scale;
+  if (route) {
+    f.clear_ptr = w.hist32;
+    f.clear_ints = ((S + 31) / 32) * a->E;
+  }
   if (fused) {
     f.fused = 1;
     f.out = a->out;
@@ -533,7 +567,19 @@ int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, vo
 
   cudaError_t e = cudaSuccess;
   const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
-  if (S > 0 && (stages & 1)) {
+  const int bn = choose_bn(Sk, E_total);
+  const int gmax = max_groups(rows_cap, E_total, bn);
+  // all stages in one call: the dispatch kernel's last CTA also waits for the peers and builds the group table
+  const bool fold_wait = (stages & 3) == 3;
+  const bool route = tc_gate && route_supported(S, a->D, Demb, a->E, a->top_k, a->dtype);
+  if (route && (stages & 1)) {
+    StageScope t(0, stream);
+    e = launch_route(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->gate_mode, 0, idx,
+                     score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf, nullptr, nullptr, stream, &ep,
+                     fold_wait);
+    if (e != cudaSuccess) return cuda_fail(e, "ep_forward/route");
+  }
+  if (S > 0 && (stages & 1) && !route) {
     StageScope t(0, stream);
     if (tc_gate)
       e = launch_gate_tc(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
@@ -544,11 +590,7 @@ int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, vo
   }
   if (e != cudaSuccess) return cuda_fail(e, "ep_forward/gate");
 
-  const int bn = choose_bn(Sk, E_total);
-  const int gmax = max_groups(rows_cap, E_total, bn);
-  // all stages in one call: the dispatch kernel's last CTA also waits for the peers and builds the group table
-  const bool fold_wait = (stages & 3) == 3;
-  if (stages & 1) {
+  if ((stages & 1) && !route) {
     StageScope t(1, stream);
     e = launch_dispatch(a->x, idx, nullptr, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
                         a->mapping_out, w.xbuf, nullptr, nullptr, tc_gate && S > 0 ? w.hist32 : nullptr, stream, &ep,
@@ -584,6 +626,10 @@ int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, vo
   f.top_k = 1;
   f.ff_scale = 1.0f;
   f.ep = &ep;
+  if (route) {
+    f.clear_ptr = w.hist32;
+    f.clear_ints = ((S + 31) / 32) * a->E;
+  }
   if (stages & 2) {
     StageScope t(2, stream);
     e = launch_ffn(f, stream);

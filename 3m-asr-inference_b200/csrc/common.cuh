@@ -113,7 +113,7 @@ inline RouteWs carve_workspace(void* base, int S, int E, int D, int H, int top_k
   w.pos = reinterpret_cast<int*>(take(sizeof(int) * Sk));
   w.row_score = reinterpret_cast<float*>(take(sizeof(float) * Sk));
   w.groups = reinterpret_cast<GroupRec*>(take(sizeof(GroupRec) * gmax));
-  w.n_groups = reinterpret_cast<int*>(take(sizeof(int) * 4));
+  w.n_groups = reinterpret_cast<int*>(take(sizeof(int) * 8));  // [0] groups, [2..5] the route kernel's barrier words
   w.h_ready = reinterpret_cast<int*>(take(sizeof(int) * gmax));
   w.idx = reinterpret_cast<int*>(take(sizeof(int) * Sk));
   w.score = reinterpret_cast<float*>(take(sizeof(float) * Sk));
@@ -158,6 +158,16 @@ cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* gro
                                 int gmax, cudaStream_t stream);
 int choose_bn(int Sk, int E);
 
+// route.cu: gate + dispatch in one launch for small batches (bf16, E <= 32, top-1); same outputs as launch_gate_tc
+// followed by launch_dispatch.
+bool route_supported(int S, int D, int Demb, int E, int top_k, int dtype);
+void set_route_trace(void* dev_buf);  // debug: 16 records of 16 B per CTA, see tools/route_trace.py
+cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed, const float* br, const int* x_len,
+                         int B, int T, int D, int Demb, int E, int gate_mode, int keep_expert_output, int* idx,
+                         float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
+                         bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream,
+                         const EpPeers* ep = nullptr, bool ep_fold_wait = false);
+
 // ffn.cu
 struct FfnLaunch {
   const bf16* xbuf;   // [n_rows, D]
@@ -181,6 +191,8 @@ struct FfnLaunch {
   float ff_scale;
   int top_k;
   const EpPeers* ep;  // expert parallelism (un-fused only): rows of group g go to rank g.src's return buffer
+  int* clear_ptr;     // optional: `clear_ints` ints zeroed at kernel start (the route kernel's tagged histogram)
+  int clear_ints;
 };
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
 // Debug timeline: every following ffn launch records per-CTA events into dev_buf (16 B records); null disables.
@@ -211,6 +223,7 @@ void count_launch(int n = 1);
 int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN: kernel launched with the PDL attribute
 int pdl_trigger();   // same bits: kernel executes griddepcontrol.launch_dependents at its start
 int prefetch_mode();
+int route_mode();   // B200MOE_ROUTE: 1 (default) = fused gate + dispatch kernel for small batches, 0 = separate kernels
 constexpr int kPdlGate = 1, kPdlDispatch = 2, kPdlFfn = 4;
 
 // Kernel launch with the programmatic-stream-serialization attribute: the kernel may become resident as soon as every

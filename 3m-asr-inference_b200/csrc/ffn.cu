@@ -67,6 +67,8 @@ struct FfnParams {
   uint8_t* ep_out[kMaxEpWorld];     // ret_y of every rank
   int* ep_ret_flag[kMaxEpWorld];    // &ret_flag[my rank] in every rank's buffer
   int* ep_ctrl;                     // local control block
+  int* clear_ptr;   // zeroed at kernel start, spread over the CTAs (tagged histogram words of the route kernel)
+  int clear_ints;
   int dbg;          // timing experiments only (B200MOE_DBG): 1 = no phase-2 stores, 2 = no phase-1 stores, 4 = no residual
   uint64_t w_policy;  // L2 eviction policy of the weight tiles: evict-first when every tile is read once
   // debug timeline (ffn_kernel<.., true> only): per CTA `trace_cap` records of {tile, event, globaltimer lo, hi}
@@ -368,6 +370,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   }
   if (warp == 2) {
     ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  if (warp == 3 && p.clear_ptr != nullptr) {
+    ptx::pdl_wait();  // (the route kernel that wrote these words has completed: ordinary stream order or PDL)
+    for (int i = blockIdx.x * 32 + lane; i < p.clear_ints; i += gridDim.x * 32) p.clear_ptr[i] = 0;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -805,6 +811,8 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
       p.ep_ret_flag[r] = reinterpret_cast<int*>(a.ep->base[r] + a.ep->lay.ret_flag) + a.ep->rank;
     }
   }
+  p.clear_ptr = a.clear_ptr;
+  p.clear_ints = a.clear_ptr ? a.clear_ints : 0;
   p.groups = a.groups;
   p.n_groups = a.n_groups;
   p.h_ready = a.h_ready;

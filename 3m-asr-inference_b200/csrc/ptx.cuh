@@ -85,6 +85,10 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -178,6 +182,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
       " [%0], [%1, {%3, %4}], [%2], %5;"
       :
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+// 3D tiled load (used with a [K/64][rows][64] view of a row-major matrix: one instruction brings several 64-element
+// k-blocks of the same rows, each landing as its own 128B-swizzled K-major tile)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1,
+                                            int32_t c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 

@@ -1,0 +1,644 @@
+// Fused gate + dispatch for small batches ("route" kernel): router GEMM + softmax / top-1 and the stable scatter of the
+// token rows in ONE launch, separated by a grid-wide barrier instead of a kernel boundary.
+//
+// Reference behaviour covered (same as gate_tc.cu + dispatch.cu): router MatMul + SoftmaxTopKPluginDynamic
+// (trainer_3m_fix/layer/positionwise_feed_forward.py:169-207,225; TRTAPI++/plugin/softmax_topk_plugin/
+// softmax_topk_kernel.cu:26-120), NaiveGate with k = 1 (trainer_3m_fix/fmoe/gates.py:51-66), ScatterMapping +
+// ScatterMappingCopy (TRTAPI++/plugin/fmoe_expert_plugin/fmoe_expert_kernel.cu:25-128), moe_prepare_forward + MOEScatter
+// (trainer_3m_fix/fmoe/functions.py:13-52,62-86).
+//
+// Why: at the 3M-ASR batch sizes (50 .. a few thousand tokens per layer) gate and dispatch each move a few MB but cost
+// ~9 us apiece in launch / prologue / dependent-load latency, and the gate's 128-token tiles occupy only S/128 SMs, each
+// of which then has to pull 384 KB through one SM's memory port.  Here a tile is 32 tokens, so 3 200 tokens spread over
+// 100 SMs, and the token rows a CTA scatters are the ones it has just read.
+//
+//   phase 1 (per 32-token tile): "swap-AB" router GEMM on tcgen05 -- A = packed router, hi rows 0..31 / lo rows 32..63
+//     of a 128-row UMMA tile whose upper 64 rows are never loaded (their accumulator lanes are garbage and never read),
+//     B = 32 tokens x K, D[expert lane, token column] in TMEM.  Two warps transpose hi / lo through shared memory, then
+//     one thread per token does softmax / arg-max in registers exactly like gate_tc_kernel and the warp emits the tile's
+//     expert histogram.
+//   grid barrier (all CTAs are co-resident: grid <= number of SMs, one CTA per SM)
+//   phase 2 (per 32-token chunk): prefix over the histograms -> offsets, stable ranks by match_any, mapping / pos /
+//     row_score, 128-bit row copies into expert order (or, under expert parallelism, into the owner GPU's receive buffer).
+//     CTA 0 publishes counts / offsets / the FFN group table.
+#include <atomic>
+
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ep_device.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace b200moe {
+
+namespace {
+
+constexpr int kTok = 32;                    // tokens per tile == UMMA N == dispatch chunk
+constexpr int kRK = 64;                     // k-block
+constexpr int kHalfKb = 8;                  // k-blocks per pipeline slot: one TMA instruction per operand per slot
+constexpr int kRABlk = 64 * kRK * 2;        // 8 KiB: 64 packed router rows (hi | lo) of one k-block
+constexpr int kRBBlk = kTok * kRK * 2;      // 4 KiB: 32 tokens of one k-block
+constexpr int kRSlotA = kHalfKb * kRABlk;   // 64 KiB
+constexpr int kRSlotB = kHalfKb * kRBBlk;   // 32 KiB  (also the slack the 128-row UMMA reads past the last A block)
+constexpr int kRSlot = kRSlotA + kRSlotB;   // 96 KiB
+constexpr int kRSlots = 2;
+constexpr int kRThreads = 256;
+constexpr uint32_t kRTmemCols = 64;         // 2 accumulator buffers x 32 token columns
+
+struct RouteParams {
+  // gate
+  const float* br;
+  const int* x_len;
+  int* idx;
+  float* score;
+  int* hist32;  // [n_tiles, E]
+  int S, T, D, Demb, E, gate_mode;
+  // dispatch
+  const bf16* x;
+  bf16* xbuf;
+  int* counts;
+  int* offsets;
+  int* mapping;
+  int* pos;
+  float* row_score;
+  GroupRec* groups;
+  int* n_groups;
+  int* h_ready;
+  int bn, gmax;
+  int* counts_out;
+  int* offsets_out;
+  int* mapping_out;
+  bf16* drop_out;
+  const bf16* drop_residual;
+  int keep_expert_output;
+  // grid barrier: two 64-bit state words {nonce, count}; see grid_arrive
+  unsigned long long* bar;
+  unsigned nonce;
+  int ep_fold_wait;
+  uint4* trace;  // debug timeline: 16 records per CTA {event, clock64 lo, hi, -}; slots 14 / 15 hold %globaltimer
+};
+
+__device__ __forceinline__ void rtrace(const RouteParams& p, int ev) {
+  if (p.trace != nullptr) {
+    const unsigned long long c = static_cast<unsigned long long>(clock64());
+    p.trace[blockIdx.x * 16 + ev] = make_uint4(static_cast<uint32_t>(ev), static_cast<uint32_t>(c),
+                                               static_cast<uint32_t>(c >> 32), 1u);
+  }
+}
+__device__ __forceinline__ void rtrace_sync(const RouteParams& p, int slot) {
+  if (p.trace != nullptr) {
+    const unsigned long long g = ptx::globaltimer_ns();
+    p.trace[blockIdx.x * 16 + slot] = make_uint4(static_cast<uint32_t>(slot), static_cast<uint32_t>(g),
+                                                 static_cast<uint32_t>(g >> 32), 1u);
+  }
+}
+
+// ---- grid barrier that needs no zero-initialised memory ----------------------------------------------------------------
+// state = (nonce << 32) | arrivals.  The first arrival of a launch finds a foreign nonce in the upper half (garbage, or the
+// complement the previous launch left behind) and installs {nonce, 1} with a compare-and-swap; everybody else adds 1.
+// The last CTA to finish the kernel overwrites both words with the complemented nonce, so a CUDA-graph replay (same
+// nonce every time) starts clean as well.
+__device__ __forceinline__ unsigned grid_arrive(unsigned long long* st, unsigned nonce) {
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(st);
+  while (true) {
+    if (static_cast<unsigned>(old >> 32) == nonce) {
+      const unsigned long long prev = atomicAdd(st, 1ull);
+      return static_cast<unsigned>(prev & 0xffffffffu) + 1u;
+    }
+    const unsigned long long nw = (static_cast<unsigned long long>(nonce) << 32) | 1ull;
+    const unsigned long long prev = atomicCAS(st, old, nw);
+    if (prev == old) return 1u;
+    old = prev;
+  }
+}
+
+template <bool kEp>
+__global__ void __launch_bounds__(kRThreads, 1)
+route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_e,
+             const __grid_constant__ CUtensorMap tm_wx, const __grid_constant__ CUtensorMap tm_we, const RouteParams p,
+             const EpPeers ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_base + kRSlots * kRSlot;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kRSlots + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kRSlots + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kRSlots + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kRSlots + 4);
+  uint8_t* misc = smem_raw + (tmem_slot - smem_base) + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(misc - 16);
+  float* s_br = reinterpret_cast<float*>(misc);               // [32]
+  float* s_hi = s_br + 32;                                     // [32][33]
+  float* s_lo = s_hi + 32 * 33;                                // [32][33]
+  int* s_hist = reinterpret_cast<int*>(s_lo + 32 * 33);       // [32]
+  int* s_total = s_hist + 32;                                  // [32]  tokens per expert over all chunks
+  int* s_before = s_total + 32;                                // [32]  ... over the chunks before the current one
+  int* s_off = s_before + 32;                                  // [33]  exclusive offsets
+  int* s_scratch = s_off + 33;                                 // [33]
+  int* s_dst = s_scratch + 33;                                 // [32]  destination row of each token of the chunk
+  int* s_exp = s_dst + 32;                                     // [32]
+  int* s_part = s_exp + 32;                                    // [8][2][32]
+  int* s_lastp = s_part + 512;                                 // [1]
+
+  if (threadIdx.x == 0) {
+    rtrace_sync(p, 14);
+    rtrace(p, 0);
+  }
+  const int E = p.E;
+  const int n_tiles = (p.S + kTok - 1) / kTok;
+  // the K dimension comes in (up to) two parts: the embed columns and the x columns (the reference's concat,
+  // positionwise_feed_forward.py:225); each part is one pipeline slot filled by two TMA instructions
+  const int kb_e = p.Demb / kRK;
+  const int kb_x = p.D / kRK;
+  const int n_parts = kb_e > 0 ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_x);
+    ptx::prefetch_tensormap(&tm_wx);
+    if (kb_e > 0) {
+      ptx::prefetch_tensormap(&tm_e);
+      ptx::prefetch_tensormap(&tm_we);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kRSlots; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), 2);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kRTmemCols>(tmem_slot);
+  if (warp == 3) s_br[lane] = (p.br != nullptr && lane < E) ? p.br[lane] : 0.0f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) rtrace(p, 1);
+
+  // ================================================ phase 1: gate ================================================
+  if (warp == 0) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int part = 0; part < n_parts; ++part) {
+          const bool is_e = n_parts == 2 && part == 0;
+          const int nkb = is_e ? kb_e : kb_x;
+          ptx::mbar_wait(empty_bar(slot), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(slot), static_cast<uint32_t>(nkb) * (kRABlk + kRBBlk));
+          const uint32_t sa = smem_base + slot * kRSlot;
+          // router k-blocks of this part: rows 0..63 of the packed router, k-blocks [kb0, kb0 + nkb)
+          ptx::tma_load_3d(sa, is_e ? &tm_we : &tm_wx, full_bar(slot), 0, 0, is_e ? 0 : kb_e, ptx::kEvictLast);
+          // the tile's 32 tokens, all k-blocks of the part
+          if (is_e)
+            ptx::tma_load_3d(sa + kRSlotA, &tm_e, full_bar(slot), 0, t * kTok, 0, ptx::kEvictFirst);
+          else
+            ptx::tma_load_3d(sa + kRSlotA, &tm_x, full_bar(slot), 0, t * kTok, 0, ptx::kEvictLast);
+          if (++slot == kRSlots) {
+            slot = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      rtrace(p, 2);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc(1u /*bf16*/, 128, kTok);
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kTok;
+        for (int part = 0; part < n_parts; ++part) {
+          const int nkb = (n_parts == 2 && part == 0) ? kb_e : kb_x;
+          ptx::mbar_wait(full_bar(slot), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + slot * kRSlot;
+          for (int j = 0; j < nkb; ++j) {
+            // A: 64 loaded rows + 64 rows of whatever follows (accumulator lanes 64..127 are never read)
+            const uint64_t a_desc = ptx::make_kmajor_sw128_desc(sa + j * kRABlk);
+            const uint64_t b_desc = ptx::make_kmajor_sw128_desc(sa + kRSlotA + j * kRBBlk);
+#pragma unroll
+            for (int k = 0; k < kRK / 16; ++k)
+              ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (part | j | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(slot));
+          if (part == n_parts - 1) ptx::umma_commit(tfull_bar(as));
+          if (++slot == kRSlots) {
+            slot = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 4 || warp == 5) {
+    // warp 4: TMEM lanes 0..31 = hi logits of experts 0..31; warp 5: lanes 32..63 = lo parts
+    const int q = warp & 3;
+    float* dstm = q == 0 ? s_hi : s_lo;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      if (q == 0 && lane == 0 && it == 0) rtrace(p, 3);
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kTok, r);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dstm[lane * 33 + j] = __uint_as_float(r[j]);
+      if (q == 0) s_hist[lane] = 0;
+      ptx::named_bar_sync(1, 64);
+      if (q == 0) {
+        // one thread per token: softmax / arg-max in registers (same arithmetic and tie rule as gate_tc_kernel)
+        const int tok = t * kTok + lane;
+        bool valid = tok < p.S;
+        if (valid && p.x_len != nullptr) valid = (tok % p.T) < p.x_len[tok / p.T];
+        float l[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          l[e] = s_hi[e * 33 + lane] + s_lo[e * 33 + lane] + s_br[e];
+          if (e >= E) l[e] = -CUDART_INF_F;
+        }
+        float bv = l[0];
+        int bi = 0;
+#pragma unroll
+        for (int e = 1; e < 32; ++e) {
+          if (l[e] > bv) {  // strict: the lowest index wins exact ties
+            bv = l[e];
+            bi = e;
+          }
+        }
+        float denom = 1.0f;
+        if (p.gate_mode == B200MOE_GATE_3M) {
+          denom = 0.0f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) denom += expf(l[e] - bv);  // exp(-inf) = 0 for the padded experts
+        }
+        const int sel = valid ? bi : -1;
+        if (tok < p.S) {
+          p.idx[tok] = sel;
+          p.score[tok] = valid ? expf(bv - bv) / denom : 0.0f;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, sel);
+        if (sel >= 0 && lane == __ffs(peers) - 1) s_hist[sel] = __popc(peers);
+        __syncwarp();
+        // Every histogram word validates itself: (launch tag << 8) | count.  Other CTAs need nothing else from this
+        // tile (idx / score are re-read by this CTA only), so no fence and no release store stand between the arg-max
+        // and the other CTAs seeing the row.
+        if (lane < E) p.hist32[static_cast<size_t>(t) * E + lane] = static_cast<int>((p.nonce << 8) | s_hist[lane]);
+        if (lane == 0 && it == 0) rtrace(p, 4);
+      }
+      ptx::named_bar_sync(1, 64);  // s_hi / s_lo / s_hist free for the next tile
+    }
+  }
+
+  // ================================================ grid barrier + prefix ================================================
+  // There is no counter to contend on and no separate wait: every histogram word carries this launch's tag, every CTA
+  // needs every row for its prefix sums anyway, so it simply re-reads a word until the tag is there.  All CTAs of the
+  // grid are co-resident (grid <= SM count, one CTA per SM), so waiting for the other tiles cannot deadlock.
+  __syncthreads();
+  if (threadIdx.x == 0) rtrace(p, 5);
+  {
+    const int e = threadIdx.x & 31;
+    const int part = threadIdx.x >> 5;  // 8 parts
+    const int c_first = blockIdx.x;
+    const unsigned tag = p.nonce & 0x00ffffffu;
+    const unsigned long long deadline = ptx::globaltimer_ns() + 2000000000ull;
+    int total = 0, before = 0;
+    if (e < E)
+      for (int r0 = part; r0 < n_tiles; r0 += 8 * 8) {
+        // eight rows per batch: the loads are independent and all in flight together (one L2 round trip per batch
+        // when the rows are already there), only a word whose tag is still missing is polled on its own
+        unsigned w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 8 * i;
+          w[i] = r < n_tiles ? static_cast<unsigned>(*(const volatile int*)(p.hist32 + static_cast<size_t>(r) * E + e))
+                             : (tag << 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 8 * i;
+          while ((w[i] >> 8) != tag) {
+            __nanosleep(20);
+            if (ptx::globaltimer_ns() > deadline) __trap();  // logic error or foreign process on the SMs: fail, no hang
+            w[i] = static_cast<unsigned>(*(const volatile int*)(p.hist32 + static_cast<size_t>(r) * E + e));
+          }
+          const int v = static_cast<int>(w[i] & 0xffu);
+          total += v;
+          if (r < c_first) before += v;
+        }
+      }
+    s_part[part * 32 + e] = total;
+    s_part[256 + part * 32 + e] = before;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int tot = 0, bef = 0;
+#pragma unroll
+    for (int pt = 0; pt < 8; ++pt) {
+      tot += s_part[pt * 32 + threadIdx.x];
+      bef += s_part[256 + pt * 32 + threadIdx.x];
+    }
+    tot = static_cast<int>(threadIdx.x) < E ? tot : 0;
+    s_total[threadIdx.x] = tot;
+    s_before[threadIdx.x] = bef;
+    // exclusive scan over the experts within the warp
+    int incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, d);
+      if (static_cast<int>(threadIdx.x) >= d) incl += n;
+    }
+    s_off[threadIdx.x] = incl - tot;
+    if (threadIdx.x == 31) s_off[32] = incl;
+    if (static_cast<int>(threadIdx.x) == E - 1) s_off[E] = incl;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    rtrace(p, 6);
+    rtrace(p, 7);
+  }
+
+  for (int c = blockIdx.x; c < n_tiles; c += gridDim.x) {
+    if (c != static_cast<int>(blockIdx.x)) {
+      // later chunks of this CTA (more tiles than SMs): add the rows in between
+      if (threadIdx.x < 32) {
+        int add = 0;
+        if (static_cast<int>(threadIdx.x) < E)
+          for (int r = c - gridDim.x; r < c; ++r) add += p.hist32[static_cast<size_t>(r) * E + threadIdx.x] & 0xff;
+        s_before[threadIdx.x] += add;
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+      const int tok = c * kTok + lane;
+      int e = -1;
+      if (tok < p.S) {
+        e = p.idx[tok];
+        if (e < 0 || e >= E) e = -1;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, e);
+      int dst = -1;
+      if (e >= 0) dst = s_off[e] + s_before[e] + __popc(peers & ((1u << lane) - 1u));
+      s_dst[lane] = dst;
+      s_exp[lane] = e;
+      if (tok < p.S) {
+        p.mapping[tok] = dst;
+        if (p.mapping_out) p.mapping_out[tok] = dst;
+        if (dst >= 0) {
+          p.pos[dst] = tok;
+          p.row_score[dst] = p.keep_expert_output ? 1.0f : p.score[tok];
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && c == static_cast<int>(blockIdx.x)) rtrace(p, 8);
+    // row copies: warp w moves rows w, w + 8, w + 16, w + 24 of the chunk, all four in flight (2 x 16 B per lane each)
+    {
+      const bf16* src[4];
+      bf16* drow[4];
+      int d[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = warp + r * 8;
+        const int tok = c * kTok + j;
+        d[r] = tok < p.S ? s_dst[j] : -1;
+        src[r] = p.x + static_cast<size_t>(tok < p.S ? tok : 0) * p.D;
+        drow[r] = p.xbuf + static_cast<size_t>(d[r] < 0 ? 0 : d[r]) * p.D;
+        if (kEp && d[r] >= 0) {
+          const int dest = s_exp[j] / ep.E_local;
+          const int slot = d[r] - s_off[dest * ep.E_local];
+          drow[r] = reinterpret_cast<bf16*>(ep.base[dest] + ep.lay.recv_x) +
+                    (static_cast<size_t>(ep.rank) * ep.cap + slot) * p.D;
+        }
+      }
+      for (int v = lane; v < p.D / 8; v += 32) {
+        uint4 regs[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (d[r] >= 0) regs[r] = __ldg(reinterpret_cast<const uint4*>(src[r]) + v);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (d[r] >= 0) reinterpret_cast<uint4*>(drow[r])[v] = regs[r];
+      }
+      if (p.drop_out != nullptr) {
+        // dropped tokens (padding): output row = residual row (or zero); the fused FFN epilogue never touches them
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int tok = c * kTok + warp + r * 8;
+          if (tok < p.S && d[r] < 0) {
+            const size_t row = static_cast<size_t>(tok) * p.D;
+            for (int k = lane; k < p.D; k += 32)
+              p.drop_out[row + k] = p.drop_residual ? p.drop_residual[row + k] : __float2bfloat16_rn(0.0f);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      p.counts[e] = s_total[e];
+      if (p.counts_out) p.counts_out[e] = s_total[e];
+    }
+    for (int e = threadIdx.x; e <= E; e += blockDim.x) {
+      p.offsets[e] = s_off[e];
+      if (p.offsets_out) p.offsets_out[e] = s_off[e];
+    }
+    if (!kEp) {
+      // FFN group table: expert e contributes ceil(count / bn) groups, in expert order
+      if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int e = 0; e < E; ++e) {
+          s_scratch[e] = acc;
+          acc += (s_total[e] + p.bn - 1) / p.bn;
+        }
+        p.n_groups[0] = acc;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const int cnt = s_total[e];
+        const int nt = (cnt + p.bn - 1) / p.bn;
+        for (int j = 0; j < nt; ++j) {
+          GroupRec r;
+          r.expert = e;
+          r.row0 = s_off[e] + j * p.bn;
+          r.nrows = min(p.bn, cnt - j * p.bn);
+          r.src = 0;
+          r.orow0 = r.row0;
+          r.pad[0] = r.pad[1] = r.pad[2] = 0;
+          p.groups[s_scratch[e] + j] = r;
+        }
+      }
+      for (int g = threadIdx.x; g < p.gmax; g += blockDim.x) p.h_ready[g] = 0;
+    }
+  }
+
+  // ================================================ completion ================================================
+  // The histogram words must not survive into a replay of the same CUDA graph (same tag): the expert-FFN kernel that
+  // always follows clears them (FfnLaunch::clear_ptr).  Only expert parallelism needs to know the last CTA here.
+  __syncthreads();
+  if (threadIdx.x == 0) rtrace(p, 9);
+  if (kEp) {
+    if (threadIdx.x == 0) {
+      ptx::fence_acq_rel_sys();  // this CTA's pushes are performed at the peers (one NVLink round trip)
+      const int last = grid_arrive(p.bar, p.nonce) == gridDim.x;
+      *s_lastp = last;
+      if (last) {
+        __threadfence();
+        // leave the counter with a foreign nonce: the next launch (or CUDA-graph replay, same nonce) starts from scratch
+        p.bar[0] = static_cast<unsigned long long>(~p.nonce) << 32;
+      }
+    }
+    __syncthreads();
+  }
+  if (kEp && *s_lastp) {
+    int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
+    const int seq = ctrl[0] + 1;
+    const int El = ep.E_local;
+    for (int i = threadIdx.x; i < ep.world * (El + 1); i += blockDim.x) {
+      const int dest = i / (El + 1);
+      const int k = i - dest * (El + 1);
+      int* rc = reinterpret_cast<int*>(ep.base[dest] + ep.lay.recv_cnt) + ep.rank * (El + 1);
+      rc[k] = k < El ? s_total[dest * El + k] : s_off[dest * El];
+    }
+    if (threadIdx.x == 0) ctrl[0] = seq;
+    __syncthreads();
+    if (threadIdx.x < ep.world)
+      ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, seq);
+    if (p.ep_fold_wait) {
+      __syncthreads();
+      // E_local * world == E <= 32 here: s_part (512 ints) holds both scratch arrays
+      ep_wait_and_build_groups(ep, seq, p.bn, p.groups, p.n_groups, p.h_ready, p.gmax, s_part,
+                               s_part + ep.world * (El + 1));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kRTmemCols>(tmem_base);
+  }
+  if (threadIdx.x == 0) {
+    rtrace(p, 10);
+    rtrace_sync(p, 15);
+  }
+}
+
+std::atomic<unsigned> g_route_nonce{1};
+void* g_route_trace = nullptr;
+
+}  // namespace
+
+void set_route_trace(void* dev_buf) { g_route_trace = dev_buf; }
+
+bool route_supported(int S, int D, int Demb, int E, int top_k, int dtype) {
+  // up to two 32-token tiles per SM; beyond that the 128-token gate re-reads the router far less often
+  return route_mode() != 0 && dtype == B200MOE_BF16 && top_k == 1 && E <= 32 && S > 0 && S <= 2 * kTok * num_sms() &&
+         D % kRK == 0 && Demb % kRK == 0 && D > 0 && D <= kHalfKb * kRK && Demb <= kHalfKb * kRK;
+}
+
+cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed, const float* br, const int* x_len,
+                         int B, int T, int D, int Demb, int E, int gate_mode, int keep_expert_output, int* idx,
+                         float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
+                         bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream, const EpPeers* ep,
+                         bool ep_fold_wait) {
+  const int S = B * T;
+  if (embed == nullptr) Demb = 0;
+  if (!route_supported(S, D, Demb, E, 1, B200MOE_BF16)) return cudaErrorInvalidValue;
+  if (ep != nullptr && (ep->world * ep->E_local != E || S > ep->cap || ep->D != D)) return cudaErrorInvalidValue;
+  // [K/64][rows][64] views: one TMA instruction per operand and K part (see make_tmap_bf16_kblocks)
+  CUtensorMap tx, te, twx, twe;
+  if (!make_tmap_bf16_kblocks(&tx, x, S, D, kTok, D / kRK)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_kblocks(&twx, wr_packed, 64, static_cast<uint64_t>(D + Demb), 64, D / kRK))
+    return cudaErrorInvalidValue;
+  if (Demb > 0) {
+    if (!make_tmap_bf16_kblocks(&te, embed, S, Demb, kTok, Demb / kRK)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_kblocks(&twe, wr_packed, 64, static_cast<uint64_t>(D + Demb), 64, Demb / kRK))
+      return cudaErrorInvalidValue;
+  } else {
+    te = tx;
+    twe = twx;
+  }
+  RouteParams p;
+  p.br = br;
+  p.x_len = x_len;
+  p.idx = idx;
+  p.score = score;
+  p.hist32 = ws.hist32;
+  p.S = S;
+  p.T = T;
+  p.D = D;
+  p.Demb = Demb;
+  p.E = E;
+  p.gate_mode = gate_mode;
+  p.x = static_cast<const bf16*>(x);
+  p.xbuf = xbuf;
+  p.counts = ws.counts;
+  p.offsets = ws.offsets;
+  p.mapping = ws.mapping;
+  p.pos = ws.pos;
+  p.row_score = ws.row_score;
+  p.groups = ws.groups;
+  p.n_groups = ws.n_groups;
+  p.h_ready = ws.h_ready;
+  p.bn = bn;
+  p.gmax = ep ? max_groups(ep->world * ep->cap, E, bn) : max_groups(S, E, bn);
+  p.counts_out = counts_out;
+  p.offsets_out = offsets_out;
+  p.mapping_out = mapping_out;
+  p.drop_out = ep ? nullptr : static_cast<bf16*>(drop_out);
+  p.drop_residual = static_cast<const bf16*>(drop_residual);
+  p.keep_expert_output = keep_expert_output;
+  p.bar = reinterpret_cast<unsigned long long*>(ws.n_groups + 2);  // completion counter {nonce, CTAs done}
+  // 24-bit launch tag, never 0: a plain count left in the same workspace by the split gate kernel has tag 0
+  unsigned nonce = g_route_nonce.fetch_add(1, std::memory_order_relaxed) & 0x00ffffffu;
+  if (nonce == 0) nonce = g_route_nonce.fetch_add(1, std::memory_order_relaxed) & 0x00ffffffu;
+  p.nonce = nonce;
+  p.ep_fold_wait = ep_fold_wait ? 1 : 0;
+  p.trace = static_cast<uint4*>(g_route_trace);
+  EpPeers epv{};
+  if (ep) epv = *ep;
+  const size_t smem = kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 16 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 64);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(route_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(route_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int n_tiles = (S + kTok - 1) / kTok;
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  cudaError_t e;
+  if (ep)
+    e = launch_kernel(route_kernel<true>, dim3(grid), dim3(kRThreads), smem, stream, 0, tx, te, twx, twe, p, epv);
+  else
+    e = launch_kernel(route_kernel<false>, dim3(grid), dim3(kRThreads), smem, stream, 0, tx, te, twx, twe, p, epv);
+  count_launch();
+  return e;
+}
+
+}  // namespace b200moe

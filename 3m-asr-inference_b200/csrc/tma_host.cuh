@@ -43,6 +43,24 @@ inline bool make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uin
   return r == CUDA_SUCCESS;
 }
 
+// The same row-major bf16 matrix [rows, cols] viewed as [cols / 64][rows][64]: a box of `box_kblocks` k-blocks x
+// `box_rows` rows lands in shared memory as box_kblocks consecutive K-major tiles of box_rows x 128 bytes, each
+// 128B-swizzled -- i.e. several pipeline stages' worth of operand with ONE TMA instruction (issuing a TMA costs
+// ~130 ns of the producer thread regardless of the box size).  cols must be a multiple of 64.
+inline bool make_tmap_bf16_kblocks(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                   uint32_t box_kblocks) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc || cols % 64 != 0 || box_kblocks == 0 || box_kblocks > 256 || box_rows > 256) return false;
+  cuuint64_t dims[3] = {64, rows, cols / 64};
+  cuuint64_t strides[2] = {cols * sizeof(bf16), 64 * sizeof(bf16)};
+  cuuint32_t box[3] = {64, box_rows, box_kblocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

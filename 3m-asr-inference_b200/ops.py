@@ -54,6 +54,11 @@ def launch_count() -> int:
     return int(_lib.load().b200moe_launch_count())
 
 
+def config(key: str, value: int) -> None:
+    """Run-time tunables ("route", "pdl", "pdl_trig", "prefetch"); see include/b200moe.h."""
+    _lib.check(_lib.load().b200moe_config(key.encode(), int(value)), "b200moe_config")
+
+
 def profile_enable(on: bool) -> None:
     _lib.check(_lib.load().b200moe_profile_enable(int(on)), "b200moe_profile_enable")
 

@@ -233,6 +233,11 @@ int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate
 int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int T, int E, int data_type,
                                  void* value, int* idx, cudaStream_t stream);
 
+/* Run-time tunables (each also has an environment default, B200MOE_<KEY>): "route" 1/0 fused gate + dispatch kernel for
+ * small batches; "pdl" / "pdl_trig" bit masks (1 gate, 2 dispatch, 4 expert FFN) for programmatic dependent launch;
+ * "prefetch" 0/1/2 L2 prefetch of the expert weights from the gate kernel.  Results do not depend on any of them. */
+int b200moe_config(const char* key, int value);
+
 /* Optional per-stage device timing with CUDA events around each stage of b200moe_forward (eager launches only, not
  * under graph capture). stage_ms / stage_calls are HOST arrays of 4: 0 gate, 1 dispatch, 2 expert_ffn (with the fused
  * combine epilogue when top_k == 1), 3 combine.  b200moe_profile_read waits for the recorded work and resets. */
@@ -243,6 +248,9 @@ int b200moe_profile_read(float* stage_ms, int* stage_calls);
  * 16-byte records {tile, event, clock64 lo, hi}: 4 roles (TMA producer, MMA issuer, epilogue, publisher) x
  * records_per_cta/4 slots per CTA, CTA-major.  dev_buf must hold 148 * records_per_cta records.  See tools/ffn_trace.py. */
 int b200moe_debug_ffn_trace(void* dev_buf, int records_per_cta);
+
+/* Debug: timeline of the fused gate + dispatch kernel, 16 records of 16 bytes per CTA (148 CTAs at most). */
+int b200moe_debug_route_trace(void* dev_buf);
 
 /* Number of kernels this library launched on behalf of the calling process (for bench accounting). */
 unsigned long long b200moe_launch_count(void);

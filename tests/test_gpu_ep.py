@@ -13,6 +13,14 @@ from conftest import pkg, rel_l2
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=[1, 0], ids=["route", "split"])
+def route_mode(request, ops):
+    """Every case runs with the fused gate + dispatch kernel (small batches take it) and with the separate kernels."""
+    ops.config("route", request.param)
+    yield
+    ops.config("route", 1)
+
 BF16_REL_L2 = 1e-2
 E, D, H, DEMB = 32, 512, 1024, 512
 

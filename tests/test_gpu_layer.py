@@ -6,6 +6,14 @@ from conftest import load_golden, pkg, rel_l2
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=[1, 0], ids=["route", "split"])
+def route_mode(request, ops):
+    """Every case runs with the fused gate + dispatch kernel (small batches take it) and with the separate kernels."""
+    ops.config("route", request.param)
+    yield
+    ops.config("route", 1)
+
 BF16_REL_L2 = 1e-2   # north_star tolerance for BF16 outputs vs the fp32 reference
 
 
