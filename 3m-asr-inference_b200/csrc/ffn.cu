@@ -60,6 +60,7 @@ struct FfnParams {
   int E, D, H, bn, act, fused;
   int stages;
   int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
+  int kps;  // k-blocks (of 64) per pipeline stage: one TMA instruction per operand brings all of them
   int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
   // expert parallelism: results go to the source rank's return buffer over peer-mapped memory (NVLink)
   int ep;                           // 0 = off
@@ -109,7 +110,7 @@ struct Tracer {
   // CTA's cycle counts on the common ns time base.
   __device__ __forceinline__ void rec(int tile, int ev) {
     if constexpr (kTrace) {
-      if (base != nullptr && n < cap) {
+      if (base != nullptr && n < cap - 2) {  // the last two slots stay free for the closing sync() pair
         const unsigned long long t = static_cast<unsigned long long>(clock64());
         base[n++] = make_uint4(static_cast<uint32_t>(tile), static_cast<uint32_t>(ev), static_cast<uint32_t>(t),
                                static_cast<uint32_t>(t >> 32));
@@ -318,7 +319,14 @@ struct Vec4Io<__half> {
   }
 };
 
-template <typename OutT, bool kTrace>
+// kCtas == 2: CTA pairs (cta_group::2).  The two CTAs of a cluster sit on neighbouring SMs and issue ONE tcgen05.mma
+// over 256 weight rows x BN tokens: each CTA stages its own 128 weight rows and HALF of the token tile, the tensor
+// cores read the other half out of the peer's shared memory.  Per CTA and k-block that is 16 KiB + BN/2 x 128 B through
+// the SM's memory port instead of 16 KiB + BN x 128 B -- at BN = 256 a third less L2 -> SM traffic and shared-memory
+// bandwidth, which is what bounds the single-CTA kernel in the compute-bound regime (128 x 256 tiles: 85 FLOP per
+// byte moved into the SM, while the MMA rate asks for ~190).  Everything else (tile schedule over pairs, the h
+// dependency flags, the epilogue of each CTA over its own 128 accumulator rows) is the single-CTA design.
+template <typename OutT, bool kTrace, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
            const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const FfnParams p) {
@@ -328,10 +336,20 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const uint32_t cta_rank = kCtas == 2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int stages = p.stages;
-  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.bn) * kBlockK * 2;
+  const int b_rows = p.bn / kCtas;  // token rows this CTA stages per k-block
+  // A pipeline stage holds kps k-blocks of both operands.  Issuing a TMA costs the producer thread ~130 ns whatever
+  // the box size, and at 128 x 256 x 64 per k-block the tensor cores need a new k-block every ~300 ns: with one k-block
+  // per instruction the producer, not the memory system, paces the MMAs (measured: 70-76 % of the MMA rate).
+  const int kps = p.kps;
+  const uint32_t a_blk_bytes = kBlockM * kBlockK * 2;                            // 16 KiB per k-block
+  const uint32_t b_blk_bytes = static_cast<uint32_t>(b_rows) * kBlockK * 2;
+  const uint32_t a_stage_bytes = a_blk_bytes * kps;
+  const uint32_t b_stage_bytes = b_blk_bytes * kps;
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + stages * kAStageBytes;
+  const uint32_t smem_b = smem_base + stages * a_stage_bytes;
   const uint32_t bar_base = smem_b + stages * b_stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -357,26 +375,28 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(full_bar(s), kCtas);  // pair: the leader's barrier takes one arrival from each CTA's producer
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), kEpiThreads / 32);
+      ptx::mbar_init(tempty_bar(s), kCtas * kEpiThreads / 32);  // pair: both CTAs' epilogue warps release the leader's
       ptx::mbar_init(pfull_bar(s), kEpiThreads / 32);
       ptx::mbar_init(pempty_bar(s), 1);
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<kTmemCols>(tmem_slot);
+    if constexpr (kCtas == 2) ptx::tmem_alloc_pair<kTmemCols>(tmem_slot);
+    else ptx::tmem_alloc<kTmemCols>(tmem_slot);
   }
   if (warp == 3 && p.clear_ptr != nullptr) {
     ptx::pdl_wait();  // (the route kernel that wrote these words has completed: ordinary stream order or PDL)
     for (int i = blockIdx.x * 32 + lane; i < p.clear_ints; i += gridDim.x * 32) p.clear_ptr[i] = 0;
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) ptx::cluster_sync();  // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -384,64 +404,80 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   // overlaps the tail of the dispatch kernel.  The routing tables, xbuf and every output come after this wait.
   ptx::pdl_wait();
   const int ng = *p.n_groups;
-  const int m1 = p.H / kBlockM;
-  const int m2 = p.D / kBlockM;
+  // a tile is kCtas x 128 weight rows of one group; this CTA's share is rows (mb * kCtas + rank) * 128 ...
+  const int m1 = p.H / (kBlockM * kCtas);
+  const int m2 = p.D / (kBlockM * kCtas);
+  const int m1_flags = p.H / kBlockM;  // every CTA publishes its own 128-row slice of h: flags per group
   const int lag = min(p.lag, ng);
   const int n_tiles = ng * (m1 + m2);
-  const int kb1 = p.D / kBlockK;  // k-blocks of the first GEMM
-  const int kb2 = p.H / kBlockK;
+  const int tile0 = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kCtas == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int kb1 = p.D / (kBlockK * kps);  // pipeline stages per tile of the first GEMM
+  const int kb2 = p.H / (kBlockK * kps);
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kAStageBytes + b_stage_bytes;
+      const uint32_t tx_bytes = (a_stage_bytes + b_stage_bytes) * kCtas;  // both CTAs' tiles land on the leader's barrier
+      // arm a stage: the leader expects the bytes of both CTAs, the other CTA only announces that its loads are issued
+      auto arm = [&](int st) {
+        if (kCtas == 1 || leader) ptx::mbar_arrive_expect_tx(full_bar(st), tx_bytes);
+        else ptx::mbar_arrive_cluster(full_bar(st) & ptx::kPeerBitMask);
+      };
+      // rows [row, ..) x k-blocks [kb * kps, (kb + 1) * kps) of a [K/64][rows][64] view
+      auto load = [&](uint32_t dst, const CUtensorMap* tm, int st, int kb, int row, uint64_t pol) {
+        if constexpr (kCtas == 2)
+          ptx::tma_load_3d_pair(dst, tm, full_bar(st) & ptx::kPeerBitMask, 0, row, kb * kps, pol);
+        else
+          ptx::tma_load_3d(dst, tm, full_bar(st), 0, row, kb * kps, pol);
+      };
       Tracer<kTrace> tr(p, 0);
       tr.sync();
       tr.rec(-1, kEvKernelStart);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = tile0; t < n_tiles; t += tile_step) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
         const GroupRec gr = p.groups[tl.g];
         tr.rec(t, kEvProdTileStart);
         const CUtensorMap* tm_a = tl.phase == 1 ? &tm_w1 : &tm_w2;
         const CUtensorMap* tm_b = tl.phase == 1 ? &tm_x : &tm_h;
-        const int a_row = gr.expert * (tl.phase == 1 ? p.H : p.D) + tl.mb * kBlockM;
+        const int a_row = gr.expert * (tl.phase == 1 ? p.H : p.D) + (tl.mb * kCtas + static_cast<int>(cta_rank)) * kBlockM;
+        const int b_row = gr.row0 + static_cast<int>(cta_rank) * b_rows;
         const int nkb = tl.phase == 1 ? kb1 : kb2;
         int pre = 0;
-        if (tl.phase == 2) {
+        const bool dep_pending = tl.phase == 2 && ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags;
+        if (tl.phase == 2 && !dep_pending) ptx::fence_proxy_async_all();  // h was written through the generic proxy
+        if (dep_pending) {
           // The W2 tiles do not depend on h: fill the ring with them first, then wait until every phase-1 tile of this
           // group has published its slice of h and add the h tiles to the same stages (one full barrier per stage
-          // expects both).
+          // expects both).  (Only when h is in fact late: in steady state this order would hold back the first h tile
+          // until the whole ring has been re-filled with weights, a ~1.5 us bubble per tile.)
           pre = nkb < stages ? nkb : stages;
           const int stage0 = stage;
           for (int kb = 0; kb < pre; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-            ptx::tma_load_2d(smem_a + stage * kAStageBytes, tm_a, full_bar(stage), kb * kBlockK, a_row,
-                             p.w_policy);
+            arm(stage);
+            load(smem_a + stage * a_stage_bytes, tm_a, stage, kb, a_row, p.w_policy);
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1) __nanosleep(32);
+          while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) __nanosleep(32);
           ptx::fence_proxy_async_all();  // generic-proxy writes of h -> async-proxy (TMA) reads
           int s2 = stage0;
           for (int kb = 0; kb < pre; ++kb) {
-            ptx::tma_load_2d(smem_b + s2 * b_stage_bytes, tm_b, full_bar(s2), kb * kBlockK, gr.row0,
-                             ptx::kEvictLast);
+            load(smem_b + s2 * b_stage_bytes, tm_b, s2, kb, b_row, ptx::kEvictLast);
             if (++s2 == stages) s2 = 0;
           }
         }
         tr.rec(t, kEvProdDepOk);
         for (int kb = pre; kb < nkb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-          ptx::tma_load_2d(smem_a + stage * kAStageBytes, tm_a, full_bar(stage), kb * kBlockK, a_row,
-                           p.w_policy);
-          ptx::tma_load_2d(smem_b + stage * b_stage_bytes, tm_b, full_bar(stage), kb * kBlockK, gr.row0,
-                           ptx::kEvictLast);
+          arm(stage);
+          load(smem_a + stage * a_stage_bytes, tm_a, stage, kb, a_row, p.w_policy);
+          load(smem_b + stage * b_stage_bytes, tm_b, stage, kb, b_row, ptx::kEvictLast);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -454,13 +490,13 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (one thread) ============================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc(1u /*bf16*/, kBlockM, static_cast<uint32_t>(p.bn));
+    if (lane == 0 && (kCtas == 1 || leader)) {  // pair: the leader issues for both CTAs
+      const uint32_t idesc = ptx::make_idesc(1u /*bf16*/, kBlockM * kCtas, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       Tracer<kTrace> tr(p, 1);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int t = tile0; t < n_tiles; t += tile_step, ++it) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
         const int nkb = tl.phase == 1 ? kb1 : kb2;
         const int as = it & 1;
@@ -473,15 +509,26 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           if (kb == 0) tr.rec(t, kEvMmaFirstData);
-          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a + stage * kAStageBytes);
-          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b + stage * b_stage_bytes);
+          for (int j = 0; j < kps; ++j) {
+            const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a + stage * a_stage_bytes + j * a_blk_bytes);
+            const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b + stage * b_stage_bytes + j * b_blk_bytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance both descriptors by k * 16 elements * 2 B = 32 B -> +2 in 16-byte units
-            ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance both descriptors by k * 16 elements * 2 B = 32 B -> +2 in 16-byte units
+              if constexpr (kCtas == 2)
+                ptx::umma_f16_ss_pair(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
+              else
+                ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
+            }
           }
-          ptx::umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
-          if (kb == nkb - 1) ptx::umma_commit(tfull_bar(as));
+          if constexpr (kCtas == 2) {
+            // the slot is free in BOTH CTAs once these MMAs have read it; both epilogues get the accumulator signal
+            ptx::umma_commit_pair(empty_bar(stage), 0x3);
+            if (kb == nkb - 1) ptx::umma_commit_pair(tfull_bar(as), 0x3);
+          } else {
+            ptx::umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
+            if (kb == nkb - 1) ptx::umma_commit(tfull_bar(as));
+          }
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -497,7 +544,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     if (lane == 0) {
       Tracer<kTrace> tr(p, 3);
       int k = 0;  // phase-1 tiles of this CTA so far
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = tile0; t < n_tiles; t += tile_step) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
         if (tl.phase != 1) continue;
         const int slot = k & 1;
@@ -532,13 +579,13 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     int k1 = 0;  // phase-1 tiles so far (publisher hand-off ring)
     Tracer<kTrace> tr(p, 2);
     const bool tracer_thread = et == 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < n_tiles; t += tile_step, ++it) {
       const Tile tl = decode_tile(t, ng, lag, m1, m2);
       const GroupRec gr = p.groups[tl.g];
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      const int feat0 = tl.mb * kBlockM;  // first feature (weight row) of the tile
+      const int feat0 = (tl.mb * kCtas + static_cast<int>(cta_rank)) * kBlockM;  // first weight row of this CTA's part
       const int nrows = gr.nrows;
       if (tl.phase == 1) {
         const float bias = p.b1 ? p.b1[static_cast<size_t>(gr.expert) * p.H + feat0 + feat_l] : 0.0f;
@@ -594,7 +641,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         // every column this warp owns has left TMEM: hand the accumulator back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if constexpr (kCtas == 2) ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::kPeerBitMask);
+          else ptx::mbar_arrive(tempty_bar(as));
+        }
         if (tracer_thread) tr.rec(t, kEvEpiStored);
         // hand the tile to the publisher: this warp's stores are ordered before lane 0's arrive (release.cta)
         if (lane == 0) {
@@ -700,17 +750,22 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if constexpr (kCtas == 2) ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::kPeerBitMask);
+          else ptx::mbar_arrive(tempty_bar(as));
+        }
         if (tracer_thread) tr.rec(t, kEvEpiStored);
       }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) ptx::cluster_sync();  // neither CTA may leave while the other can still signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (kCtas == 2) ptx::tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
   if (p.ep && threadIdx.x == 0) {
     // Every store of this CTA into the peers' return buffers precedes the barrier above.  The last CTA of the grid to
@@ -736,39 +791,62 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
 void* g_trace_buf = nullptr;
 int g_trace_cap = 0;
 
-int stages_for_bn(int bn) {
-  int s = kStageBudget / (kAStageBytes + bn * kBlockK * 2);
+// b_rows: token rows one CTA stages per k-block (BN, or BN / 2 for CTA pairs); kps: k-blocks per stage
+int stages_for(int b_rows, int kps) {
+  int s = kStageBudget / (kps * (kAStageBytes + b_rows * kBlockK * 2));
   return s > kMaxStages ? kMaxStages : s;
 }
 
-size_t smem_bytes_for(int bn, int stages) {
-  return static_cast<size_t>(stages) * (kAStageBytes + bn * kBlockK * 2) + 8 * (2 * kMaxStages + 8) + 32 +
+size_t smem_bytes_for(int b_rows, int kps, int stages) {
+  return static_cast<size_t>(stages) * kps * (kAStageBytes + b_rows * kBlockK * 2) + 8 * (2 * kMaxStages + 8) + 32 +
          2 * kStagingBytes + 2 * 256 * 4;
 }
 
-template <typename OutT>
+template <typename OutT, int kCtas>
 cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
                          const CUtensorMap& th, const FfnParams& p, cudaStream_t stream) {
-  const size_t smem = smem_bytes_for(a.bn, p.stages);
-  static bool attr_set = false;  // per OutT instantiation
+  const size_t smem = smem_bytes_for(a.bn / kCtas, p.kps, p.stages);
+  static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(ffn_kernel<OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ffn_kernel<OutT, false, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(ffn_kernel<OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(ffn_kernel<OutT, true, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int m1 = a.H / kBlockM, m2 = a.D / kBlockM;
-  long long tiles_ub = static_cast<long long>(a.gmax) * (m1 + m2);
+  const int m1 = a.H / (kBlockM * kCtas), m2 = a.D / (kBlockM * kCtas);
+  long long tiles_ub = static_cast<long long>(a.gmax) * (m1 + m2) * kCtas;  // in CTAs
   int grid = num_sms();
   if (tiles_ub < grid) grid = static_cast<int>(tiles_ub);
-  if (grid < 1) grid = 1;
+  if (kCtas == 2) grid &= ~1;  // whole pairs
+  if (grid < kCtas) grid = kCtas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (kPdlFfn & pdl_mask()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (kCtas == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
   cudaError_t e;
   if (p.trace != nullptr)
-    e = launch_kernel(ffn_kernel<OutT, true>, dim3(grid), dim3(kThreads), smem, stream, kPdlFfn, tw1, tw2, tx, th, p);
+    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, true, kCtas>, tw1, tw2, tx, th, p);
   else
-    e = launch_kernel(ffn_kernel<OutT, false>, dim3(grid), dim3(kThreads), smem, stream, kPdlFfn, tw1, tw2, tx, th, p);
+    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, false, kCtas>, tw1, tw2, tx, th, p);
   count_launch();
   return e;
 }
@@ -785,11 +863,25 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   if (a.D % kBlockM != 0 || a.H % kBlockM != 0) return cudaErrorInvalidValue;
   if (a.bn % 16 != 0 || a.bn < 16 || a.bn > 256) return cudaErrorInvalidValue;
   if (a.fused && a.top_k != 1) return cudaErrorInvalidValue;
+  // CTA pairs for the compute-bound regime: full 256-token tiles and an even number of 128-row blocks per GEMM
+  static const int pair_env = [] {
+    const char* v = std::getenv("B200MOE_PAIR");
+    return (v && *v) ? std::atoi(v) : 1;
+  }();
+  const bool pair = pair_env != 0 && a.bn == 256 && (a.H / kBlockM) % 2 == 0 && (a.D / kBlockM) % 2 == 0;
+  const int ctas = pair ? 2 : 1;
+  // two k-blocks per pipeline stage (one TMA instruction per operand and stage) wherever that still leaves >= 3 stages
+  static const int kps_env = [] {
+    const char* v = std::getenv("B200MOE_KPS");
+    return (v && *v) ? std::atoi(v) : 2;
+  }();
+  int kps = kps_env == 1 ? 1 : 2;
+  if (stages_for(a.bn / ctas, kps) < 3 || (a.D / kBlockK) % kps != 0 || (a.H / kBlockK) % kps != 0) kps = 1;
   CUtensorMap tw1, tw2, tx, th;
-  if (!make_tmap_bf16(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kBlockK) ||
-      !make_tmap_bf16(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM, kBlockK) ||
-      !make_tmap_bf16(&tx, a.xbuf, a.n_rows, a.D, a.bn, kBlockK) ||
-      !make_tmap_bf16(&th, a.hbuf, a.n_rows, a.H, a.bn, kBlockK)) {
+  if (!make_tmap_bf16_kblocks(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kps) ||
+      !make_tmap_bf16_kblocks(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM, kps) ||
+      !make_tmap_bf16_kblocks(&tx, a.xbuf, a.n_rows, a.D, a.bn / ctas, kps) ||
+      !make_tmap_bf16_kblocks(&th, a.hbuf, a.n_rows, a.H, a.bn / ctas, kps)) {
     return cudaErrorInvalidValue;
   }
   FfnParams p;
@@ -831,7 +923,8 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   p.bn = a.bn;
   p.act = a.act;
   p.fused = a.fused;
-  p.stages = stages_for_bn(a.bn);
+  p.kps = kps;
+  p.stages = stages_for(a.bn / ctas, kps);
   {
     static const int dbg = [] {
       const char* v = std::getenv("B200MOE_DBG");
@@ -846,15 +939,18 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   p.trace = static_cast<uint4*>(g_trace_buf);
   p.trace_cap = g_trace_cap;
   // phase-2 tiles trail their group's phase-1 tiles by ~3 waves of the grid
-  const int m1 = a.H / kBlockM;
-  p.lag = (3 * num_sms() + m1 - 1) / m1;
+  const int m1 = a.H / (kBlockM * ctas);
+  p.lag = (3 * (num_sms() / ctas) + m1 - 1) / m1;
   switch (a.out_dtype) {
     case B200MOE_F32:
-      return launch_typed<float>(a, tw1, tw2, tx, th, p, stream);
+      return pair ? launch_typed<float, 2>(a, tw1, tw2, tx, th, p, stream)
+                  : launch_typed<float, 1>(a, tw1, tw2, tx, th, p, stream);
     case B200MOE_F16:
-      return launch_typed<__half>(a, tw1, tw2, tx, th, p, stream);
+      return pair ? launch_typed<__half, 2>(a, tw1, tw2, tx, th, p, stream)
+                  : launch_typed<__half, 1>(a, tw1, tw2, tx, th, p, stream);
     case B200MOE_BF16:
-      return launch_typed<bf16>(a, tw1, tw2, tx, th, p, stream);
+      return pair ? launch_typed<bf16, 2>(a, tw1, tw2, tx, th, p, stream)
+                  : launch_typed<bf16, 1>(a, tw1, tw2, tx, th, p, stream);
     default:
       return cudaErrorInvalidValue;
   }
