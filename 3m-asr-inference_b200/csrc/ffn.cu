@@ -17,9 +17,13 @@
 //    positionwise_feed_forward.py:257-258, fmoe_transformer.py:155-158).
 //  * both phases live in one static round-robin tile list; phase-2 tiles of a group are scheduled ~3 waves after
 //    its phase-1 tiles and wait on a per-group counter in global memory, so h only ever travels through L2.
-//  * warp roles: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, multi-stage mbarrier ring),
-//    warp 1 = single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, double buffered: 2 x 256 columns),
-//    warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias/activation -> global).
+//  * warp roles (384 threads): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier ring of stages
+//    holding two k-blocks each), warp 1 = single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, double
+//    buffered: 2 x 256 columns), warp 2 = TMEM allocator, warp 3 = publisher of the h flags, warps 4-11 = epilogue
+//    (two sets of four warps; tcgen05.ld -> bias/activation -> smem transpose -> row-wise vector stores).
+//  * 256-token tiles run on CTA pairs (cta_group::2, kCtas = 2): see ffn_kernel.
+//  * expert parallelism: the second GEMM's epilogue stores its rows straight into the source GPU's return buffer and
+//    the last CTA raises the "rows are back" flags (trainer_3m_fix/fmoe/functions.py:185-191 without the collective).
 #include <cstdlib>
 #include <mutex>
 
@@ -171,72 +175,6 @@ __device__ __forceinline__ Tile decode_tile(int t, int ng, int lag, int m1, int 
   r.mb = u % m2;
   return r;
 }
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == B200MOE_ACT_SILU) {
-    // x * sigmoid(x)  (trainer_3m_fix/utils/common.py:24-28; TRTAPI++/plugin/common/common.cuh sigmoid)
-    return __fdividef(v, 1.0f + __expf(-v));
-  } else if (act == B200MOE_ACT_RELU) {
-    return fmaxf(v, 0.0f);
-  } else {
-    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-  }
-}
-
-// sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5, so SiLU costs ONE special-function op (tanh.approx) instead of ex2 + rcp: the
-// epilogue of the first GEMM is otherwise bound by the 16 MUFU results per clock of an SM.  tanh.approx is good to
-// ~2^-11 relative, the result is rounded to bf16 (2^-9) right after.
-__device__ __forceinline__ float silu_fast(float v) {
-  const float hv = 0.5f * v;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hv));
-  return fmaf(hv, t, hv);
-}
-
-__device__ __forceinline__ float apply_act_fast(float v, int act) {
-  if (act == B200MOE_ACT_SILU) return silu_fast(v);
-  if (act == B200MOE_ACT_RELU) return fmaxf(v, 0.0f);
-  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-}
-
-__device__ __forceinline__ uint16_t bf16_bits(float v) {
-  const __nv_bfloat16 b = __float2bfloat16_rn(v);
-  return *reinterpret_cast<const uint16_t*>(&b);
-}
-
-// One boundary element per lane, predicated (direct epilogue: a warp instruction covers 32 consecutive features).
-template <typename T>
-struct ScalarIo;
-template <>
-struct ScalarIo<float> {
-  using raw_t = uint32_t;
-  static __device__ __forceinline__ raw_t load(const float* p, bool pred) { return ptx::ld_global_pred_b32(p, pred); }
-  static __device__ __forceinline__ float to_f(raw_t r) { return __uint_as_float(r); }
-  static __device__ __forceinline__ void store(float* p, float v, bool pred) {
-    ptx::st_global_pred_b32(p, __float_as_uint(v), pred);
-  }
-};
-template <>
-struct ScalarIo<bf16> {
-  using raw_t = uint16_t;
-  static __device__ __forceinline__ raw_t load(const bf16* p, bool pred) { return ptx::ld_global_pred_b16(p, pred); }
-  static __device__ __forceinline__ float to_f(raw_t r) { return __uint_as_float(static_cast<uint32_t>(r) << 16); }
-  static __device__ __forceinline__ void store(bf16* p, float v, bool pred) {
-    ptx::st_global_pred_b16(p, bf16_bits(v), pred);
-  }
-};
-template <>
-struct ScalarIo<__half> {
-  using raw_t = uint16_t;
-  static __device__ __forceinline__ raw_t load(const __half* p, bool pred) { return ptx::ld_global_pred_b16(p, pred); }
-  static __device__ __forceinline__ float to_f(raw_t r) {
-    return __half2float(*reinterpret_cast<const __half*>(&r));
-  }
-  static __device__ __forceinline__ void store(__half* p, float v, bool pred) {
-    const __half h = __float2half_rn(v);
-    ptx::st_global_pred_b16(p, *reinterpret_cast<const uint16_t*>(&h), pred);
-  }
-};
 
 // Four consecutive boundary elements as one vector access (8 B for 16-bit types, 16 B for fp32), predicated so that
 // the code stays branch-free (a C++ `if` around a store makes the compiler sink the value's whole computation into a
@@ -603,7 +541,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           ptx::tmem_ld_32x32b_x32(taddr + c0, r);
           ptx::tmem_ld_wait();
           if (act == B200MOE_ACT_SILU) {
-            // silu(a + b) with h = (a + b) / 2:  h * tanh(h) + h
+            // silu(v) = v * sigmoid(v) with sigmoid(v) = (tanh(v / 2) + 1) / 2, so with h = v / 2: h * tanh(h) + h.
+            // ONE special-function op (tanh.approx, ~2^-11 relative) instead of ex2 + rcp: the 16 MUFU results per
+            // clock of an SM are what this loop would otherwise wait for.  The result is rounded to bf16 (2^-9).
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float hv = fmaf(__uint_as_float(r[j]), 0.5f, hbias);
