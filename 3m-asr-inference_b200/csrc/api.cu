@@ -103,8 +103,11 @@ int knob(std::atomic<int>& v, const char* env, int dflt) {
 }
 }  // namespace
 
-int pdl_mask() { return knob(g_pdl, "B200MOE_PDL", 0); }
-int pdl_trigger() { return knob(g_pdl_trig, "B200MOE_PDL_TRIG", 7); }
+// Defaults: the gate / route kernel and the expert-FFN kernel are launched with the PDL attribute and the FFN kernel
+// releases its dependents at its start, so that the next layer's route kernel does the embed half of the router GEMM
+// (constants only) while this layer's FFN kernel drains: measured 32.7 -> 29.8 us per layer on cfg3 under CUDA graphs.
+int pdl_mask() { return knob(g_pdl, "B200MOE_PDL", kPdlGate | kPdlFfn); }
+int pdl_trigger() { return knob(g_pdl_trig, "B200MOE_PDL_TRIG", kPdlFfn); }
 int route_mode() { return knob(g_route, "B200MOE_ROUTE", 1); }
 
 int prefetch_mode() { return knob(g_prefetch, "B200MOE_PREFETCH", 0); }

@@ -215,9 +215,9 @@ cudaError_t launch_pack_bf16(const void* src, int src_dtype, bf16* dst, size_t n
 void count_launch(int n = 1);
 
 // Tunables read once from the environment (api.cu):
-//   B200MOE_PDL=m       bit mask of the kernels launched with programmatic dependent launch (1 gate, 2 dispatch,
-//                       4 expert FFN); 0 = ordinary stream ordering.  B200MOE_PDL_TRIG=m: which of them release their
-//                       dependents at their start (otherwise at exit)
+//   B200MOE_PDL=m       bit mask of the kernels launched with programmatic dependent launch (1 gate / route, 2 dispatch,
+//                       4 expert FFN; default 5); 0 = ordinary stream ordering.  B200MOE_PDL_TRIG=m: which of them
+//                       release their dependents at their start instead of at exit (default 4)
 //   B200MOE_PREFETCH=0  no L2 prefetch of the layer's expert weights from the gate kernel; 1 (default) = issued before
 //                       the gate waits for the previous kernel; 2 = issued after that wait
 int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN: kernel launched with the PDL attribute

@@ -353,7 +353,9 @@ cudaError_t launch_gate_tc(const void* x, const void* embed, const void* wr_pack
     p.pf_bytes[1] = pf1 ? pf1_bytes : 0;
     grid = num_sms();  // CTAs without a token tile only prefetch
   }
-  cudaError_t e = launch_kernel(gate_tc_kernel, dim3(grid), dim3(kThreadsG), smem, stream, kPdlGate, tx, te, tw, p);
+  // PDL only pays when there is work to do before the dependency (the weight prefetch); otherwise ordinary ordering
+  cudaError_t e = launch_kernel(gate_tc_kernel, dim3(grid), dim3(kThreadsG), smem, stream,
+                                p.pf_mode == 1 ? kPdlGate : 0, tx, te, tw, p);
   count_launch();
   return e;
 }

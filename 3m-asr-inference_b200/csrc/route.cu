@@ -188,10 +188,17 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
+      bool waited = false;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int part = 0; part < n_parts; ++part) {
           const bool is_e = n_parts == 2 && part == 0;
           const int nkb = is_e ? kb_e : kb_x;
+          // Programmatic dependent launch: the embed half of the router GEMM (embed and the router are constants) runs
+          // while the previous layer's FFN kernel is still draining; x, its output, is only touched after this wait.
+          if (!is_e && !waited) {
+            ptx::pdl_wait();
+            waited = true;
+          }
           ptx::mbar_wait(empty_bar(slot), phase ^ 1u);
           ptx::mbar_arrive_expect_tx(full_bar(slot), static_cast<uint32_t>(nkb) * (kRABlk + kRBBlk));
           const uint32_t sa = smem_base + slot * kRSlot;
@@ -249,6 +256,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const int q = warp & 3;
     float* dstm = q == 0 ? s_hi : s_lo;
     int it = 0;
+    ptx::pdl_wait();  // idx / score / histogram words may still be read by the previous layer's kernels
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -314,6 +322,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   // needs every row for its prefix sums anyway, so it simply re-reads a word until the tag is there.  All CTAs of the
   // grid are co-resident (grid <= SM count, one CTA per SM), so waiting for the other tiles cannot deadlock.
   __syncthreads();
+  ptx::pdl_wait();  // (every thread: phase 2 reads and writes the workspace and the row buffers)
   if (threadIdx.x == 0) rtrace(p, 5);
   {
     const int e = threadIdx.x & 31;
@@ -634,9 +643,10 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   cudaError_t e;
   if (ep)
-    e = launch_kernel(route_kernel<true>, dim3(grid), dim3(kRThreads), smem, stream, 0, tx, te, twx, twe, p, epv);
+    e = launch_kernel(route_kernel<true>, dim3(grid), dim3(kRThreads), smem, stream, kPdlGate, tx, te, twx, twe, p, epv);
   else
-    e = launch_kernel(route_kernel<false>, dim3(grid), dim3(kRThreads), smem, stream, 0, tx, te, twx, twe, p, epv);
+    e = launch_kernel(route_kernel<false>, dim3(grid), dim3(kRThreads), smem, stream, kPdlGate, tx, te, twx, twe, p,
+                      epv);
   count_launch();
   return e;
 }
