@@ -48,6 +48,13 @@ __device__ __forceinline__ void bf16x8_to_f(const uint4& v, float (&o)[8]) {
 __global__ void __launch_bounds__(256)
 ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float* __restrict__ score,
                   const bf16* __restrict__ residual, float ff_scale, int S, int D, int top_k, bf16* __restrict__ out) {
+  // Programmatic dependent launch, both ways.  (1) The next layer's route kernel may start now: it only touches
+  // constants (embed, router) until its own griddepcontrol.wait, which returns when this grid has completed.  (2) This
+  // kernel itself never calls griddepcontrol.wait although it is launched early: everything it consumes from the FFN
+  // kernels -- of this rank and of the peers alike -- is covered by the return flags below (this rank's own flag is
+  // raised by the last CTA of its FFN kernel after every CTA's system-scope fence), mapping / score / seq were written
+  // by this layer's route kernel, which completed before the FFN kernel could pass its own wait.
+  ptx::pdl_launch_dependents();
   int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
   const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ret_flag);
   if (threadIdx.x < ep.world) {
@@ -111,10 +118,10 @@ cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float
   int blocks = (S + 7) / 8;
   if (blocks < 1) blocks = 1;  // the wait on the return flags must happen even for a rank without tokens
   if (blocks > 4 * 148) blocks = 4 * 148;
-  ep_combine_kernel<<<blocks, 256, 0, stream>>>(ep, mapping, score, static_cast<const bf16*>(residual), ff_scale, S, D,
-                                                top_k, static_cast<bf16*>(out));
+  cudaError_t e = launch_kernel(ep_combine_kernel, dim3(blocks), dim3(256), 0, stream, kPdlFfn, ep, mapping, score,
+                                static_cast<const bf16*>(residual), ff_scale, S, D, top_k, static_cast<bf16*>(out));
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace b200moe
