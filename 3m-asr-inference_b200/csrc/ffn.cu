@@ -221,6 +221,32 @@ __device__ __forceinline__ void st_pred_v2(void* p, uint32_t a, uint32_t b, bool
                : "l"(p), "r"(a), "r"(b), "r"(static_cast<int>(pred))
                : "memory");
 }
+__device__ __forceinline__ uint4 ld_pred_v4(const void* p, bool pred) {
+  uint4 r;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\t"
+      "mov.b32 %3, 0;\n\t@p ld.global.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+      : "l"(p), "r"(static_cast<int>(pred)));
+  return r;
+}
+// two 16-bit elements: a + b with one rounding (the exact sum of two bf16 / fp16 values, rounded to nearest)
+template <typename T>
+__device__ __forceinline__ uint32_t add_packed(uint32_t a, uint32_t b);
+template <>
+__device__ __forceinline__ uint32_t add_packed<bf16>(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t add_packed<__half>(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t add_packed<float>(uint32_t a, uint32_t) { return a; }  // never used (fp32 path)
 __device__ __forceinline__ void st_pred_v4(void* p, const uint4& v, bool pred) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
                :
@@ -614,87 +640,178 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           s_sc[i] = sc;
         }
         ptx::named_bar_sync(3, kEpiThreads);  // routing table visible to all epilogue warps
-        using Io = Vec4Io<OutT>;
-        const size_t fo = static_cast<size_t>(feat0 + lane * 4);
-        // Residual rows of this set's first two chunks are requested now, while the MMAs of the tile still run (a global
-        // load under full HBM load takes 1-2 us); the rows of chunk k+2 are requested as soon as chunk k is done.
-        typename Io::raw_t rres[2][8];
+        if constexpr (sizeof(OutT) == 2) {
+          // ---- 16-bit outputs.  The column phase stages  sc * (y + b2)  already rounded to the output type (8 KiB per
+          // chunk, two buffers per set, ONE barrier per chunk); the row phase adds the residual with packed adds
+          // (add.rn.{bf16x2,f16x2}: one rounding of the exact sum) and writes 256-byte row segments, a half-warp per row.
+          // Rounding the MoE term before the residual add perturbs `out` by 2^-9 of a term that is itself ~1e-2 of the
+          // residual; without a residual (sc * y alone) it is the same single rounding as before.
+          const int half = lane >> 4;
+          const int l16 = lane & 15;
+          const size_t fo16 = static_cast<size_t>(feat0 + l16 * 8);
+          // Residual rows of this set's first two chunks are requested now, while the MMAs of the tile still run (a
+          // global load under full HBM load takes 1-2 us); the rows of chunk k+2 as soon as chunk k is done.
+          uint4 rres[2][4];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int col = (2 * cc + set) * 32 + q * 8 + i;
-            const bool v = col < nrows;
-            const int tok = v ? s_tok[col] : 0;
-            rres[cc][i] = Io::load(res + static_cast<size_t>(tok) * p.D + fo, v && with_res);
-          }
-        }
-        ptx::mbar_wait(tfull_bar(as), aphase);
-        ptx::tc_fence_after();
-        if (tracer_thread) tr.rec(t, kEvEpiAccReady);
-#pragma unroll 1
-        for (int cb = set * 32; cb < nrows; cb += 128) {
-#pragma unroll
-          for (int cs = 0; cs < 2; ++cs) {  // spelled out twice: the residual registers need static indices
-            const int c0 = cb + cs * 64;
-            if (c0 < nrows) {               // uniform over the set
-              {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c0, r);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stg_f[j * kBlockM + feat_l] = __uint_as_float(r[j]) + bias;
-              }
-              if (tracer_thread) tr.rec(t, kEvEpiChunkLd);
-              ptx::named_bar_sync(set_bar, kSetThreads);  // staging complete
-              if (tracer_thread) tr.rec(t, kEvEpiChunkStaged);
-              // row phase: warp q owns columns 8q .. 8q+7, lane l the 4 features 4l .. 4l+3 of each
-              float4 a[8];
-              float sc[8];
-              size_t ofs[8];
-              bool vv[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int j = q * 8 + i;
-                const int col = c0 + j;
-                vv[i] = col < nrows;
-                const int tok = vv[i] ? s_tok[col] : 0;
-                sc[i] = vv[i] ? s_sc[col] : 0.0f;
-                a[i] = *reinterpret_cast<const float4*>(stg_f + j * kBlockM + lane * 4);
-                ofs[i] = static_cast<size_t>(tok) * p.D + fo;
-              }
-              ptx::named_bar_sync(set_bar, kSetThreads);  // staging buffer free again (values are in registers)
-              float o[8][4];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float rv[4];
-                Io::to_f(rres[cs][i], rv);
-                o[i][0] = fmaf(sc[i], a[i].x, rv[0]);
-                o[i][1] = fmaf(sc[i], a[i].y, rv[1]);
-                o[i][2] = fmaf(sc[i], a[i].z, rv[2]);
-                o[i][3] = fmaf(sc[i], a[i].w, rv[3]);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) Io::store(out + ofs[i], o[i], vv[i] && st2);
-              // residual rows of the chunk two steps ahead
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int col = c0 + 128 + q * 8 + i;
-                const bool v = col < nrows;
-                const int tok = v ? s_tok[col] : 0;
-                rres[cs][i] = Io::load(res + static_cast<size_t>(tok) * p.D + fo, v && with_res);
-              }
-              if (tracer_thread) tr.rec(t, kEvEpiChunkDone);
+            for (int i = 0; i < 4; ++i) {
+              const int col = (2 * cc + set) * 32 + q * 8 + 2 * i + half;
+              const bool v = col < nrows;
+              const int tok = v ? s_tok[col] : 0;
+              rres[cc][i] = ld_pred_v4(res + static_cast<size_t>(tok) * p.D + fo16, v && with_res);
             }
           }
+          ptx::mbar_wait(tfull_bar(as), aphase);
+          ptx::tc_fence_after();
+          if (tracer_thread) tr.rec(t, kEvEpiAccReady);
+          int ci = 0;
+#pragma unroll 1
+          for (int cb = set * 32; cb < nrows; cb += 128) {
+#pragma unroll
+            for (int cs = 0; cs < 2; ++cs) {  // spelled out twice: the residual registers need static indices
+              const int c0 = cb + cs * 64;
+              if (c0 < nrows) {               // uniform over the set
+                OutT* sb = reinterpret_cast<OutT*>(stg_raw) + (ci & 1) * (32 * kBlockM);
+                ++ci;
+                {
+                  uint32_t r[32];
+                  ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+                  float scv[32];
+#pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(s_sc + c0 + 4 * j4);  // broadcast reads
+                    scv[4 * j4] = v4.x;
+                    scv[4 * j4 + 1] = v4.y;
+                    scv[4 * j4 + 2] = v4.z;
+                    scv[4 * j4 + 3] = v4.w;
+                  }
+                  ptx::tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    sb[j * kBlockM + feat_l] = from_float<OutT>((__uint_as_float(r[j]) + bias) * scv[j]);
+                }
+                if (tracer_thread) tr.rec(t, kEvEpiChunkLd);
+                ptx::named_bar_sync(set_bar, kSetThreads);  // this chunk is staged; the other buffer's readers are done
+                if (tracer_thread) tr.rec(t, kEvEpiChunkStaged);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int j = q * 8 + 2 * i + half;
+                  const int col = c0 + j;
+                  const bool v = col < nrows;
+                  const int tok = v ? s_tok[col] : 0;
+                  const uint4 a = *reinterpret_cast<const uint4*>(sb + j * kBlockM + l16 * 8);
+                  uint4 o;
+                  o.x = add_packed<OutT>(rres[cs][i].x, a.x);
+                  o.y = add_packed<OutT>(rres[cs][i].y, a.y);
+                  o.z = add_packed<OutT>(rres[cs][i].z, a.z);
+                  o.w = add_packed<OutT>(rres[cs][i].w, a.w);
+                  st_pred_v4(out + static_cast<size_t>(tok) * p.D + fo16, o, v && st2);
+                }
+                // residual rows of the chunk two steps ahead
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int col = c0 + 128 + q * 8 + 2 * i + half;
+                  const bool v = col < nrows;
+                  const int tok = v ? s_tok[col] : 0;
+                  rres[cs][i] = ld_pred_v4(res + static_cast<size_t>(tok) * p.D + fo16, v && with_res);
+                }
+                if (tracer_thread) tr.rec(t, kEvEpiChunkDone);
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtas == 2) ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::kPeerBitMask);
+            else ptx::mbar_arrive(tempty_bar(as));
+          }
+          if (tracer_thread) tr.rec(t, kEvEpiStored);
+          ptx::named_bar_sync(set_bar, kSetThreads);  // staging buffers free before the next tile reuses them
+        } else {
+          // ---- fp32 outputs: fp32 staging (16 KiB per chunk, one buffer per set, two barriers per chunk)
+          using Io = Vec4Io<OutT>;
+          const size_t fo = static_cast<size_t>(feat0 + lane * 4);
+          // Residual rows of this set's first two chunks are requested now, while the MMAs of the tile still run (a global
+          // load under full HBM load takes 1-2 us); the rows of chunk k+2 are requested as soon as chunk k is done.
+          typename Io::raw_t rres[2][8];
+  #pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int col = (2 * cc + set) * 32 + q * 8 + i;
+              const bool v = col < nrows;
+              const int tok = v ? s_tok[col] : 0;
+              rres[cc][i] = Io::load(res + static_cast<size_t>(tok) * p.D + fo, v && with_res);
+            }
+          }
+          ptx::mbar_wait(tfull_bar(as), aphase);
+          ptx::tc_fence_after();
+          if (tracer_thread) tr.rec(t, kEvEpiAccReady);
+  #pragma unroll 1
+          for (int cb = set * 32; cb < nrows; cb += 128) {
+  #pragma unroll
+            for (int cs = 0; cs < 2; ++cs) {  // spelled out twice: the residual registers need static indices
+              const int c0 = cb + cs * 64;
+              if (c0 < nrows) {               // uniform over the set
+                {
+                  uint32_t r[32];
+                  ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+                  ptx::tmem_ld_wait();
+  #pragma unroll
+                  for (int j = 0; j < 32; ++j) stg_f[j * kBlockM + feat_l] = __uint_as_float(r[j]) + bias;
+                }
+                if (tracer_thread) tr.rec(t, kEvEpiChunkLd);
+                ptx::named_bar_sync(set_bar, kSetThreads);  // staging complete
+                if (tracer_thread) tr.rec(t, kEvEpiChunkStaged);
+                // row phase: warp q owns columns 8q .. 8q+7, lane l the 4 features 4l .. 4l+3 of each
+                float4 a[8];
+                float sc[8];
+                size_t ofs[8];
+                bool vv[8];
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int j = q * 8 + i;
+                  const int col = c0 + j;
+                  vv[i] = col < nrows;
+                  const int tok = vv[i] ? s_tok[col] : 0;
+                  sc[i] = vv[i] ? s_sc[col] : 0.0f;
+                  a[i] = *reinterpret_cast<const float4*>(stg_f + j * kBlockM + lane * 4);
+                  ofs[i] = static_cast<size_t>(tok) * p.D + fo;
+                }
+                ptx::named_bar_sync(set_bar, kSetThreads);  // staging buffer free again (values are in registers)
+                float o[8][4];
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float rv[4];
+                  Io::to_f(rres[cs][i], rv);
+                  o[i][0] = fmaf(sc[i], a[i].x, rv[0]);
+                  o[i][1] = fmaf(sc[i], a[i].y, rv[1]);
+                  o[i][2] = fmaf(sc[i], a[i].z, rv[2]);
+                  o[i][3] = fmaf(sc[i], a[i].w, rv[3]);
+                }
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) Io::store(out + ofs[i], o[i], vv[i] && st2);
+                // residual rows of the chunk two steps ahead
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int col = c0 + 128 + q * 8 + i;
+                  const bool v = col < nrows;
+                  const int tok = v ? s_tok[col] : 0;
+                  rres[cs][i] = Io::load(res + static_cast<size_t>(tok) * p.D + fo, v && with_res);
+                }
+                if (tracer_thread) tr.rec(t, kEvEpiChunkDone);
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtas == 2) ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::kPeerBitMask);
+            else ptx::mbar_arrive(tempty_bar(as));
+          }
+          if (tracer_thread) tr.rec(t, kEvEpiStored);
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (kCtas == 2) ptx::mbar_arrive_cluster(tempty_bar(as) & ptx::kPeerBitMask);
-          else ptx::mbar_arrive(tempty_bar(as));
-        }
-        if (tracer_thread) tr.rec(t, kEvEpiStored);
       }
     }
   }
