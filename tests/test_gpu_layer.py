@@ -108,6 +108,23 @@ def test_layer_3m_repo_dims(ops, oracle, synth, S, dtype, random_bias, tc_gate):
         assert rel_l2(moe, ref["moe"]) <= 2 * BF16_REL_L2
 
 
+@pytest.mark.parametrize("S,E,D,H,Demb", [
+    (333, 16, 256, 512, 128),    # smaller model, short embed part (two K parts of different length in the route kernel)
+    (77, 8, 128, 256, 0),        # no embed input: single K part
+    (1500, 32, 384, 640, 64),    # odd number of 128-row blocks in the first GEMM (no CTA pairs even at large tiles)
+    (5000, 4, 512, 1024, 512),   # few experts, > 1 000 tokens each: 256-token tiles -> CTA pairs; two route tiles per SM
+])
+def test_layer_other_dims(ops, oracle, synth, S, E, D, H, Demb):
+    """The reference leaves idim / hidden_units / num_expert to the plugin fields (fmoe_expert_plugin.cpp:325-366)."""
+    w = synth.make_weights(7000 + S, E, D, H, Demb, random_bias=True)
+    x, embed = synth.make_activations(7100 + S, S, D, Demb, w)
+    ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
+    res = run_layer(ops, w, x, embed, ff_scale=0.5)
+    check_against_oracle(oracle, res, ref)
+    res2 = run_layer(ops, w, x, embed, residual=False, ff_scale=1.0)
+    assert rel_l2(res2.out.float().cpu(), ref["moe"]) <= BF16_REL_L2
+
+
 def test_layer_padding_and_keep_output(ops, oracle, synth):
     E, D, H, Demb, B, T = 32, 512, 1024, 512, 6, 60
     w = synth.make_weights(31, E, D, H, Demb, random_bias=True)

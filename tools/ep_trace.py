@@ -50,13 +50,18 @@ def main():
     dist.barrier()
     cap, n_cta = 256, 148
     buf = torch.zeros(n_cta * cap, 4, dtype=torch.int32, device=dev)
+    rbuf = torch.zeros(148 * 16, 4, dtype=torch.int32, device=dev)
     if rank == 0:
         lib.b200moe_debug_ffn_trace(buf.data_ptr(), cap)
+        lib.b200moe_debug_route_trace(rbuf.data_ptr())
     Wr, ex, wp = layers[0]
     ctx.forward(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
     torch.cuda.synchronize()
     if rank == 0:
         lib.b200moe_debug_ffn_trace(None, 0)
+        lib.b200moe_debug_route_trace(None)
+        from route_trace import analyze as route_analyze
+        route_analyze(rbuf.cpu().numpy().astype(np.int64).reshape(148, 16, 4), S)
         rec = buf.cpu().numpy().astype(np.int64).reshape(n_cta, 4, cap // 4, 4)
         analyze(rec, cap, n_cta, S, 2)
     print(f"rank {rank} status {ctx.status()}", flush=True)

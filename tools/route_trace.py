@@ -41,7 +41,10 @@ def main():
     ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
     torch.cuda.synchronize()
     lib.b200moe_debug_route_trace(None)
-    rec = buf.cpu().numpy().astype(np.int64).reshape(148, 16, 4)
+    analyze(buf.cpu().numpy().astype(np.int64).reshape(148, 16, 4), S)
+
+
+def analyze(rec, S):
     val = (rec[..., 1] & 0xFFFFFFFF) | ((rec[..., 2] & 0xFFFFFFFF) << 32)
     ok = rec[..., 3] == 1
     ctas = [c for c in range(148) if ok[c, 14] and ok[c, 15] and ok[c, 0] and ok[c, 10]]
