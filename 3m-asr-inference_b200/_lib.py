@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb200moe.so")
 F32, F16, BF16 = 0, 1, 2
 ACT_SILU, ACT_RELU, ACT_GELU = 0, 1, 2
 GATE_3M, GATE_NAIVE = 0, 1
+COMPUTE_BF16, COMPUTE_TF32 = 0, 1
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -28,6 +29,7 @@ class LayerArgs(C.Structure):
         ("gate_mode", _i), ("act_type", _i), ("dtype", _i),
         ("keep_expert_output", _i), ("ff_scale", _f),
         ("idx_out", _vp), ("score_out", _vp), ("counts_out", _vp), ("mapping_out", _vp),
+        ("compute", _i),
     ]
 
 

@@ -352,6 +352,11 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   float* score = a->score_out ? a->score_out : w.score;
 
   cudaError_t e;
+  const bool tf32 = a->compute == B200MOE_COMPUTE_TF32;
+  if (a->compute != B200MOE_COMPUTE_BF16 && !tf32) return fail(B200MOE_ERR_ARG, "forward: bad compute mode %d", a->compute);
+  if (tf32 && a->dtype != B200MOE_F32)
+    return fail(B200MOE_ERR_ARG, "forward: TF32 compute takes fp32 activations and fp32 weights");
+  if (tf32 && !a->Wr) return fail(B200MOE_ERR_ARG, "forward: TF32 compute needs the fp32 router (Wr)");
   const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
   const int bn = choose_bn(Sk, a->E);
   const int gmax = max_groups(Sk, a->E, bn);
@@ -384,7 +389,7 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
     StageScope t(1, stream);
     e = launch_dispatch(a->x, idx, a->keep_expert_output ? nullptr : score, S, a->D, a->E, a->top_k, a->dtype, bn, w,
                         a->counts_out, nullptr, a->mapping_out, w.xbuf, fused ? a->out : nullptr, a->residual,
-                        tc_gate ? w.hist32 : nullptr, stream);
+                        tc_gate ? w.hist32 : nullptr, stream, nullptr, false, tf32);
   }
   if (e != cudaSuccess) return cuda_fail(e, "forward/dispatch");
   }
@@ -409,6 +414,7 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   f.out_dtype = a->dtype;
   f.top_k = a->top_k;
   f.ff_scale = a->ff_scale;
+  f.tf32 = tf32 ? 1 : 0;
   if (route) {
     f.clear_ptr = w.hist32;
     f.clear_ints = ((S + 31) / 32) * a->E;
@@ -551,6 +557,7 @@ int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, vo
   if (a->D % 128 != 0 || a->H % 128 != 0)
     return fail(B200MOE_ERR_ARG, "ep_forward: D=%d and H=%d must be multiples of 128", a->D, a->H);
   if (a->dtype != B200MOE_BF16) return fail(B200MOE_ERR_ARG, "ep_forward: activations must be bf16");
+  if (a->compute != B200MOE_COMPUTE_BF16) return fail(B200MOE_ERR_ARG, "ep_forward: bf16 compute only");
   if (a->top_k < 1 || a->top_k > 8 || a->top_k > a->E) return fail(B200MOE_ERR_ARG, "ep_forward: bad top_k %d", a->top_k);
   if (a->gate_mode == B200MOE_GATE_3M && a->top_k != 1) return fail(B200MOE_ERR_ARG, "ep_forward: the 3M router is top-1");
   if (a->act_type < 0 || a->act_type > 2) return fail(B200MOE_ERR_ARG, "ep_forward: bad act_type %d", a->act_type);

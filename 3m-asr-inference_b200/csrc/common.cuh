@@ -117,9 +117,10 @@ inline RouteWs carve_workspace(void* base, int S, int E, int D, int H, int top_k
   w.h_ready = reinterpret_cast<int*>(take(sizeof(int) * gmax));
   w.idx = reinterpret_cast<int*>(take(sizeof(int) * Sk));
   w.score = reinterpret_cast<float*>(take(sizeof(float) * Sk));
-  w.xbuf = reinterpret_cast<bf16*>(take(sizeof(bf16) * Sk * D));
+  // xbuf / hbuf are sized for fp32 rows so that the same workspace serves the TF32 flavour
+  w.xbuf = reinterpret_cast<bf16*>(take(sizeof(float) * Sk * D));
   w.ybuf = take(sizeof(float) * Sk * D);
-  w.hbuf = take(sizeof(bf16) * Sk * H);  // last: the only field whose size depends on H
+  w.hbuf = take(sizeof(float) * Sk * H);  // last: the only field whose size depends on H
   w.bytes = off;
   return w;
 }
@@ -151,7 +152,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
                             const int* hist32, cudaStream_t stream, const EpPeers* ep = nullptr,
-                            bool ep_fold_wait = false);
+                            bool ep_fold_wait = false, bool xbuf_f32 = false);
 constexpr int kMaxHistRows = 512;  // above this many 32-token rows the scatter CTAs would re-read too much
 // Builds only the group table (+ zeroes the flags) from an existing offsets array.
 cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
@@ -193,6 +194,7 @@ struct FfnLaunch {
   const EpPeers* ep;  // expert parallelism (un-fused only): rows of group g go to rank g.src's return buffer
   int* clear_ptr;     // optional: `clear_ints` ints zeroed at kernel start (the route kernel's tagged histogram)
   int clear_ints;
+  int tf32;           // 1: xbuf, W1, W2 and hbuf hold fp32 (the pointers above are reinterpreted), TF32 tensor-core math
 };
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
 // Debug timeline: every following ffn launch records per-CTA events into dev_buf (16 B records); null disables.

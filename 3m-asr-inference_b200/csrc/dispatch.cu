@@ -131,7 +131,8 @@ __device__ void build_groups_block(const int* offsets_sm /*[E+1] in smem or glob
 // at recv_x[my rank][mapping - offsets[first expert of that rank]].  The last CTA to finish then writes the per-expert
 // counts into every peer and raises its arrival flag with a system-scope release (the reference does this with two
 // NCCL all-to-alls and a host round trip: trainer_3m_fix/fmoe/functions.py:37-50,74-80).
-template <typename InT, bool kEp>
+// kXf32: the expert-order buffer keeps fp32 rows (TF32 compute; fp32 activations only) instead of bf16.
+template <typename InT, bool kEp, bool kXf32>
 __global__ void __launch_bounds__(kDispatchThreads)
 dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, const float* __restrict__ score,
                         int Sk, int D, int E, int top_k, int chunk, int nchunks,
@@ -268,6 +269,19 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
                     (static_cast<size_t>(ep.rank) * ep.cap + slot) * D;
         }
       }
+      if constexpr (kXf32) {
+        // fp32 rows: xbuf is really float [Sk, D]
+        for (int v = lane; v < D / 4; v += 32) {
+          float4 regs[kRowsPerBatch];
+#pragma unroll
+          for (int r = 0; r < kRowsPerBatch; ++r)
+            if (d[r] >= 0) regs[r] = __ldg(reinterpret_cast<const float4*>(src[r]) + v);
+#pragma unroll
+          for (int r = 0; r < kRowsPerBatch; ++r)
+            if (d[r] >= 0)
+              reinterpret_cast<float4*>(reinterpret_cast<float*>(xbuf) + static_cast<size_t>(d[r]) * D)[v] = regs[r];
+        }
+      } else {
       for (int v = lane; v < D / 8; v += 32) {
         uint4 regs[kRowsPerBatch];
 #pragma unroll
@@ -276,6 +290,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
 #pragma unroll
         for (int r = 0; r < kRowsPerBatch; ++r)
           if (d[r] >= 0) reinterpret_cast<uint4*>(drow[r])[v] = regs[r];
+      }
       }
       if (drop_out != nullptr) {
         // dropped tokens (padding / invalid expert): output row = residual row (or zero)
@@ -377,7 +392,9 @@ int choose_bn(int Sk, int E) {
 cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, int S, int D, int E, int top_k,
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
-                            const int* hist32, cudaStream_t stream, const EpPeers* ep, bool ep_fold_wait) {
+                            const int* hist32, cudaStream_t stream, const EpPeers* ep, bool ep_fold_wait,
+                            bool xbuf_f32) {
+  if (xbuf_f32 && (dtype != B200MOE_F32 || ep != nullptr || D % 4 != 0)) return cudaErrorInvalidValue;
   const int Sk = S * top_k;
   if (top_k != 1 || ep != nullptr) drop_out = nullptr;
   if (ep != nullptr && (ep->world * ep->E_local != E || Sk > ep->cap || ep->D != D)) return cudaErrorInvalidValue;
@@ -415,7 +432,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
   EpPeers epv{};
   if (ep) epv = *ep;
 #define B200MOE_SCATTER_K(T, EP)                                                                                  \
-  lerr = launch_kernel(dispatch_scatter_kernel<T, EP>, dim3(ck.nchunks), dim3(kDispatchThreads), dyn, stream,     \
+  lerr = launch_kernel(dispatch_scatter_kernel<T, EP, false>, dim3(ck.nchunks), dim3(kDispatchThreads), dyn, stream, \
       kPdlDispatch,                                                                                               \
       static_cast<const T*>(x), idx, score, Sk, D, E, top_k, ck.chunk, ck.nchunks, hist, hist_rows,               \
       rows_per_chunk, bn, gmax,                                                                                   \
@@ -429,6 +446,15 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
     B200MOE_SCATTER_K(T, false)
   switch (dtype) {
     case B200MOE_F32:
+      if (xbuf_f32) {
+        lerr = launch_kernel(dispatch_scatter_kernel<float, false, true>, dim3(ck.nchunks), dim3(kDispatchThreads), dyn,
+                             stream, kPdlDispatch, static_cast<const float*>(x), idx, score, Sk, D, E, top_k, ck.chunk,
+                             ck.nchunks, hist, hist_rows, rows_per_chunk, bn, gmax, ws.counts, ws.offsets, ws.mapping,
+                             ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready, counts_out, offsets_out,
+                             mapping_out, static_cast<float*>(drop_out), static_cast<const float*>(drop_residual),
+                             (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, 0);
+        break;
+      }
       B200MOE_SCATTER(float);
       break;
     case B200MOE_F16:

@@ -54,7 +54,7 @@ struct FfnParams {
   int* h_ready;
   const float* b1;
   const float* b2;
-  bf16* hbuf;
+  void* hbuf;  // bf16 [rows, H], or fp32 for TF32 compute
   void* out;
   const void* residual;
   const int* pos;
@@ -290,7 +290,10 @@ struct Vec4Io<__half> {
 // bandwidth, which is what bounds the single-CTA kernel in the compute-bound regime (128 x 256 tiles: 85 FLOP per
 // byte moved into the SM, while the MMA rate asks for ~190).  Everything else (tile schedule over pairs, the h
 // dependency flags, the epilogue of each CTA over its own 128 accumulator rows) is the single-CTA design.
-template <typename OutT, bool kTrace, int kCtas>
+// kTf32: operands are fp32 in memory (x rows, the reference's fp32 FMoELinear weights, h) and the tensor cores read
+// them as TF32 (tcgen05.mma.kind::tf32: 10-bit mantissa, fp32 accumulation) -- the <= 1e-3 flavour of the path.  A
+// 128-byte swizzle row then holds 32 elements instead of 64, i.e. twice the k-blocks and twice the bytes per tile.
+template <typename OutT, bool kTrace, int kCtas, bool kTf32>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
            const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const FfnParams p) {
@@ -376,8 +379,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   const int n_tiles = ng * (m1 + m2);
   const int tile0 = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = kCtas == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int kb1 = p.D / (kBlockK * kps);  // pipeline stages per tile of the first GEMM
-  const int kb2 = p.H / (kBlockK * kps);
+  constexpr int kKel = kTf32 ? kBlockK / 2 : kBlockK;  // elements per 128-byte k-block
+  const int kb1 = p.D / (kKel * kps);  // pipeline stages per tile of the first GEMM
+  const int kb2 = p.H / (kKel * kps);
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -455,7 +459,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   } else if (warp == 1) {
     // ============================ MMA issuer (one thread) ============================
     if (lane == 0 && (kCtas == 1 || leader)) {  // pair: the leader issues for both CTAs
-      const uint32_t idesc = ptx::make_idesc(1u /*bf16*/, kBlockM * kCtas, static_cast<uint32_t>(p.bn));
+      const uint32_t idesc = ptx::make_idesc(kTf32 ? 2u /*tf32*/ : 1u /*bf16*/, kBlockM * kCtas,
+                                             static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -479,7 +484,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance both descriptors by k * 16 elements * 2 B = 32 B -> +2 in 16-byte units
-              if constexpr (kCtas == 2)
+              if constexpr (kTf32)
+                ptx::umma_tf32_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
+              else if constexpr (kCtas == 2)
                 ptx::umma_f16_ss_pair(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
               else
                 ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
@@ -560,6 +567,36 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         ptx::tc_fence_after();
         if (tracer_thread) tr.rec(t, kEvEpiAccReady);
         int ci = 0;
+        if constexpr (kTf32) {
+          // fp32 h: fp32 staging (one 16 KiB buffer per set, two barriers per chunk), exact activation
+          float* hb = static_cast<float*>(p.hbuf);
+#pragma unroll 1
+          for (int c0 = set * 32; c0 < nrows; c0 += 64) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]) + bias;
+              if (act == B200MOE_ACT_SILU) v = __fdividef(v, 1.0f + __expf(-v));
+              else if (act == B200MOE_ACT_RELU) v = fmaxf(v, 0.0f);
+              else v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+              stg_f[j * kBlockM + feat_l] = v;
+            }
+            ptx::named_bar_sync(set_bar, kSetThreads);
+            float* hrow = hb + static_cast<size_t>(gr.row0 + c0 + q * 8) * p.H + feat0 + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = q * 8 + i;
+              const float4 val = *reinterpret_cast<const float4*>(stg_f + j * kBlockM + lane * 4);
+              st_pred_v4(hrow + static_cast<size_t>(i) * p.H,
+                         make_uint4(__float_as_uint(val.x), __float_as_uint(val.y), __float_as_uint(val.z),
+                                    __float_as_uint(val.w)),
+                         c0 + j < nst);
+            }
+            ptx::named_bar_sync(set_bar, kSetThreads);
+          }
+        } else
 #pragma unroll 1
         for (int c0 = set * 32; c0 < nrows; c0 += 64, ++ci) {
           bf16* sb = reinterpret_cast<bf16*>(stg_raw) + (ci & 1) * (32 * kBlockM);  // two 8 KB buffers per set
@@ -594,7 +631,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           {
             const int half = lane >> 4;
             const int l16 = lane & 15;
-            bf16* hrow = p.hbuf + static_cast<size_t>(gr.row0 + c0 + q * 8 + half) * p.H + feat0 + l16 * 8;
+            bf16* hrow =
+                static_cast<bf16*>(p.hbuf) + static_cast<size_t>(gr.row0 + c0 + q * 8 + half) * p.H + feat0 + l16 * 8;
             const size_t step = 2 * static_cast<size_t>(p.H);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -859,16 +897,17 @@ size_t smem_bytes_for(int b_rows, int kps, int stages) {
          2 * kStagingBytes + 2 * 256 * 4;
 }
 
-template <typename OutT, int kCtas>
+template <typename OutT, int kCtas, bool kTf32 = false>
 cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
                          const CUtensorMap& th, const FfnParams& p, cudaStream_t stream) {
   const size_t smem = smem_bytes_for(a.bn / kCtas, p.kps, p.stages);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_kernel<OutT, false, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ffn_kernel<OutT, false, kCtas, kTf32>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(ffn_kernel<OutT, true, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(ffn_kernel<OutT, true, kCtas, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -901,9 +940,9 @@ cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUten
   cfg.numAttrs = na;
   cudaError_t e;
   if (p.trace != nullptr)
-    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, true, kCtas>, tw1, tw2, tx, th, p);
+    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, true, kCtas, kTf32>, tw1, tw2, tx, th, p);
   else
-    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, false, kCtas>, tw1, tw2, tx, th, p);
+    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, false, kCtas, kTf32>, tw1, tw2, tx, th, p);
   count_launch();
   return e;
 }
@@ -925,7 +964,9 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
     const char* v = std::getenv("B200MOE_PAIR");
     return (v && *v) ? std::atoi(v) : 1;
   }();
-  const bool pair = pair_env != 0 && a.bn == 256 && (a.H / kBlockM) % 2 == 0 && (a.D / kBlockM) % 2 == 0;
+  const bool tf32 = a.tf32 != 0;
+  if (tf32 && (a.out_dtype != B200MOE_F32 || a.ep != nullptr)) return cudaErrorInvalidValue;
+  const bool pair = !tf32 && pair_env != 0 && a.bn == 256 && (a.H / kBlockM) % 2 == 0 && (a.D / kBlockM) % 2 == 0;
   const int ctas = pair ? 2 : 1;
   // two k-blocks per pipeline stage (one TMA instruction per operand and stage) wherever that still leaves >= 3 stages
   static const int kps_env = [] {
@@ -933,9 +974,17 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
     return (v && *v) ? std::atoi(v) : 2;
   }();
   int kps = kps_env == 1 ? 1 : 2;
-  if (stages_for(a.bn / ctas, kps) < 3 || (a.D / kBlockK) % kps != 0 || (a.H / kBlockK) % kps != 0) kps = 1;
+  const int kel = tf32 ? kBlockK / 2 : kBlockK;  // elements per 128-byte k-block
+  if (stages_for(a.bn / ctas, kps) < 3 || (a.D / kel) % kps != 0 || (a.H / kel) % kps != 0) kps = 1;
   CUtensorMap tw1, tw2, tx, th;
-  if (!make_tmap_bf16_kblocks(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kps) ||
+  if (tf32) {
+    if (!make_tmap_f32_kblocks(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kps) ||
+        !make_tmap_f32_kblocks(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM, kps) ||
+        !make_tmap_f32_kblocks(&tx, a.xbuf, a.n_rows, a.D, a.bn, kps) ||
+        !make_tmap_f32_kblocks(&th, a.hbuf, a.n_rows, a.H, a.bn, kps)) {
+      return cudaErrorInvalidValue;
+    }
+  } else if (!make_tmap_bf16_kblocks(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kps) ||
       !make_tmap_bf16_kblocks(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM, kps) ||
       !make_tmap_bf16_kblocks(&tx, a.xbuf, a.n_rows, a.D, a.bn / ctas, kps) ||
       !make_tmap_bf16_kblocks(&th, a.hbuf, a.n_rows, a.H, a.bn / ctas, kps)) {
@@ -998,6 +1047,7 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   // phase-2 tiles trail their group's phase-1 tiles by ~3 waves of the grid
   const int m1 = a.H / (kBlockM * ctas);
   p.lag = (3 * (num_sms() / ctas) + m1 - 1) / m1;
+  if (tf32) return launch_typed<float, 1, true>(a, tw1, tw2, tx, th, p, stream);
   switch (a.out_dtype) {
     case B200MOE_F32:
       return pair ? launch_typed<float, 2>(a, tw1, tw2, tx, th, p, stream)

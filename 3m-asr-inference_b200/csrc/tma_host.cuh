@@ -61,6 +61,21 @@ inline bool make_tmap_bf16_kblocks(CUtensorMap* tm, const void* base, uint64_t r
   return r == CUDA_SUCCESS;
 }
 
+// fp32 flavour (TF32 compute): a 128-byte swizzle row holds 32 elements, so the view is [cols / 32][rows][32].
+inline bool make_tmap_f32_kblocks(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                  uint32_t box_kblocks) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc || cols % 32 != 0 || box_kblocks == 0 || box_kblocks > 256 || box_rows > 256) return false;
+  cuuint64_t dims[3] = {32, rows, cols / 32};
+  cuuint64_t strides[2] = {cols * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, box_rows, box_kblocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

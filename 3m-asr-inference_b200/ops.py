@@ -15,7 +15,8 @@ from typing import Dict, NamedTuple, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_RELU, ACT_SILU, BF16, F16, F32, GATE_3M, GATE_NAIVE  # noqa: F401 (re-exported)
+from ._lib import (ACT_GELU, ACT_RELU, ACT_SILU, BF16, COMPUTE_BF16, COMPUTE_TF32, F16, F32, GATE_3M,  # noqa: F401
+                   GATE_NAIVE)
 
 _DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -119,6 +120,13 @@ def pack_experts(W1, b1, W2, b2) -> PackedExperts:
     def f32(b):
         return None if b is None else b.detach().float().contiguous()
     return PackedExperts(pack_bf16(W1.detach().contiguous()), f32(b1), pack_bf16(W2.detach().contiguous()), f32(b2))
+
+
+def fp32_experts(W1, b1, W2, b2) -> PackedExperts:
+    """The reference's fp32 FMoELinear weights as they are ([E, out, in], no packing): for compute=COMPUTE_TF32."""
+    def f32(t):
+        return None if t is None else t.detach().float().contiguous()
+    return PackedExperts(f32(W1), f32(b1), f32(W2), f32(b2))
 
 
 def pack_router(Wr: torch.Tensor) -> torch.Tensor:
@@ -262,8 +270,9 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
               seq_len: Optional[int] = None, top_k: int = 1, gate_mode: int = GATE_3M, act_type: int = ACT_SILU,
               ff_scale: float = 1.0, keep_expert_output: bool = False, out: Optional[torch.Tensor] = None,
               return_routing: bool = False, ws: Optional[torch.Tensor] = None,
-              Wr_packed: Optional[torch.Tensor] = None) -> LayerOut:
-    """The fused layer: out = (residual) + ff_scale * sum_k score_k * FFN_{e_k}(x).  x [S, D] or [B, T, D]."""
+              Wr_packed: Optional[torch.Tensor] = None, compute: int = COMPUTE_BF16) -> LayerOut:
+    """The fused layer: out = (residual) + ff_scale * sum_k score_k * FFN_{e_k}(x).  x [S, D] or [B, T, D].
+    compute=COMPUTE_TF32: fp32 activations, `experts` from fp32_experts() (tensor cores in TF32, fp32 intermediates)."""
     dev = _need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out,
                      Wr_packed)
     shape = x.shape
@@ -291,7 +300,12 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
         Wr=_ptr(Wr), Wr_packed=_ptr(Wr_packed), br=_ptr(br), W1=_ptr(experts.W1), b1=_ptr(experts.b1), W2=_ptr(experts.W2), b2=_ptr(experts.b2),
         B=B, T=T, D=D, Demb=Demb, E=E, H=H, top_k=top_k, gate_mode=gate_mode, act_type=act_type,
         dtype=dtype_code(x), keep_expert_output=int(keep_expert_output), ff_scale=float(ff_scale),
-        idx_out=_ptr(idx), score_out=_ptr(score), counts_out=_ptr(counts), mapping_out=_ptr(mapping))
+        idx_out=_ptr(idx), score_out=_ptr(score), counts_out=_ptr(counts), mapping_out=_ptr(mapping),
+        compute=int(compute))
+    if compute == COMPUTE_TF32 and (x.dtype != torch.float32 or experts.W1.dtype != torch.float32):
+        raise TypeError("TF32 compute takes fp32 activations and fp32 expert weights (ops.fp32_experts)")
+    if compute == COMPUTE_BF16 and experts.W1.dtype != torch.bfloat16:
+        raise TypeError("bf16 compute takes bf16-packed expert weights (ops.pack_experts)")
     lib = _lib.load()
     import ctypes
     _lib.check(lib.b200moe_forward(ctypes.byref(a), _ptr(ws), ws.numel(), _stream()), "b200moe_forward")

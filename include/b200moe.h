@@ -160,6 +160,11 @@ typedef struct b200moe_layer_args {
   float* score_out;
   int* counts_out;
   int* mapping_out;
+  /* Arithmetic of the expert GEMMs.  B200MOE_COMPUTE_BF16 (0, default): W1 / W2 are the bf16-packed weights.
+   * B200MOE_COMPUTE_TF32 (1): W1 / W2 point at the reference's own fp32 FMoELinear weights ([E, H, D] / [E, D, H],
+   * no packing), activations must be fp32 (`dtype` 0), the tensor cores run tcgen05 kind::tf32 with fp32 accumulation
+   * and fp32 intermediates: outputs within rel-L2 1e-3 of the fp32 reference instead of 1e-2. */
+  int compute;
 } b200moe_layer_args;
 
 int b200moe_forward(const b200moe_layer_args* args, void* ws, size_t ws_bytes, cudaStream_t stream);

@@ -125,6 +125,42 @@ def test_layer_other_dims(ops, oracle, synth, S, E, D, H, Demb):
     assert rel_l2(res2.out.float().cpu(), ref["moe"]) <= BF16_REL_L2
 
 
+TF32_REL_L2 = 1e-3   # north_star tolerance for TF32 outputs vs the fp32 reference
+
+
+@pytest.mark.parametrize("S,top_k", [(50, 1), (3200, 1), (777, 2)])
+def test_layer_tf32(ops, oracle, synth, S, top_k):
+    """fp32 activations + the reference's own fp32 expert weights (no packing), tensor cores in TF32: <= 1e-3.
+    The expert weights are taken OFF the bf16 grid here (the bf16-grid weights of the other tests are exactly
+    representable in TF32, which would hide the TF32 rounding of a real checkpoint)."""
+    E, D, H = 32, 512, 1024
+    naive = top_k > 1
+    Demb = 0 if naive else 512
+    w = synth.make_weights(9000 + S, E, D, H, Demb, random_bias=True, router_bias=naive)
+    g = torch.Generator().manual_seed(9100 + S)
+    w.W1 = w.W1 * (1.0 + 1e-3 * torch.randn(w.W1.shape, generator=g))
+    w.W2 = w.W2 * (1.0 + 1e-3 * torch.randn(w.W2.shape, generator=g))
+    x, embed = synth.make_activations(9200 + S, S, D, Demb, w, top_k=top_k)
+    # (x and the router stay on the grid: the routing margin the generator guarantees must not be disturbed)
+    gm_o = oracle.GATE_NAIVE if naive else oracle.GATE_3M
+    gm = ops.GATE_NAIVE if naive else ops.GATE_3M
+    ref = oracle.moe_forward(x, embed, w.Wr, w.br, w.W1, w.b1, w.W2, w.b2, top_k=top_k, gate_mode=gm_o, residual=x,
+                             ff_scale=0.5)
+    experts = ops.fp32_experts(dev(w.W1), dev(w.b1), dev(w.W2), dev(w.b2))
+    xd, ed = dev(x), dev(embed)
+    res = ops.moe_layer(xd, ed, dev(w.Wr), dev(w.br), experts, residual=xd, top_k=top_k, gate_mode=gm, ff_scale=0.5,
+                        return_routing=True, compute=ops.COMPUTE_TF32)
+    if top_k == 1:
+        assert torch.equal(res.idx.cpu().long(), ref["idx"])
+        assert torch.equal(res.mapping.cpu().long(), ref["mapping"].view(-1))
+    assert torch.equal(res.counts.cpu().long(), ref["counts"])
+    assert rel_l2(res.out.cpu(), ref["out"]) <= TF32_REL_L2
+    res2 = ops.moe_layer(xd, ed, dev(w.Wr), dev(w.br), experts, residual=None, top_k=top_k, gate_mode=gm, ff_scale=1.0,
+                         compute=ops.COMPUTE_TF32)
+    err = rel_l2(res2.out.cpu(), ref["moe"])
+    assert err <= TF32_REL_L2, f"MoE term rel-L2 {err:.2e}"
+
+
 def test_layer_padding_and_keep_output(ops, oracle, synth):
     E, D, H, Demb, B, T = 32, 512, 1024, 512, 6, 60
     w = synth.make_weights(31, E, D, H, Demb, random_bias=True)
