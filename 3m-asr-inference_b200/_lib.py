@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200moe_profile_enable": (_i, [_i]),
     "b200moe_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "b200moe_pack_bf16": (_i, [_vp, _i, _vp, _sz, _vp]),
+    "b200moe_pack_tf32": (_i, [_vp, _vp, _sz, _vp]),
     "b200moe_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "b200moe_gate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200moe_router_pack_bytes": (_sz, [_i]),

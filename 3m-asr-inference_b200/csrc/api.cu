@@ -196,6 +196,13 @@ int b200moe_pack_bf16(const void* src, int src_dtype, void* dst_bf16, size_t n, 
   return B200MOE_OK;
 }
 
+int b200moe_pack_tf32(const float* src, float* dst, size_t n, cudaStream_t stream) {
+  if ((!src || !dst) && n > 0) return fail(B200MOE_ERR_ARG, "pack_tf32: null pointer");
+  cudaError_t e = launch_pack_tf32(src, dst, n, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pack_tf32");
+  return B200MOE_OK;
+}
+
 size_t b200moe_workspace_bytes(int S, int E, int D, int H, int top_k) {
   if (S < 0 || E < 1 || D < 1 || H < 0 || top_k < 1) return 0;
   return carve_workspace(nullptr, S, E, D, H, top_k).bytes;

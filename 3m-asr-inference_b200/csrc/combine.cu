@@ -8,6 +8,7 @@
 //   x ff_scale, + residual                                trainer_3m_fix/layer/fmoe_transformer.py:155-158
 // HBM-bound: one warp per token row, 128-bit loads and stores, fp32 accumulation.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace b200moe {
 
@@ -172,6 +173,23 @@ cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* sc
       return cudaErrorInvalidValue;
   }
 #undef B200MOE_COMBINE
+  count_launch();
+  return cudaGetLastError();
+}
+
+namespace {
+__global__ void __launch_bounds__(256) pack_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = ptx::round_tf32(src[i]);
+}
+}  // namespace
+
+cudaError_t launch_pack_tf32(const float* src, float* dst, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  size_t want = (n + 255) / 256;
+  const int grid = static_cast<int>(want > 148 * 16 ? 148 * 16 : want);
+  pack_tf32_kernel<<<grid, 256, 0, stream>>>(src, dst, n);
   count_launch();
   return cudaGetLastError();
 }

@@ -213,6 +213,7 @@ cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
                            float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream);
 cudaError_t launch_pack_bf16(const void* src, int src_dtype, bf16* dst, size_t n, cudaStream_t stream);
+cudaError_t launch_pack_tf32(const float* src, float* dst, size_t n, cudaStream_t stream);  // round to nearest TF32
 
 void count_launch(int n = 1);
 

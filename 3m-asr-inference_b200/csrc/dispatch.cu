@@ -275,7 +275,14 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
           float4 regs[kRowsPerBatch];
 #pragma unroll
           for (int r = 0; r < kRowsPerBatch; ++r)
-            if (d[r] >= 0) regs[r] = __ldg(reinterpret_cast<const float4*>(src[r]) + v);
+            if (d[r] >= 0) {
+              regs[r] = __ldg(reinterpret_cast<const float4*>(src[r]) + v);
+              // the tensor cores truncate fp32 words to TF32: round to nearest here instead
+              regs[r].x = ptx::round_tf32(regs[r].x);
+              regs[r].y = ptx::round_tf32(regs[r].y);
+              regs[r].z = ptx::round_tf32(regs[r].z);
+              regs[r].w = ptx::round_tf32(regs[r].w);
+            }
 #pragma unroll
           for (int r = 0; r < kRowsPerBatch; ++r)
             if (d[r] >= 0)

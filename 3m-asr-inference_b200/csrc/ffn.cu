@@ -581,7 +581,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
               if (act == B200MOE_ACT_SILU) v = __fdividef(v, 1.0f + __expf(-v));
               else if (act == B200MOE_ACT_RELU) v = fmaxf(v, 0.0f);
               else v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-              stg_f[j * kBlockM + feat_l] = v;
+              stg_f[j * kBlockM + feat_l] = ptx::round_tf32(v);  // the second GEMM would truncate it otherwise
             }
             ptx::named_bar_sync(set_bar, kSetThreads);
             float* hrow = hb + static_cast<size_t>(gr.row0 + c0 + q * 8) * p.H + feat0 + lane * 4;

@@ -300,6 +300,14 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t smem_dst, const void* 
       : "memory");
 }
 
+// fp32 -> nearest TF32 value (10-bit mantissa), kept in an fp32 word.  tcgen05 kind::tf32 TRUNCATES the fp32 words it
+// reads; rounding first removes the systematic -2^-11 bias per operand that truncation alone would leave.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -123,10 +123,17 @@ def pack_experts(W1, b1, W2, b2) -> PackedExperts:
 
 
 def fp32_experts(W1, b1, W2, b2) -> PackedExperts:
-    """The reference's fp32 FMoELinear weights as they are ([E, out, in], no packing): for compute=COMPUTE_TF32."""
+    """The reference's fp32 FMoELinear weights ([E, out, in]) rounded once to TF32 values: for compute=COMPUTE_TF32."""
     def f32(t):
         return None if t is None else t.detach().float().contiguous()
-    return PackedExperts(f32(W1), f32(b1), f32(W2), f32(b2))
+
+    def tf32(t):
+        _need_cuda(t)
+        src = t.detach().float().contiguous()
+        dst = torch.empty_like(src)
+        _lib.check(_lib.load().b200moe_pack_tf32(_ptr(src), _ptr(dst), src.numel(), _stream()), "b200moe_pack_tf32")
+        return dst
+    return PackedExperts(tf32(W1), f32(b1), tf32(W2), f32(b2))
 
 
 def pack_router(Wr: torch.Tensor) -> torch.Tensor:

@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--compute", default="bf16", choices=["bf16", "tf32"],
+                    help="bf16 (default, the headline) or tf32: fp32 activations + fp32 weights, <= 1e-3 parity bar")
     ap.add_argument("--ep", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: peer-memory kernels (product) or NCCL all-to-all (comparison)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -204,6 +206,9 @@ def main():
     ep = importlib.import_module(PKG + (".ep" if args.ep == "nccl" else ".ep_p2p")) if world > 1 else None
 
     wl = WORKLOADS[args.workload]
+    tf32 = args.compute == "tf32"
+    if tf32 and world > 1:
+        raise SystemExit("--compute tf32 is single-GPU")
     L = wl["layers"]
     S = wl["utts"] * wl["tok_per_utt"]          # tokens per layer on THIS rank (weak scaling)
     E_local = E // world
@@ -218,18 +223,22 @@ def main():
 
     layers = []
     for _ in range(L):
-        W1 = xavier((E_local, H, D), H * D, E * D, gen).bfloat16()
-        W2 = xavier((E_local, D, H), D * H, E * H, gen).bfloat16()
+        W1 = xavier((E_local, H, D), H * D, E * D, gen)
+        W2 = xavier((E_local, D, H), D * H, E * H, gen)
+        if not tf32:
+            W1, W2 = W1.bfloat16(), W2.bfloat16()
         b1 = torch.zeros(E_local, H, device=dev)
         b2 = torch.zeros(E_local, D, device=dev)
         Wr = xavier((DEMB + D, E), DEMB + D, E, gen_shared).bfloat16().float()
-        layers.append((Wr, ops.PackedExperts(W1, b1, W2, b2), ops.pack_router(Wr)))
+        experts = ops.fp32_experts(W1, b1, W2, b2) if tf32 else ops.PackedExperts(W1, b1, W2, b2)
+        layers.append((Wr, experts, ops.pack_router(Wr)))
 
     # ---- synthetic activations: pinned host copies (for e2e) and device-resident copies (for value)
     g = torch.Generator().manual_seed(20260003 + rank)
-    x_host = torch.randn(S, D, generator=g).bfloat16().pin_memory()
-    e_host = torch.randn(S, DEMB, generator=g).bfloat16().pin_memory()
-    out_host = torch.empty(S, D, dtype=torch.bfloat16).pin_memory()
+    act_dtype = torch.float32 if tf32 else torch.bfloat16
+    x_host = torch.randn(S, D, generator=g).bfloat16().to(act_dtype).pin_memory()
+    e_host = torch.randn(S, DEMB, generator=g).bfloat16().to(act_dtype).pin_memory()
+    out_host = torch.empty(S, D, dtype=act_dtype).pin_memory()
     x_dev = x_host.to(dev)
     e_dev = e_host.to(dev)
     x_stage = torch.empty_like(x_dev)
@@ -253,7 +262,8 @@ def main():
                                 Wr_packed=Wrp)
             else:
                 ops.moe_layer(cur, e_in, Wr, None, experts, residual=cur, top_k=1, gate_mode=ops.GATE_3M,
-                              act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=Wrp)
+                              act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=None if tf32 else Wrp,
+                              compute=ops.COMPUTE_TF32 if tf32 else ops.COMPUTE_BF16)
             cur = out
         return cur
 
@@ -388,14 +398,15 @@ def main():
     traffic = None   # DRAM bytes per launch of the same kernel from one `ncu --set full` capture (profiles/)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ffn_traffic.json")))
-        if args.workload == tr.get("workload") and world == 1:
+        if args.workload == tr.get("workload") and world == 1 and not tf32:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
-    w_bytes = 2 * E_local * D * H * 2 + (E_local * H + E_local * D) * 4         # bf16 W1 + W2, fp32 biases (this rank)
+    es = 4 if tf32 else 2                                                       # bytes per weight / activation element
+    w_bytes = 2 * E_local * D * H * es + (E_local * H + E_local * D) * 4        # W1 + W2, fp32 biases (this rank)
     if stage_calls.get("expert_ffn"):
         t_ffn = stage_ms["expert_ffn"] / stage_calls["expert_ffn"] * 1e-3      # seconds per launch
-        act_bytes = S * (2 * D + 2 * D + 2 * D + 8)                             # xbuf read, residual read, out write, pos+score
+        act_bytes = S * (3 * es * D + 8)                                        # xbuf read, residual read, out write, pos+score
         alg_bytes = w_bytes + act_bytes
         flops = S * 4 * D * H
         hbm_time = alg_bytes / (hbm_peak * 1e9)
@@ -412,7 +423,7 @@ def main():
                         "algorithmic_flops_per_launch": flops, "us_per_launch": t_ffn * 1e6}
     # the whole layer (gate + dispatch + expert FFN with the fused combine) against the same peaks: SURVEY section 8(d)'s
     # 9 236 B per token (bf16, top-1) + the expert weights once, over the time a layer takes inside the timed region
-    layer_bytes = w_bytes + S * 9236
+    layer_bytes = w_bytes + S * 9236 * (es // 2)
     layer_flops = S * (4 * D * H + 2 * (D + DEMB) * E)
     t_layer = ms_step * 1e-3 / L
     layer_roofline = {
@@ -447,7 +458,7 @@ def main():
         line = {
             "metric": "moe_layer_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32" if tf32 else "bf16", "data": "synthetic",
             "config": workload_config(args, wl, S * world),
             "utterances_per_sec": wl["utts"] * world / (ms_step * 1e-3),
             "mode": "cuda_graph" if use_graph else "eager",
@@ -459,8 +470,8 @@ def main():
             "layer_roofline": layer_roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": x_host.numel() * 2 + e_host.numel() * 2,
-                    "d2h_bytes_per_step": out_host.numel() * 2},
+                    "h2d_bytes_per_step": (x_host.numel() + e_host.numel()) * x_host.element_size(),
+                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,

@@ -80,6 +80,10 @@ int b200moe_device_supported(int dev);
  * (trainer_3m_fix/fmoe/layers.py:34), which is already the K-major B operand the tensor cores want; packing
  * only casts them to bf16.  n = number of elements. */
 int b200moe_pack_bf16(const void* src, int src_dtype, void* dst_bf16, size_t n, cudaStream_t stream);
+/* For B200MOE_COMPUTE_TF32: the fp32 weights rounded to the nearest TF32 value (10-bit mantissa), still fp32 words in
+ * the same [E, out, in] layout; dst may alias src.  tcgen05 kind::tf32 truncates whatever fp32 words it reads, which
+ * on un-rounded weights leaves a systematic ~1e-3 relative bias. */
+int b200moe_pack_tf32(const float* src, float* dst, size_t n, cudaStream_t stream);
 
 /* ---- workspace --------------------------------------------------------------------------------------------
  * Bytes of scratch b200moe_forward / b200moe_plugin_enqueue / the staged entry points need for S tokens.
@@ -161,9 +165,9 @@ typedef struct b200moe_layer_args {
   int* counts_out;
   int* mapping_out;
   /* Arithmetic of the expert GEMMs.  B200MOE_COMPUTE_BF16 (0, default): W1 / W2 are the bf16-packed weights.
-   * B200MOE_COMPUTE_TF32 (1): W1 / W2 point at the reference's own fp32 FMoELinear weights ([E, H, D] / [E, D, H],
-   * no packing), activations must be fp32 (`dtype` 0), the tensor cores run tcgen05 kind::tf32 with fp32 accumulation
-   * and fp32 intermediates: outputs within rel-L2 1e-3 of the fp32 reference instead of 1e-2. */
+   * B200MOE_COMPUTE_TF32 (1): W1 / W2 are the reference's fp32 FMoELinear weights ([E, H, D] / [E, D, H]) after
+   * b200moe_pack_tf32, activations must be fp32 (`dtype` 0), the tensor cores run tcgen05 kind::tf32 with fp32
+   * accumulation and fp32 intermediates: outputs within rel-L2 1e-3 of the fp32 reference instead of 1e-2. */
   int compute;
 } b200moe_layer_args;
 
