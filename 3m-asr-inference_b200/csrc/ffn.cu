@@ -862,21 +862,29 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     if constexpr (kCtas == 2) ptx::tmem_dealloc_pair<kTmemCols>(tmem_base);
     else ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
-  if (p.ep && threadIdx.x == 0) {
+  if (p.ep) {
     // Every store of this CTA into the peers' return buffers precedes the barrier above.  The last CTA of the grid to
     // get here tells every source rank that its rows are back (functions.py:185-191's all-to-all, without the host).
-    Tracer<kTrace> tr(p, 3, 4);
-    tr.rec(-2, kEvEpiChunkLd);
-    ptx::fence_acq_rel_sys();
-    tr.rec(-2, kEvEpiChunkStaged);
-    const int prev = atomicAdd(&p.ep_ctrl[2], 1);
-    tr.rec(-2, kEvEpiChunkDone);
-    if (prev == static_cast<int>(gridDim.x) - 1) {
-      ptx::fence_acq_rel_gpu();  // the other CTAs' system-wide fences precede their increments
-      p.ep_ctrl[2] = 0;
-      const int seq = p.ep_ctrl[0];
-      for (int r = 0; r < p.ep_world; ++r) ptx::st_release_sys(p.ep_ret_flag[r], seq);
+    // One thread per peer raises the flag: a single thread would serialise `world` NVLink round trips (each release
+    // waits for the previous flag's acknowledgement), which is what made this tail grow with the number of GPUs.
+    int* s_ep_last = s_tok;  // (the epilogue's routing table is free after the barrier above; no static smem here)
+    if (threadIdx.x == 0) {
+      Tracer<kTrace> tr(p, 3, 4);
+      tr.rec(-2, kEvEpiChunkLd);
+      ptx::fence_acq_rel_sys();
+      tr.rec(-2, kEvEpiChunkStaged);
+      const int prev = atomicAdd(&p.ep_ctrl[2], 1);
+      tr.rec(-2, kEvEpiChunkDone);
+      const int last = prev == static_cast<int>(gridDim.x) - 1;
+      if (last) {
+        ptx::fence_acq_rel_gpu();  // the other CTAs' system-wide fences precede their increments
+        p.ep_ctrl[2] = 0;
+      }
+      *s_ep_last = last;
     }
+    __syncthreads();
+    if (*s_ep_last && static_cast<int>(threadIdx.x) < p.ep_world)
+      ptx::st_release_sys(p.ep_ret_flag[threadIdx.x], p.ep_ctrl[0]);
   }
 }
 
