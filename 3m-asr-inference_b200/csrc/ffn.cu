@@ -689,33 +689,39 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           const size_t fo16 = static_cast<size_t>(feat0 + l16 * 8);
           // Residual rows of this set's first two chunks are requested now, while the MMAs of the tile still run (a
           // global load under full HBM load takes 1-2 us); the rows of chunk k+2 as soon as chunk k is done.
-          uint4 rres[2][4];
+          // ALL of this set's chunks (up to four at 256-token tiles) are requested here.  Loads issued inside the chunk
+          // loop instead stalled the next chunk's column phase until they returned (6.2 vs 4.4 us per 256-token tile).
+          uint4 rres[4][4];
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < 4; ++cc) {
+            if (cc < 2 || nrows > 128) {  // (uniform) tiles of up to 128 tokens have two chunks per set
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int col = (2 * cc + set) * 32 + q * 8 + 2 * i + half;
-              const bool v = col < nrows;
-              const int tok = v ? s_tok[col] : 0;
-              rres[cc][i] = ld_pred_v4(res + static_cast<size_t>(tok) * p.D + fo16, v && with_res);
+              for (int i = 0; i < 4; ++i) {
+                const int col = (2 * cc + set) * 32 + q * 8 + 2 * i + half;
+                const bool v = col < nrows;
+                const int tok = v ? s_tok[col] : 0;
+                rres[cc][i] = ld_pred_v4(res + static_cast<size_t>(tok) * p.D + fo16, v && with_res);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rres[cc][i] = make_uint4(0u, 0u, 0u, 0u);
             }
           }
           ptx::mbar_wait(tfull_bar(as), aphase);
           ptx::tc_fence_after();
           if (tracer_thread) tr.rec(t, kEvEpiAccReady);
           int ci = 0;
-#pragma unroll 1
-          for (int cb = set * 32; cb < nrows; cb += 128) {
+          {
 #pragma unroll
-            for (int cs = 0; cs < 2; ++cs) {  // spelled out twice: the residual registers need static indices
-              const int c0 = cb + cs * 64;
+            for (int cs = 0; cs < 4; ++cs) {  // spelled out: the residual registers need static indices
+              const int c0 = set * 32 + cs * 64;
               if (c0 < nrows) {               // uniform over the set
                 OutT* sb = reinterpret_cast<OutT*>(stg_raw) + (ci & 1) * (32 * kBlockM);
                 ++ci;
                 {
                   uint32_t r[32];
                   ptx::tmem_ld_32x32b_x32(taddr + c0, r);
-                  float scv[32];
+                  float scv[32];  // per-column scale, fetched while the TMEM load is in flight
 #pragma unroll
                   for (int j4 = 0; j4 < 8; ++j4) {
                     const float4 v4 = *reinterpret_cast<const float4*>(s_sc + c0 + 4 * j4);  // broadcast reads
@@ -745,14 +751,6 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
                   o.z = add_packed<OutT>(rres[cs][i].z, a.z);
                   o.w = add_packed<OutT>(rres[cs][i].w, a.w);
                   st_pred_v4(out + static_cast<size_t>(tok) * p.D + fo16, o, v && st2);
-                }
-                // residual rows of the chunk two steps ahead
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int col = c0 + 128 + q * 8 + 2 * i + half;
-                  const bool v = col < nrows;
-                  const int tok = v ? s_tok[col] : 0;
-                  rres[cs][i] = ld_pred_v4(res + static_cast<size_t>(tok) * p.D + fo16, v && with_res);
                 }
                 if (tracer_thread) tr.rec(t, kEvEpiChunkDone);
               }
