@@ -420,6 +420,36 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     }
     __syncthreads();
     if (threadIdx.x == 0 && c == static_cast<int>(blockIdx.x)) rtrace(p, 8);
+    if (n_tiles <= static_cast<int>(gridDim.x)) {
+      // One tile per CTA: the 32 token rows are still in the ring (the B operand of the x part, 128B-swizzled K-major
+      // blocks of 32 rows), so they are copied out of shared memory instead of being fetched from L2 a second time.
+      // Lane l of warp w: row 4w + l/8, 16-byte chunk l%8 of every k-block (4 rows x 128 B per instruction, no bank
+      // conflicts: the XOR swizzle permutes chunks inside a row's 128 bytes).
+      const int r = warp * 4 + (lane >> 3);
+      const int ch = lane & 7;
+      const int tok = c * kTok + r;
+      const int d = tok < p.S ? s_dst[r] : -1;
+      if (d >= 0) {
+        bf16* drow = p.xbuf + static_cast<size_t>(d) * p.D;
+        if (kEp) {
+          const int dest = s_exp[r] / ep.E_local;
+          const int slot = d - s_off[dest * ep.E_local];
+          drow = reinterpret_cast<bf16*>(ep.base[dest] + ep.lay.recv_x) +
+                 (static_cast<size_t>(ep.rank) * ep.cap + slot) * p.D;
+        }
+        const uint8_t* sx = smem_raw + (n_parts - 1) * kRSlot + kRSlotA + r * 128 + ((ch ^ (r & 7)) << 4);
+#pragma unroll 4
+        for (int j = 0; j < kb_x; ++j)
+          reinterpret_cast<uint4*>(drow)[j * 8 + ch] = *reinterpret_cast<const uint4*>(sx + j * kRBBlk);
+      } else if (tok < p.S && p.drop_out != nullptr) {
+        // dropped token (padding): output row = residual row (or zero); the fused FFN epilogue never touches it
+        const size_t row = static_cast<size_t>(tok) * p.D;
+        for (int k = ch * 8; k < p.D; k += 64)
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            p.drop_out[row + k + u] = p.drop_residual ? p.drop_residual[row + k + u] : __float2bfloat16_rn(0.0f);
+      }
+    } else
     // row copies: warp w moves rows w, w + 8, w + 16, w + 24 of the chunk, all four in flight (2 x 16 B per lane each)
     {
       const bf16* src[4];
