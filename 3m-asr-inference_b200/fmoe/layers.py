@@ -86,6 +86,7 @@ class FMoE(nn.Module):
         self.gate_hook = gate_hook
         self._cache = PackedExpertCache()
         self.ep_group = None  # torch.distributed group of the expert-parallel workers (world_size > 1)
+        self.ep_capacity = 8192  # tokens per rank per call the expert-parallel receive buffers are sized for
 
     def _expert_layers(self):
         e = self.experts
@@ -99,8 +100,22 @@ class FMoE(nn.Module):
         packed = self._cache.get(w1, w2)
         x = inp.reshape(-1, self.d_model).contiguous()
         Wr, br = self.gate.router_params()
+        if self.world_size > 1 and x.dtype == torch.bfloat16:
+            # expert parallelism over peer-mapped memory (the product path; context created collectively on first use)
+            from .. import ep_p2p
+            if getattr(self, "_ep_ctx", None) is None:
+                self._ep_ctx = ep_p2p.EpContext.from_process_group(self.num_expert, self.d_model,
+                                                                   max(self.ep_capacity, x.shape[0]) * self.top_k,
+                                                                   group=self.ep_group)
+            if x.shape[0] * self.top_k > self._ep_ctx.cap:
+                raise RuntimeError(f"{x.shape[0]} tokens x top-{self.top_k} exceed the expert-parallel capacity "
+                                   f"{self._ep_ctx.cap}; set a larger `ep_capacity` on every rank before the first forward")
+            out = self._ep_ctx.forward(x, None, Wr, br, packed, top_k=self.top_k, gate_mode=ops.GATE_NAIVE,
+                                       act_type=activation_code(act),
+                                       Wr_packed=self.gate.router_packed() if hasattr(self.gate, "router_packed") else None)
+            return out.reshape(inp.shape)
         if self.world_size > 1:
-            from .. import ep
+            from .. import ep   # fp32 / fp16 activations: the NCCL all-to-all formulation
             out = ep.ep_moe_layer(x, None, Wr, br, packed, num_local_expert=self.num_expert, group=self.ep_group,
                                   top_k=self.top_k, gate_mode=ops.GATE_NAIVE, act_type=activation_code(act))
             return out.reshape(inp.shape)

@@ -63,6 +63,20 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
         if capacity_factor is not None and capacity_factor > 0:
             raise NotImplementedError("token dropping by capacity is a training-time feature (cf = -1 at inference)")
 
+    ep_capacity = 8192   # tokens per rank per call the expert-parallel receive buffers are sized for
+
+    def _ep_context(self, n_tokens: int):
+        from . import ep_p2p
+        ctx = getattr(self, "_ep_ctx", None)
+        if ctx is None:
+            ctx = ep_p2p.EpContext.from_process_group(self.num_experts, self.idim, max(self.ep_capacity, n_tokens),
+                                                      group=self.comm)
+            self._ep_ctx = ctx
+        if n_tokens > ctx.cap:
+            raise RuntimeError(f"{n_tokens} tokens exceed ep_capacity={ctx.cap}; set a larger `ep_capacity` on every "
+                               f"rank before the first forward")
+        return ctx
+
     def _router(self):
         w = self.router_weights
         wr = w.detach()
@@ -95,8 +109,17 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
         packed = self._cache.get(self.experts.w_1, self.experts.w_2)
         act = activation_code(self.experts.activation)
         x_len = None if mask is None else mask.reshape(-1).to(torch.int32).contiguous()
+        if self.world_size > 1 and x.dtype == torch.bfloat16:
+            # expert parallelism over peer-mapped memory (the product path); the context is created collectively on
+            # the first call, `ep_capacity` (tokens per rank per call) sizes its receive buffers
+            ctx = self._ep_context(B * T)
+            out = ctx.forward(x.view(B * T, D), None if e is None else e.view(B * T, -1), Wr, br, packed,
+                              residual=None if residual is None else residual.contiguous().view(B * T, D), x_len=x_len,
+                              seq_len=T, top_k=1, gate_mode=ops.GATE_3M, act_type=act, ff_scale=ff_scale,
+                              keep_expert_output=self.keep_expert_output, Wr_packed=self._router_packed(Wr))
+            return out.view(B, T, D)
         if self.world_size > 1:
-            from . import ep
+            from . import ep   # fp32 / fp16 activations: the NCCL all-to-all formulation
             out = ep.ep_moe_layer(x.view(B * T, D), None if e is None else e.view(B * T, -1), Wr, br, packed,
                                   num_local_expert=self.num_experts, group=self.comm, top_k=1,
                                   gate_mode=ops.GATE_3M, act_type=act, ff_scale=ff_scale,

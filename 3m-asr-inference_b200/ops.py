@@ -317,3 +317,26 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
     import ctypes
     _lib.check(lib.b200moe_forward(ctypes.byref(a), _ptr(ws), ws.numel(), _stream()), "b200moe_forward")
     return LayerOut(out, idx, score, counts, mapping)
+
+
+# ---- torch.library registration ---------------------------------------------------------------------------------------------
+# The layer as a registered PyTorch operator, `torch.ops.b200moe.fmoe_forward`: the op the reference's FMoE.forward /
+# LocalFmoeCatEmbedFeedForward.forward boil down to (trainer_3m_fix/fmoe/layers.py:186-210, positionwise_feed_forward.py:
+# 209-265), so that it can sit in exported / compiled graphs like any ATen op.  Inference only (no autograd formula).
+@torch.library.custom_op("b200moe::fmoe_forward", mutates_args=(), device_types="cuda")
+def fmoe_forward(x: torch.Tensor, embed: Optional[torch.Tensor], router_weight: torch.Tensor,
+                 router_bias: Optional[torch.Tensor], w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+                 b2: Optional[torch.Tensor], residual: Optional[torch.Tensor], top_k: int, gate_mode: int, act_type: int,
+                 ff_scale: float) -> torch.Tensor:
+    """x [S, D] (or [B, T, D]); w1 [E, H, D] / w2 [E, D, H] bf16-packed (pack_experts); router_weight [Demb + D, E] fp32."""
+    Wrp = pack_router(router_weight) if gate_tc_usable(x.dtype, x.shape[-1], 0 if embed is None else embed.shape[-1],
+                                                       router_weight.shape[1], top_k) else None
+    return moe_layer(x.contiguous(), None if embed is None else embed.contiguous(), router_weight, router_bias,
+                     PackedExperts(w1, b1, w2, b2), residual=residual, top_k=top_k, gate_mode=gate_mode,
+                     act_type=act_type, ff_scale=ff_scale, Wr_packed=Wrp).out
+
+
+@fmoe_forward.register_fake
+def _fmoe_forward_fake(x, embed, router_weight, router_bias, w1, b1, w2, b2, residual, top_k, gate_mode, act_type,
+                       ff_scale):
+    return torch.empty_like(x)

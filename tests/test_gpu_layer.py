@@ -274,3 +274,16 @@ def test_module_mirrors(ops, oracle, synth):
                               gate_mode=oracle.GATE_NAIVE, act_type=oracle.ACT_GELU)
     assert tuple(y.shape) == (3, 100, 256)
     assert rel_l2(y.float().cpu().view(300, 256), ref2["out"]) <= BF16_REL_L2
+
+
+def test_registered_torch_op(ops, oracle, synth):
+    """torch.ops.b200moe.fmoe_forward (the registered custom op) == the oracle's FMoE forward."""
+    E, D, H, Demb, S = 32, 512, 1024, 512, 300
+    w = synth.make_weights(8800, E, D, H, Demb, random_bias=True)
+    x, embed = synth.make_activations(8801, S, D, Demb, w)
+    ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
+    ex = ops.pack_experts(dev(w.W1), dev(w.b1), dev(w.W2), dev(w.b2))
+    xd = dev(x, torch.bfloat16)
+    out = torch.ops.b200moe.fmoe_forward(xd, dev(embed, torch.bfloat16), dev(w.Wr), None, ex.W1, ex.b1, ex.W2, ex.b2, xd,
+                                         1, ops.GATE_3M, ops.ACT_SILU, 0.5)
+    assert rel_l2(out.float().cpu(), ref["out"]) <= BF16_REL_L2

@@ -67,3 +67,19 @@ def test_plugin_registry_names_and_fields():
     assert q.fields == p.fields and q.get_plugin_type() == "FMoEExpertPluginDynamic"
     assert c.create_plugin("plugin", {"data_type": 9, "num_expert": 32, "idim": 512, "hidden_units": 1024}) is None
     assert reg.get_plugin_creator("SoftmaxTopKPluginDynamic", "1", "") is not None
+
+
+def test_registered_torch_op_schema_and_shape_inference():
+    """torch.ops.b200moe.fmoe_forward exists with the expected schema; its fake (meta) kernel infers the output shape
+    without touching a GPU.  (The CUDA kernel itself is exercised in tests/test_gpu_layer.py.)"""
+    pkg("ops")
+    op = torch.ops.b200moe.fmoe_forward
+    schema = str(op.default._schema)
+    for name in ("x", "embed", "router_weight", "w1", "w2", "residual", "top_k", "gate_mode", "act_type", "ff_scale"):
+        assert name in schema
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        x = torch.empty(50, 512, dtype=torch.bfloat16)
+        out = op(x, None, torch.empty(512, 32), None, torch.empty(32, 1024, 512, dtype=torch.bfloat16), None,
+                 torch.empty(32, 512, 1024, dtype=torch.bfloat16), None, None, 1, 0, 0, 1.0)
+        assert out.shape == x.shape and out.dtype == x.dtype

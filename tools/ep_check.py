@@ -90,9 +90,34 @@ def main():
     ok = ok and good
     print(f"rank {rank} p2p 12 layers back to back: rel-L2 vs single-GPU chain {err:.2e}, status {ctx.status()} -> "
           f"{'ok' if good else 'FAIL'}", flush=True)
+    # the module mirror (LocalFmoeCatEmbedFeedForward with world_size > 1) takes the same path
+    layer_mod = importlib.import_module(PKG + ".layer")
+    mod = layer_mod.LocalFmoeCatEmbedFeedForward(D, Demb, num_experts=E_local, rank=rank, world_size=world,
+                                                 hidden_units=H, activation=layer_mod.Swish(), rand_init_router=True)
+    mod = mod.to(dev)
+    with torch.no_grad():
+        mod.router_weights.copy_(w.Wr.to(dev))
+        mod.experts.w_1.weight.copy_(w.W1[sl].to(dev))
+        mod.experts.w_1.bias.copy_(w.b1[sl].to(dev))
+        mod.experts.w_2.weight.copy_(w.W2[sl].to(dev))
+        mod.experts.w_2.bias.copy_(w.b2[sl].to(dev))
+    Bm, Tm = 4, 60 + rank
+    xm, em = synth.make_activations(77 + rank, Bm * Tm, D, Demb, w)
+    xm, em = xm.to(dev).bfloat16().view(Bm, Tm, D), em.to(dev).bfloat16().view(Bm, Tm, Demb)
+    with torch.no_grad():
+        om = mod(xm, em, residual=xm, ff_scale=0.5)
+    refm = ops.moe_layer(xm.view(-1, D), em.view(-1, Demb), Wr, None, full, residual=xm.view(-1, D), ff_scale=0.5,
+                         Wr_packed=Wrp).out
+    torch.cuda.synchronize()
+    errm = float((om.view(-1, D).float() - refm.float()).norm() / refm.float().norm())
+    goodm = errm < 5e-3 and getattr(mod, "_ep_ctx", None) is not None and mod._ep_ctx.status() == 0
+    ok = ok and goodm
+    print(f"rank {rank} module LocalFmoeCatEmbedFeedForward(world_size={world}) over peer memory: rel-L2 {errm:.2e} -> "
+          f"{'ok' if goodm else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
+    mod._ep_ctx.close()
     ctx.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
