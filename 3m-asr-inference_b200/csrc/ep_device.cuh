@@ -18,8 +18,13 @@ __device__ __forceinline__ bool ep_wait_flag_sys(const int* flag, int want, unsi
 }
 
 // Called by every thread of ONE CTA.  Waits until the rows of layer call `seq` from every rank have landed in this
-// rank's receive buffer, then builds the FFN group table over it (expert-major, source rank inside an expert, so that
-// consecutive tiles reuse an expert's weights while they are hot in L2) and clears the h flags.
+// rank's receive buffer, then builds the FFN group table over it and clears the h flags.  Groups of rows that came from
+// OTHER ranks are listed first, this rank's own rows last: the FFN kernel works through the table in order, so the
+// results that have to cross NVLink leave early and the system-scope fence at the end of the kernel mostly finds local
+// stores outstanding.  Every expert's weights are thus streamed twice, the second time from L2.
+// (Measured and dropped: telling the remote ranks "your rows are back" as soon as the remote groups are done, from inside
+// the running kernel.  It needs a fence.acq_rel.sys on every SM in mid-kernel, and that stalls the SM's other warps for
+// the NVLink round trip: +6 us on a 30 us kernel at 2 GPUs, against the ~3 us the early flag could save.)
 //   s_cnt: shared, world * (E_local + 1) ints;  s_g0: shared, E_local * world + 1 ints.
 __device__ __forceinline__ void ep_wait_and_build_groups(const EpPeers& ep, int seq, int bn, GroupRec* groups,
                                                          int* n_groups, int* h_ready, int gmax, int* s_cnt, int* s_g0) {
@@ -36,19 +41,33 @@ __device__ __forceinline__ void ep_wait_and_build_groups(const EpPeers& ep, int 
   // a peer that never showed up: run the rest of the layer over nothing rather than over garbage
   for (int i = threadIdx.x; i < W * stride; i += blockDim.x) s_cnt[i] = failed ? 0 : rc[i];
   __syncthreads();
+  // table order: (expert, source) for the REMOTE sources first, expert-major, then this rank's own rows per expert
+  const int n_rem = El * (W - 1);
+  auto entry = [&](int i, int& e, int& s) {
+    if (i < n_rem) {
+      e = i / (W - 1);
+      s = i - e * (W - 1);
+      s += s >= ep.rank;
+    } else {
+      e = i - n_rem;
+      s = ep.rank;
+    }
+  };
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int e = 0; e < El; ++e)
-      for (int s = 0; s < W; ++s) {
-        s_g0[e * W + s] = acc;
-        acc += (s_cnt[s * stride + e] + bn - 1) / bn;
-      }
+    for (int i = 0; i < El * W; ++i) {
+      int e, s;
+      entry(i, e, s);
+      s_g0[i] = acc;
+      acc += (s_cnt[s * stride + e] + bn - 1) / bn;
+    }
     s_g0[El * W] = acc;
     n_groups[0] = acc < gmax ? acc : gmax;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < El * W; i += blockDim.x) {
-    const int e = i / W, s = i - e * W;
+    int e, s;
+    entry(i, e, s);
     const int c = s_cnt[s * stride + e];
     int off = 0;  // rows of source s that precede expert e in its segment
     for (int k = 0; k < e; ++k) off += s_cnt[s * stride + k];
