@@ -33,6 +33,12 @@ class LayerArgs(C.Structure):
     ]
 
 
+class BlockArgs(C.Structure):
+    """struct b200moe_block_args"""
+    _fields_ = [("layer", LayerArgs), ("norm_ff_gamma", _vp), ("norm_ff_beta", _vp), ("norm_final_gamma", _vp),
+                ("norm_final_beta", _vp), ("eps", _f)]
+
+
 # name -> (restype, argtypes); every symbol include/b200moe.h declares
 SIGNATURES = {
     "b200moe_last_error": (C.c_char_p, []),
@@ -67,6 +73,11 @@ SIGNATURES = {
     "b200moe_ep_forward": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _vp]),
     "b200moe_ep_forward_stages": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _i, _vp]),
     "b200moe_ep_status": (_i, [_vp, C.POINTER(_i)]),
+    "b200moe_block_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "b200moe_block_forward": (_i, [C.POINTER(BlockArgs), _vp, _sz, _vp]),
+    "b200moe_ep_block_workspace_bytes": (_sz, [_vp, _i]),
+    "b200moe_ep_block_forward": (_i, [_vp, C.POINTER(BlockArgs), _vp, _sz, _vp]),
+    "b200moe_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp]),
     "b200moe_plugin_create": (_vp, [_i, _i, _i, _i, _i]),
     "b200moe_plugin_clone": (_vp, [_vp]),
     "b200moe_plugin_serialization_size": (_sz, [_vp]),

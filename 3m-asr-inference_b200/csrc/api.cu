@@ -106,7 +106,7 @@ int knob(std::atomic<int>& v, const char* env, int dflt) {
 // Defaults: the gate / route kernel and the expert-FFN kernel are launched with the PDL attribute and the FFN kernel
 // releases its dependents at its start, so that the next layer's route kernel does the embed half of the router GEMM
 // (constants only) while this layer's FFN kernel drains: measured 32.7 -> 29.8 us per layer on cfg3 under CUDA graphs.
-int pdl_mask() { return knob(g_pdl, "B200MOE_PDL", kPdlGate | kPdlFfn); }
+int pdl_mask() { return knob(g_pdl, "B200MOE_PDL", kPdlGate | kPdlFfn | kPdlLn); }
 int pdl_trigger() { return knob(g_pdl_trig, "B200MOE_PDL_TRIG", kPdlFfn); }
 int route_mode() { return knob(g_route, "B200MOE_ROUTE", 1); }
 
@@ -809,6 +809,115 @@ int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate
   f.top_k = 1;
   e = launch_ffn(f, stream);
   if (e != cudaSuccess) return cuda_fail(e, "enqueue/expert_ffn");
+  return B200MOE_OK;
+}
+
+// ---- the block around the layer: norm_ff in front, norm_final behind (fmoe_transformer.py:144-166) -----------------
+namespace {
+inline size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
+inline size_t dtype_bytes(int dtype) { return dtype == B200MOE_F32 ? 4 : 2; }
+
+// The normalised input lives behind the layer's own workspace.
+struct BlockPlan {
+  b200moe_layer_args layer;
+  size_t layer_ws;
+  void* xn;
+};
+
+int plan_block(const b200moe_block_args* b, size_t layer_ws, void* ws, size_t ws_bytes, BlockPlan* plan, const char* who) {
+  const b200moe_layer_args& a = b->layer;
+  const int S = a.B * a.T;
+  const bool ln_in = b->norm_ff_gamma != nullptr, ln_out = b->norm_final_gamma != nullptr;
+  if ((ln_in && !b->norm_ff_beta) || (ln_out && !b->norm_final_beta))
+    return fail(B200MOE_ERR_ARG, "%s: a LayerNorm needs both gamma and beta", who);
+  if ((ln_in || ln_out) && !layernorm_supported(a.D))
+    return fail(B200MOE_ERR_ARG, "%s: LayerNorm over D=%d is not supported (multiple of 8, at most 1024)", who, a.D);
+  if (!(b->eps >= 0.0f)) return fail(B200MOE_ERR_ARG, "%s: bad eps", who);
+  plan->layer = a;
+  plan->layer_ws = layer_ws;
+  plan->xn = nullptr;
+  if (ln_in && S > 0) {
+    const size_t need = align256(layer_ws) + static_cast<size_t>(S) * a.D * dtype_bytes(a.dtype);
+    if (!ws || ws_bytes < need)
+      return fail(B200MOE_ERR_WORKSPACE, "%s: workspace %zu B < required %zu B", who, ws_bytes, need);
+    plan->xn = static_cast<uint8_t*>(ws) + align256(layer_ws);
+    plan->layer.x = plan->xn;
+  }
+  return B200MOE_OK;
+}
+}  // namespace
+
+size_t b200moe_block_workspace_bytes(int S, int E, int D, int H, int top_k) {
+  const size_t layer = b200moe_workspace_bytes(S, E, D, H, top_k);
+  if (layer == 0) return 0;
+  return align256(layer) + static_cast<size_t>(S) * D * 4;
+}
+
+size_t b200moe_ep_block_workspace_bytes(const b200moe_ep_ctx* c, int H) {
+  const size_t layer = b200moe_ep_workspace_bytes(c, H);
+  if (layer == 0) return 0;
+  return align256(layer) + static_cast<size_t>(c->peers.cap) * c->peers.D * 4;
+}
+
+int b200moe_layernorm(const void* in, const float* gamma, const float* beta, float eps, int S, int D, int dtype,
+                      void* out, cudaStream_t stream) {
+  if (S < 0 || !dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "layernorm: bad S=%d / dtype=%d", S, dtype);
+  if (!layernorm_supported(D)) return fail(B200MOE_ERR_ARG, "layernorm: D=%d is not supported (multiple of 8, at most 1024)", D);
+  if (S > 0 && (!in || !out || !gamma || !beta)) return fail(B200MOE_ERR_ARG, "layernorm: null pointer");
+  cudaError_t e = launch_layernorm(in, gamma, beta, eps, S, D, dtype, out, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "layernorm");
+  return B200MOE_OK;
+}
+
+int b200moe_block_forward(const b200moe_block_args* b, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!b) return fail(B200MOE_ERR_ARG, "block_forward: null args");
+  const b200moe_layer_args& a = b->layer;
+  if (a.B < 0 || a.T < 0 || a.E < 1 || a.D < 1 || a.H < 0 || a.top_k < 1)
+    return fail(B200MOE_ERR_ARG, "block_forward: bad shape");
+  const int S = a.B * a.T;
+  BlockPlan plan;
+  const size_t layer_ws = b200moe_workspace_bytes(S, a.E, a.D, a.H, a.top_k);
+  int rc = plan_block(b, layer_ws, ws, ws_bytes, &plan, "block_forward");
+  if (rc != B200MOE_OK) return rc;
+  if (plan.xn) {
+    if (!a.x) return fail(B200MOE_ERR_ARG, "block_forward: null pointer");
+    StageScope t(0, stream);
+    cudaError_t e = launch_layernorm(a.x, b->norm_ff_gamma, b->norm_ff_beta, b->eps, S, a.D, a.dtype, plan.xn, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "block_forward/norm_ff");
+  }
+  rc = b200moe_forward(&plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, stream);
+  if (rc != B200MOE_OK) return rc;
+  if (b->norm_final_gamma && S > 0) {
+    StageScope t(3, stream);
+    cudaError_t e = launch_layernorm(a.out, b->norm_final_gamma, b->norm_final_beta, b->eps, S, a.D, a.dtype, a.out,
+                                     stream);
+    if (e != cudaSuccess) return cuda_fail(e, "block_forward/norm_final");
+  }
+  return B200MOE_OK;
+}
+
+int b200moe_ep_block_forward(b200moe_ep_ctx* c, const b200moe_block_args* b, void* ws, size_t ws_bytes,
+                             cudaStream_t stream) {
+  if (!c || !b) return fail(B200MOE_ERR_ARG, "ep_block_forward: null argument");
+  const b200moe_layer_args& a = b->layer;
+  if (a.B < 0 || a.T < 0) return fail(B200MOE_ERR_ARG, "ep_block_forward: bad B/T");
+  const int S = a.B * a.T;
+  BlockPlan plan;
+  const size_t layer_ws = b200moe_ep_workspace_bytes(c, a.H);
+  int rc = plan_block(b, layer_ws, ws, ws_bytes, &plan, "ep_block_forward");
+  if (rc != B200MOE_OK) return rc;
+  if (plan.xn) {
+    if (!a.x) return fail(B200MOE_ERR_ARG, "ep_block_forward: null pointer");
+    cudaError_t e = launch_layernorm(a.x, b->norm_ff_gamma, b->norm_ff_beta, b->eps, S, a.D, a.dtype, plan.xn, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ep_block_forward/norm_ff");
+  }
+  rc = b200moe_ep_forward_stages(c, &plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, 7, stream);
+  if (rc != B200MOE_OK) return rc;
+  if (b->norm_final_gamma && S > 0) {
+    cudaError_t e = launch_layernorm(a.out, b->norm_final_gamma, b->norm_final_beta, b->eps, S, a.D, a.dtype, a.out,
+                                     stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ep_block_forward/norm_final");
+  }
   return B200MOE_OK;
 }
 

@@ -209,6 +209,12 @@ cudaError_t launch_ep_wait_build(const EpPeers& ep, int bn, GroupRec* groups, in
 cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float* score, const void* residual,
                               float ff_scale, int S, int D, int top_k, void* out, cudaStream_t stream);
 
+// layernorm.cu
+// out[s, :] = LayerNorm(in[s, :]) * gamma + beta over D features (biased variance, eps inside the root); in == out allowed.
+bool layernorm_supported(int D);
+cudaError_t launch_layernorm(const void* in, const float* gamma, const float* beta, float eps, int S, int D, int dtype,
+                             void* out, cudaStream_t stream);
+
 // combine.cu
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
                            float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream);
@@ -219,15 +225,15 @@ void count_launch(int n = 1);
 
 // Tunables read once from the environment (api.cu):
 //   B200MOE_PDL=m       bit mask of the kernels launched with programmatic dependent launch (1 gate / route, 2 dispatch,
-//                       4 expert FFN; default 5); 0 = ordinary stream ordering.  B200MOE_PDL_TRIG=m: which of them
+//                       4 expert FFN, 8 LayerNorm; default 13); 0 = ordinary stream ordering.  B200MOE_PDL_TRIG=m: which of them
 //                       release their dependents at their start instead of at exit (default 4)
 //   B200MOE_PREFETCH=0  no L2 prefetch of the layer's expert weights from the gate kernel; 1 (default) = issued before
 //                       the gate waits for the previous kernel; 2 = issued after that wait
-int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN: kernel launched with the PDL attribute
+int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN, bit 3 LayerNorm: kernel launched with the PDL attribute
 int pdl_trigger();   // same bits: kernel executes griddepcontrol.launch_dependents at its start
 int prefetch_mode();
 int route_mode();   // B200MOE_ROUTE: 1 (default) = fused gate + dispatch kernel for small batches, 0 = separate kernels
-constexpr int kPdlGate = 1, kPdlDispatch = 2, kPdlFfn = 4;
+constexpr int kPdlGate = 1, kPdlDispatch = 2, kPdlFfn = 4, kPdlLn = 8;
 
 // Kernel launch with the programmatic-stream-serialization attribute: the kernel may become resident as soon as every
 // CTA of the previous kernel in the stream has executed griddepcontrol.launch_dependents (or exited); everything it reads

@@ -99,11 +99,13 @@ class EpContext:
             self._owned_local = None
 
     # ---- per layer ------------------------------------------------------------------------------------------------------
-    def workspace(self, hidden: int) -> torch.Tensor:
-        key = (hidden, ops._stream())
+    def workspace(self, hidden: int, block: bool = False) -> torch.Tensor:
+        key = (hidden, ops._stream(), block)
         ws = self._ws.get(key)
         if ws is None:
-            n = int(_lib.load().b200moe_ep_workspace_bytes(self._ctx, hidden))
+            lib = _lib.load()
+            n = int(lib.b200moe_ep_block_workspace_bytes(self._ctx, hidden) if block
+                    else lib.b200moe_ep_workspace_bytes(self._ctx, hidden))
             ws = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
@@ -119,10 +121,15 @@ class EpContext:
                 gate_mode: int = ops.GATE_3M, act_type: int = ops.ACT_SILU, ff_scale: float = 1.0,
                 keep_expert_output: bool = False, out: Optional[torch.Tensor] = None,
                 Wr_packed: Optional[torch.Tensor] = None, return_routing: bool = False, stages: int = 7,
-                routing_bufs=None):
-        """x [S, D] bf16: this rank's tokens.  experts: this rank's `num_local_expert` experts.  Wr [R, E_total]."""
+                routing_bufs=None, norm_ff=None, norm_final=None, eps: float = 1e-12):
+        """x [S, D] bf16: this rank's tokens.  experts: this rank's `num_local_expert` experts.  Wr [R, E_total].
+        norm_ff / norm_final = (gamma, beta) fp32 [D]: the block's LayerNorms either side of the layer (ops.moe_layer)."""
+        block = norm_ff is not None or norm_final is not None
+        norms = [t for pair in (norm_ff, norm_final) if pair is not None for t in pair]
+        if block and stages != 7:
+            raise ValueError("the block call runs all stages at once")
         dev = ops._need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out,
-                             Wr_packed)
+                             Wr_packed, *norms)
         if x.dtype != torch.bfloat16:
             raise TypeError("the expert-parallel path takes bf16 activations")
         S, D = x.shape
@@ -144,7 +151,7 @@ class EpContext:
                 score = torch.empty(S, top_k, dtype=torch.float32, device=dev)
                 counts = torch.empty(E_total, dtype=torch.int32, device=dev)
                 mapping = torch.empty(S * top_k, dtype=torch.int32, device=dev)
-        ws = self.workspace(H)
+        ws = self.workspace(H, block)
         p = ops._ptr
         a = _lib.LayerArgs(
             x=p(x), embed=p(embed), residual=p(residual), out=p(out), x_len=p(x_len), Wr=p(Wr), Wr_packed=p(Wr_packed),
@@ -152,8 +159,16 @@ class EpContext:
             E=E_total, H=H, top_k=top_k, gate_mode=gate_mode, act_type=act_type, dtype=ops.dtype_code(x),
             keep_expert_output=int(keep_expert_output), ff_scale=float(ff_scale), idx_out=p(idx), score_out=p(score),
             counts_out=p(counts), mapping_out=p(mapping))
-        _lib.check(_lib.load().b200moe_ep_forward_stages(self._ctx, C.byref(a), p(ws), ws.numel(), stages,
-                                                         ops._stream()), "b200moe_ep_forward")
+        if block:
+            b = _lib.BlockArgs(layer=a, norm_ff_gamma=p(norm_ff[0]) if norm_ff else None,
+                               norm_ff_beta=p(norm_ff[1]) if norm_ff else None,
+                               norm_final_gamma=p(norm_final[0]) if norm_final else None,
+                               norm_final_beta=p(norm_final[1]) if norm_final else None, eps=float(eps))
+            _lib.check(_lib.load().b200moe_ep_block_forward(self._ctx, C.byref(b), p(ws), ws.numel(), ops._stream()),
+                       "b200moe_ep_block_forward")
+        else:
+            _lib.check(_lib.load().b200moe_ep_forward_stages(self._ctx, C.byref(a), p(ws), ws.numel(), stages,
+                                                             ops._stream()), "b200moe_ep_forward")
         if return_routing:
             return out, idx, score, counts, mapping
         return out

@@ -97,12 +97,26 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
         return self._wrp
 
     def forward(self, inputs: torch.Tensor, embed: Optional[torch.Tensor], mask: Optional[torch.Tensor] = None, *,
-                residual: Optional[torch.Tensor] = None, ff_scale: float = 1.0, return_routing: bool = False):
+                residual: Optional[torch.Tensor] = None, ff_scale: float = 1.0, return_routing: bool = False,
+                norm_ff: Optional[torch.nn.LayerNorm] = None, norm_final: Optional[torch.nn.LayerNorm] = None):
         """inputs [B, T, idim]; embed [B, T, embed_dim]; mask [B] int32 valid lengths (the plugin's `mask` input,
         softmax_topk_plugin.cpp:88-127).  Returns the gate-weighted expert output [B, T, idim]; with `residual` /
-        `ff_scale` the Conformer block's  residual + ff_scale * out  is fused in as well."""
+        `ff_scale` the Conformer block's  residual + ff_scale * out  is fused in as well, and with `norm_ff` /
+        `norm_final` (the block's nn.LayerNorm modules, fmoe_transformer.py:54-65) the LayerNorms either side of it:
+        norm_final(residual + ff_scale * MoE(norm_ff(inputs), embed))  -- see `feed_forward_block`."""
         assert inputs.dim() == 3
         B, T, D = inputs.shape
+        norms = {}
+        for name, ln in (("norm_ff", norm_ff), ("norm_final", norm_final)):
+            if ln is not None:
+                if tuple(ln.normalized_shape) != (D,) or ln.weight is None or ln.bias is None:
+                    raise ValueError(f"{name} must be an affine LayerNorm over the {D} features")
+                norms[name] = (ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous())
+        if norms:
+            eps = {float(ln.eps) for ln in (norm_ff, norm_final) if ln is not None}
+            if len(eps) != 1:
+                raise ValueError("norm_ff and norm_final must share eps (the reference uses 1e-12 for both)")
+            norms["eps"] = eps.pop()
         x = inputs.contiguous()
         e = None if embed is None else embed.contiguous()
         Wr, br = self._router()
@@ -116,9 +130,11 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
             out = ctx.forward(x.view(B * T, D), None if e is None else e.view(B * T, -1), Wr, br, packed,
                               residual=None if residual is None else residual.contiguous().view(B * T, D), x_len=x_len,
                               seq_len=T, top_k=1, gate_mode=ops.GATE_3M, act_type=act, ff_scale=ff_scale,
-                              keep_expert_output=self.keep_expert_output, Wr_packed=self._router_packed(Wr))
+                              keep_expert_output=self.keep_expert_output, Wr_packed=self._router_packed(Wr), **norms)
             return out.view(B, T, D)
         if self.world_size > 1:
+            if norms:
+                raise NotImplementedError("LayerNorm fusion under expert parallelism needs bf16 activations")
             from . import ep   # fp32 / fp16 activations: the NCCL all-to-all formulation
             out = ep.ep_moe_layer(x.view(B * T, D), None if e is None else e.view(B * T, -1), Wr, br, packed,
                                   num_local_expert=self.num_experts, group=self.comm, top_k=1,
@@ -129,5 +145,26 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
         res = ops.moe_layer(x, e, Wr, br, packed, residual=None if residual is None else residual.contiguous(),
                             x_len=x_len, top_k=1, gate_mode=ops.GATE_3M, act_type=act, ff_scale=ff_scale,
                             keep_expert_output=self.keep_expert_output, return_routing=return_routing,
-                            Wr_packed=self._router_packed(Wr))
+                            Wr_packed=self._router_packed(Wr), **norms)
         return res if return_routing else res.out
+
+
+def feed_forward_block(block: torch.nn.Module, x: torch.Tensor, embed: Optional[torch.Tensor],
+                       mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The feed-forward part of FmoeConformerLayer.forward (trainer_3m_fix/layer/fmoe_transformer.py:144-166) as ONE
+    call, for any module `block` that carries the reference's members: `feed_forward` (a LocalFmoeCatEmbedFeedForward),
+    `norm_ff`, `ff_scale`, `normalize_before`, and -- for blocks with a convolution module -- `norm_final`:
+
+        residual = x;  x = norm_ff(x);  x = feed_forward(x, embed, x_len);  x = residual + ff_scale * x;  x = norm_final(x)
+
+    Post-norm blocks (normalize_before = False, :160-162) apply norm_ff behind the residual add instead; then norm_ff
+    takes the place of the output norm and, if the block also has norm_final, that one runs as a second LayerNorm."""
+    ff = block.feed_forward
+    if getattr(block, "normalize_before", True):
+        final = block.norm_final if getattr(block, "conv_module", None) is not None else None
+        return ff(x, embed, mask, residual=x, ff_scale=block.ff_scale, norm_ff=block.norm_ff, norm_final=final)
+    y = ff(x, embed, mask, residual=x, ff_scale=block.ff_scale, norm_final=block.norm_ff)
+    if getattr(block, "conv_module", None) is not None:
+        ln = block.norm_final
+        y = ops.layernorm(y, ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous(), ln.eps)
+    return y

@@ -82,12 +82,14 @@ def workspace_bytes(S: int, E: int, D: int, H: int, top_k: int) -> int:
     return int(_lib.load().b200moe_workspace_bytes(S, E, D, H, top_k))
 
 
-def get_workspace(device, S: int, E: int, D: int, H: int, top_k: int) -> torch.Tensor:
-    """One cached scratch buffer per (device, stream, shape). Sized by the library, owned by torch's allocator."""
-    key = (str(device), _stream(), S, E, D, H, top_k)
+def get_workspace(device, S: int, E: int, D: int, H: int, top_k: int, block: bool = False) -> torch.Tensor:
+    """One cached scratch buffer per (device, stream, shape). Sized by the library, owned by torch's allocator.
+    block=True: sized for b200moe_block_forward (the layer's workspace + the normalised input)."""
+    key = (str(device), _stream(), S, E, D, H, top_k, block)
     ws = _WS.get(key)
     if ws is None:
-        n = workspace_bytes(S, E, D, H, top_k)
+        n = (int(_lib.load().b200moe_block_workspace_bytes(S, E, D, H, top_k)) if block
+             else workspace_bytes(S, E, D, H, top_k))
         ws = torch.empty(max(n, 1), dtype=torch.uint8, device=device)
         _WS[key] = ws
     return ws
@@ -277,11 +279,20 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
               seq_len: Optional[int] = None, top_k: int = 1, gate_mode: int = GATE_3M, act_type: int = ACT_SILU,
               ff_scale: float = 1.0, keep_expert_output: bool = False, out: Optional[torch.Tensor] = None,
               return_routing: bool = False, ws: Optional[torch.Tensor] = None,
-              Wr_packed: Optional[torch.Tensor] = None, compute: int = COMPUTE_BF16) -> LayerOut:
+              Wr_packed: Optional[torch.Tensor] = None, compute: int = COMPUTE_BF16,
+              norm_ff: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              norm_final: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-12) -> LayerOut:
     """The fused layer: out = (residual) + ff_scale * sum_k score_k * FFN_{e_k}(x).  x [S, D] or [B, T, D].
-    compute=COMPUTE_TF32: fp32 activations, `experts` from fp32_experts() (tensor cores in TF32, fp32 intermediates)."""
+    compute=COMPUTE_TF32: fp32 activations, `experts` from fp32_experts() (tensor cores in TF32, fp32 intermediates).
+    norm_ff / norm_final = (gamma, beta) fp32 [D]: the Conformer block's LayerNorms either side of the layer
+    (fmoe_transformer.py:144-166):  out = norm_final(residual + ff_scale * MoE(norm_ff(x), embed))."""
+    block = norm_ff is not None or norm_final is not None
+    norms = [t for pair in (norm_ff, norm_final) if pair is not None for t in pair]
+    for t in norms:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError("LayerNorm gamma / beta must be contiguous fp32 tensors")
     dev = _need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out,
-                     Wr_packed)
+                     Wr_packed, *norms)
     shape = x.shape
     if x.dim() == 3:
         B, T, D = x.shape
@@ -295,7 +306,7 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
     if out is None:
         out = torch.empty(shape, dtype=x.dtype, device=dev)
     if ws is None:
-        ws = get_workspace(dev, S, E, D, H, top_k)
+        ws = get_workspace(dev, S, E, D, H, top_k, block)
     idx = score = counts = mapping = None
     if return_routing:
         idx = torch.empty(S, top_k, dtype=torch.int32, device=dev)
@@ -315,8 +326,31 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
         raise TypeError("bf16 compute takes bf16-packed expert weights (ops.pack_experts)")
     lib = _lib.load()
     import ctypes
-    _lib.check(lib.b200moe_forward(ctypes.byref(a), _ptr(ws), ws.numel(), _stream()), "b200moe_forward")
+    if block:
+        b = _lib.BlockArgs(layer=a, norm_ff_gamma=_ptr(norm_ff[0]) if norm_ff else None,
+                           norm_ff_beta=_ptr(norm_ff[1]) if norm_ff else None,
+                           norm_final_gamma=_ptr(norm_final[0]) if norm_final else None,
+                           norm_final_beta=_ptr(norm_final[1]) if norm_final else None, eps=float(eps))
+        _lib.check(lib.b200moe_block_forward(ctypes.byref(b), _ptr(ws), ws.numel(), _stream()),
+                   "b200moe_block_forward")
+    else:
+        _lib.check(lib.b200moe_forward(ctypes.byref(a), _ptr(ws), ws.numel(), _stream()), "b200moe_forward")
     return LayerOut(out, idx, score, counts, mapping)
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-12,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row LayerNorm over the last dimension (LayerNormPluginDynamic's job, in the activation dtype); out may be x."""
+    dev = _need_cuda(x, gamma, beta, out)
+    D = x.shape[-1]
+    S = x.numel() // D if D else 0
+    if not x.is_contiguous() or gamma.dtype != torch.float32 or beta.dtype != torch.float32:
+        raise TypeError("layernorm takes a contiguous input and fp32 gamma / beta")
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.load().b200moe_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), S, D, dtype_code(x),
+                                             _ptr(out), _stream()), "b200moe_layernorm")
+    return out
 
 
 # ---- torch.library registration ---------------------------------------------------------------------------------------------

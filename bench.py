@@ -53,6 +53,9 @@ def parse():
                     help="bf16 (default, the headline) or tf32: fp32 activations + fp32 weights, <= 1e-3 parity bar")
     ap.add_argument("--ep", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: peer-memory kernels (product) or NCCL all-to-all (comparison)")
+    ap.add_argument("--block", action="store_true",
+                    help="time the Conformer block's feed-forward part instead of the bare layer: norm_ff in front, "
+                         "norm_final behind (SURVEY 8 f1); not the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -175,7 +178,9 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, wl, S_total):
-    return {"workload": f"{args.workload}: {wl['desc']}", "layers": wl["layers"], "tokens_per_layer": S_total,
+    return {"workload": f"{args.workload}: {wl['desc']}" + (" + norm_ff / norm_final around every layer" if args.block
+                                                            else ""),
+            "layers": wl["layers"], "tokens_per_layer": S_total,
             "utterances": wl["utts"] * max(args.gpus, 1), "experts": E, "idim": D, "hidden_units": H, "embed_dim": DEMB,
             "top_k": 1, "gate": "3m softmax->max", "activation": "silu", "ff_scale": 0.5,
             "cache": "inputs larger than L2 (18 x 64 MiB weight sets cycle through a 126 MB L2)",
@@ -231,7 +236,13 @@ def main():
         b2 = torch.zeros(E_local, D, device=dev)
         Wr = xavier((DEMB + D, E), DEMB + D, E, gen_shared).bfloat16().float()
         experts = ops.fp32_experts(W1, b1, W2, b2) if tf32 else ops.PackedExperts(W1, b1, W2, b2)
-        layers.append((Wr, experts, ops.pack_router(Wr)))
+        norms = {}
+        if args.block:
+            norms = {"norm_ff": (1.0 + 0.1 * torch.randn(D, generator=gen_shared, device=dev),
+                                 0.1 * torch.randn(D, generator=gen_shared, device=dev)),
+                     "norm_final": (1.0 + 0.1 * torch.randn(D, generator=gen_shared, device=dev),
+                                    0.1 * torch.randn(D, generator=gen_shared, device=dev))}
+        layers.append((Wr, experts, ops.pack_router(Wr), norms))
 
     # ---- synthetic activations: pinned host copies (for e2e) and device-resident copies (for value)
     g = torch.Generator().manual_seed(20260003 + rank)
@@ -251,11 +262,11 @@ def main():
 
     def step(x_in, e_in):
         cur = x_in
-        for li, (Wr, experts, Wrp) in enumerate(layers):
+        for li, (Wr, experts, Wrp, norms) in enumerate(layers):
             out = bufs[li & 1]
             if ep_ctx is not None:
                 ep_ctx.forward(cur, e_in, Wr, None, experts, residual=cur, top_k=1, gate_mode=ops.GATE_3M,
-                               act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=Wrp)
+                               act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=Wrp, **norms)
             elif world > 1:
                 ep.ep_moe_layer(cur, e_in, Wr, None, experts, num_local_expert=E_local, group=None, top_k=1,
                                 gate_mode=ops.GATE_3M, act_type=ops.ACT_SILU, ff_scale=0.5, residual=cur, out=out,
@@ -263,7 +274,7 @@ def main():
             else:
                 ops.moe_layer(cur, e_in, Wr, None, experts, residual=cur, top_k=1, gate_mode=ops.GATE_3M,
                               act_type=ops.ACT_SILU, ff_scale=0.5, out=out, Wr_packed=None if tf32 else Wrp,
-                              compute=ops.COMPUTE_TF32 if tf32 else ops.COMPUTE_BF16)
+                              compute=ops.COMPUTE_TF32 if tf32 else ops.COMPUTE_BF16, **norms)
             cur = out
         return cur
 
@@ -440,7 +451,7 @@ def main():
         torch.set_num_threads(cores)
         n_sets = min(L, 2)
         cpu_layers = [dict(Wr=Wr.cpu(), W1=ex.W1.float().cpu(), b1=ex.b1.cpu(), W2=ex.W2.float().cpu(), b2=ex.b2.cpu())
-                      for (Wr, ex, _) in layers[:n_sets]]
+                      for (Wr, ex, _, _n) in layers[:n_sets]]
         seq = [cpu_layers[i % n_sets] for i in range(L)]
         xc, ec = x_host.float(), e_host.float()
         with torch.no_grad():

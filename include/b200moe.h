@@ -242,8 +242,40 @@ int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate
 int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int T, int E, int data_type,
                                  void* value, int* idx, cudaStream_t stream);
 
+/* ---- the Conformer block's feed-forward part: LayerNorms either side of the layer --------
+ * Replaces, in trainer_3m_fix/layer/fmoe_transformer.py:144-166 (FmoeConformerLayer.forward, normalize_before = True):
+ *   :145-148  residual = x;  x = addLayerNorm(norm_ff, x)            -> norm_ff_gamma / norm_ff_beta
+ *   :152      x = feed_forward(x, embed, x_len)                       -> the layer (b200moe_forward)
+ *   :155-158  x = residual + ff_scale * x                             -> layer.residual / layer.ff_scale
+ *   :164-166  x = addLayerNorm(norm_final, x)   (blocks with a conv module) -> norm_final_gamma / norm_final_beta
+ * i.e.  out = norm_final( residual + ff_scale * MoE( norm_ff(x), embed ) ).
+ * `layer.x` is the block input BEFORE norm_ff (normally also `layer.residual`); gamma / beta are fp32 [D]; a NULL gamma
+ * skips that norm; eps is shared (the reference uses nn.LayerNorm(size, eps=1e-12) for both, :54-65).  LayerNorm
+ * semantics: biased variance over the D features, y = (x - mean) * rsqrt(var + eps) * gamma + beta, statistics in fp32,
+ * the normalised input rounded to `dtype` (what the reference's LayerNorm plugin hands to the next graph layer).
+ * D: multiple of 8, at most 1024.  ws: b200moe_block_workspace_bytes (the layer's workspace + one [S, D] buffer). */
+typedef struct b200moe_block_args {
+  b200moe_layer_args layer;
+  const float* norm_ff_gamma;
+  const float* norm_ff_beta;
+  const float* norm_final_gamma;
+  const float* norm_final_beta;
+  float eps;
+} b200moe_block_args;
+
+size_t b200moe_block_workspace_bytes(int S, int E, int D, int H, int top_k);
+int b200moe_block_forward(const b200moe_block_args* args, void* ws, size_t ws_bytes, cudaStream_t stream);
+/* The same block with the experts partitioned over the GPUs of `ctx` (see above). */
+size_t b200moe_ep_block_workspace_bytes(const b200moe_ep_ctx* ctx, int H);
+int b200moe_ep_block_forward(b200moe_ep_ctx* ctx, const b200moe_block_args* args, void* ws, size_t ws_bytes,
+                             cudaStream_t stream);
+/* The LayerNorm alone (LayerNormPluginDynamic, TRTAPI++/plugin/layer_norm_plugin/layer_norm_kernel.cu, with the eps the
+ * plugin drops): out [S, D] = LN(in [S, D]); in == out allowed. */
+int b200moe_layernorm(const void* in, const float* gamma, const float* beta, float eps, int S, int D, int dtype,
+                      void* out, cudaStream_t stream);
+
 /* Run-time tunables (each also has an environment default, B200MOE_<KEY>): "route" 1/0 fused gate + dispatch kernel for
- * small batches; "pdl" / "pdl_trig" bit masks (1 gate, 2 dispatch, 4 expert FFN) for programmatic dependent launch;
+ * small batches; "pdl" / "pdl_trig" bit masks (1 gate, 2 dispatch, 4 expert FFN, 8 LayerNorm) for programmatic dependent launch;
  * "prefetch" 0/1/2 L2 prefetch of the expert weights from the gate kernel.  Results do not depend on any of them. */
 int b200moe_config(const char* key, int value);
 

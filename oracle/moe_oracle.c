@@ -145,6 +145,22 @@ void oracle_combine(const float* ybuf, const int32_t* mapping, const float* scor
   }
 }
 
+/* nn.LayerNorm(D, eps) over every row (trainer_3m_fix/layer/fmoe_transformer.py:54-65; the TensorRT build uses
+ * TRTAPI++/plugin/layer_norm_plugin/layer_norm_kernel.cu): biased variance, eps inside the root. in == out allowed. */
+void oracle_layer_norm(const float* in, const float* gamma, const float* beta, float eps, int S, int D, float* out) {
+  for (int s = 0; s < S; ++s) {
+    const float* x = in + (size_t)s * D;
+    float* y = out + (size_t)s * D;
+    double mean = 0.0, var = 0.0;
+    for (int d = 0; d < D; ++d) mean += x[d];
+    mean /= D;
+    for (int d = 0; d < D; ++d) var += (x[d] - mean) * (x[d] - mean);
+    var /= D;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    for (int d = 0; d < D; ++d) y[d] = (float)((x[d] - mean) * rstd * gamma[d] + beta[d]);
+  }
+}
+
 /* The whole 3M layer (top-1): gate -> prepare -> scatter -> FFN -> combine. Scratch is allocated here. */
 void oracle_moe_forward_3m(const float* x, const float* embed, const float* Wr, const float* br, const float* W1,
                            const float* b1, const float* W2, const float* b2, const float* residual, float ff_scale,
@@ -163,4 +179,23 @@ void oracle_moe_forward_3m(const float* x, const float* embed, const float* Wr, 
   free(pos);
   free(xbuf);
   free(ybuf);
+}
+
+/* The feed-forward part of a Conformer block (layer/fmoe_transformer.py:144-166):
+ * out = norm_final(x + ff_scale * MoE(norm_ff(x), embed)); a NULL gamma skips that norm. */
+void oracle_moe_block_forward_3m(const float* x, const float* embed, const float* Wr, const float* br, const float* W1,
+                                 const float* b1, const float* W2, const float* b2, const float* ff_gamma,
+                                 const float* ff_beta, const float* final_gamma, const float* final_beta, float eps,
+                                 float ff_scale, int S, int D, int Demb, int E, int H, int act, int32_t* idx,
+                                 float* value, int32_t* counts, int32_t* mapping, float* out) {
+  float* xn = (float*)malloc(sizeof(float) * (size_t)(S > 0 ? S : 1) * D);
+  float* moe = (float*)malloc(sizeof(float) * (size_t)(S > 0 ? S : 1) * D);
+  if (ff_gamma) oracle_layer_norm(x, ff_gamma, ff_beta, eps, S, D, xn);
+  else memcpy(xn, x, sizeof(float) * (size_t)S * D);
+  oracle_moe_forward_3m(xn, embed, Wr, br, W1, b1, W2, b2, NULL, 1.0f, S, D, Demb, E, H, act, idx, value, counts,
+                        mapping, moe);
+  for (size_t i = 0; i < (size_t)S * D; ++i) out[i] = x[i] + ff_scale * moe[i];
+  if (final_gamma) oracle_layer_norm(out, final_gamma, final_beta, eps, S, D, out);
+  free(xn);
+  free(moe);
 }

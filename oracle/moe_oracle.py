@@ -17,6 +17,11 @@ path.  Citations are relative to the upstream tree (/root/reference):
                  fmoe/transformer.py:22-30; activation trainer_3m_fix/utils/common.py:24-28
   combine        positionwise_feed_forward.py:257-258 (x gate_value), fmoe/layers.py:199-206 (top-k bmm),
                  layer/fmoe_transformer.py:155-158 and layer/fmoeExMarc_transformer.py:150-154 (x ff_scale + residual)
+  layer_norm     nn.LayerNorm(size, eps=1e-12) of trainer_3m_fix/layer/fmoe_transformer.py:54-65 (norm_ff, norm_final);
+                 the TensorRT build swaps in TRTAPI++/plugin/layer_norm_plugin/layer_norm_kernel.cu, same formula in
+                 fp32 with eps dropped -- indistinguishable at eps = 1e-12
+  moe_block_forward  layer/fmoe_transformer.py:144-166: residual = x; x = norm_ff(x); x = feed_forward(x, embed);
+                 x = residual + ff_scale * x; x = norm_final(x)
 
 Pinning.  The reference ships no tests, golden vectors or fixtures for this path, and its arithmetic lives in the
 un-vendored, un-pinned third-party extension `fmoe_cuda` (laekov/fastmoe, Tencent-modified; call sites
@@ -161,6 +166,31 @@ def moe_forward(x, embed, Wr, br, W1, b1, W2, b2, *, top_k=1, gate_mode=GATE_3M,
         out = residual.float() + out
     return {"idx": idx, "score": score, "logits": logits, "counts": prep["counts"], "offsets": prep["offsets"],
             "pos": pos, "mapping": prep["mapping"].view(S, top_k), "xbuf": xbuf, "ybuf": ybuf, "moe": moe, "out": out}
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """torch.nn.LayerNorm over the last dimension, written out: biased variance, eps inside the root, fp32."""
+    x = x.float()
+    mean = x.mean(-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(-1, keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps) * gamma.float() + beta.float()
+
+
+def moe_block_forward(x, embed, Wr, br, W1, b1, W2, b2, *, norm_ff=None, norm_final=None, eps=1e-12, ff_scale=0.5,
+                      round_norm_to=None, **layer_kw) -> Dict[str, torch.Tensor]:
+    """The feed-forward part of one Conformer block (fmoe_transformer.py:144-166):
+    out = norm_final(x + ff_scale * MoE(norm_ff(x), embed)).  norm_* = (gamma, beta) or None.
+    round_norm_to: dtype the normalised input is rounded to before it enters the layer -- the reference hands the
+    LayerNorm plugin's output to the next graph layer in the engine's activation dtype."""
+    xn = x.float() if norm_ff is None else layer_norm(x, norm_ff[0], norm_ff[1], eps)
+    if round_norm_to is not None:
+        xn = xn.to(round_norm_to).float()
+    r = moe_forward(xn, embed, Wr, br, W1, b1, W2, b2, residual=x.float(), ff_scale=ff_scale, **layer_kw)
+    r["xn"] = xn
+    r["pre_norm_out"] = r["out"]
+    if norm_final is not None:
+        r["out"] = layer_norm(r["out"], norm_final[0], norm_final[1], eps)
+    return r
 
 
 def _expert_ffn_bf16(xbuf, counts, W1, b1, W2, b2, act_type):

@@ -10,6 +10,7 @@ What is executed from the reference tree (unmodified, imported from /root/refere
   model.dfsmn_base_fmoe_localComm_catEmbed.cFSMN_layer.gate                      :166-192 (the live 3M router)
   fmoe.layers.FMoELinear (parameter shapes + init)                               fmoe/layers.py:21-40
   utils.common.Swish                                                             utils/common.py:24-28
+  layer.fmoe_transformer.FmoeConformerLayer (constructor: norm_ff, norm_final, ff_scale)  layer/fmoe_transformer.py:33-70
 
 What is NOT in the reference tree: `fmoe_cuda`, the CUDA extension of laekov/fastmoe (Tencent-modified, un-vendored,
 un-pinned).  Its four primitives on this path are stubbed below with their published semantics
@@ -150,6 +151,43 @@ def main():
         W2_bf16=bits(w.W2), b2_bf16=bits(w.b2), gate_idx=idx.view(S, K).numpy().astype(np.int64), gate_score=score.view(S, K).numpy(),
         expert_count=local_cnt.numpy().astype(np.int64), y_entries=y_entries.numpy(), out=out.numpy())
     print("case_naive_top2: counts", local_cnt.tolist())
+
+    # ---------------- case C: the Conformer block's feed-forward part: norm_ff -> 3M MoE -> x ff_scale + residual -> norm_final
+    # The LayerNorms and ff_scale come from the reference's own FmoeConformerLayer constructor; its forward emits
+    # TensorRT graph layers, so the wiring (fmoe_transformer.py:144-166) is restated with the module's members.
+    fmoe_tr = importlib.import_module("layer.fmoe_transformer")
+    E, D, Demb, H, S = 4, 128, 128, 128, 41
+    w = synth.make_weights(1003, E, D, H, Demb, random_bias=True)
+    x, embed = synth.make_activations(2003, S, D, Demb, w, top_k=1)
+    x = (x * 3.0 + 0.25).bfloat16().float()   # rows that are not already zero-mean / unit-variance
+    block = fmoe_tr.FmoeConformerLayer(D, self_attn=None, feed_forward=None, feed_forward_macaron=torch.nn.Identity(),
+                                       conv_module=torch.nn.Identity())
+    assert block.ff_scale == 0.5 and block.norm_ff.eps == 1e-12 and block.norm_final.eps == 1e-12
+    g = torch.Generator().manual_seed(3003)
+    with torch.no_grad():
+        for ln in (block.norm_ff, block.norm_final):
+            ln.weight.copy_((1.0 + 0.2 * torch.randn(D, generator=g)).bfloat16().float())
+            ln.bias.copy_((0.1 * torch.randn(D, generator=g)).bfloat16().float())
+        layer = dfsmn.cFSMN_layer(D, Demb, hid_dim=H, mem_dim=D, num_experts=E, rank=0, world_size=1,
+                                  capacity_factor=-1, skip_connect=True, rand_init_router=True)
+        layer.rooter_weights.copy_(w.Wr)
+        residual = x
+        xn = block.norm_ff(x)                                                 # :145-148
+        gate_idx, gate_value, _aux, _n = layer.gate(torch.cat([embed, xn], dim=-1))
+        expert_fn = expert_fn_factory(w.W1, w.b1, w.W2, w.b2, swish)
+        y = dfsmn._fmoe_general_global_forward(xn, gate_idx, expert_fn, E, 1, capacity=-1) * gate_value.unsqueeze(1)
+        pre = residual + block.ff_scale * y                                   # :155-158
+        out = block.norm_final(pre)                                           # :164-166
+        _pos, local_cnt, _g, _f, _bs = F.moe_prepare_forward(gate_idx, E, 1)
+    np.savez_compressed(
+        os.path.join(HERE, "case_block_3m.npz"),
+        x_bf16=bits(x), embed_bf16=bits(embed), Wr_bf16=bits(w.Wr), W1_bf16=bits(w.W1), b1_bf16=bits(w.b1),
+        W2_bf16=bits(w.W2), b2_bf16=bits(w.b2), ff_gamma_bf16=bits(block.norm_ff.weight.detach()),
+        ff_beta_bf16=bits(block.norm_ff.bias.detach()), final_gamma_bf16=bits(block.norm_final.weight.detach()),
+        final_beta_bf16=bits(block.norm_final.bias.detach()), xn=xn.numpy(), gate_idx=gate_idx.numpy().astype(np.int64),
+        gate_value=gate_value.numpy(), expert_count=local_cnt.numpy().astype(np.int64), pre_norm=pre.numpy(),
+        out=out.numpy(), ff_scale=np.float32(block.ff_scale), eps=np.float64(block.norm_ff.eps))
+    print("case_block_3m: counts", local_cnt.tolist())
 
 
 if __name__ == "__main__":

@@ -65,3 +65,24 @@ def test_c_naive_gate_and_prepare(clib, oracle, synth):
     assert nv == p["pos"].numel()
     assert np.array_equal(counts, p["counts"].numpy()) and np.array_equal(offsets, p["offsets"].numpy())
     assert np.array_equal(mapping, p["mapping"].numpy()) and np.array_equal(pos[:nv], p["pos"].numpy())
+
+
+def test_c_block_matches_golden(clib):
+    g = load_golden("case_block_3m.npz")
+    S, D = g["x"].shape
+    Demb, E, H = g["embed"].shape[1], g["W1"].shape[0], g["W1"].shape[1]
+    a = {k: _np(g[k]) for k in ("x", "embed", "Wr", "W1", "b1", "W2", "b2", "ff_gamma", "ff_beta", "final_gamma",
+                                 "final_beta")}
+    idx = np.zeros(S, np.int32); val = np.zeros(S, np.float32); counts = np.zeros(E, np.int32)
+    mapping = np.zeros(S, np.int32); out = np.zeros((S, D), np.float32)
+    clib.oracle_moe_block_forward_3m(_p(a["x"]), _p(a["embed"]), _p(a["Wr"]), None, _p(a["W1"]), _p(a["b1"]),
+                                     _p(a["W2"]), _p(a["b2"]), _p(a["ff_gamma"]), _p(a["ff_beta"]),
+                                     _p(a["final_gamma"]), _p(a["final_beta"]), C.c_float(float(g["eps"])),
+                                     C.c_float(float(g["ff_scale"])), S, D, Demb, E, H, 0, _p(idx), _p(val),
+                                     _p(counts), _p(mapping), _p(out))
+    assert np.array_equal(idx, g["gate_idx"].numpy())
+    assert np.array_equal(counts, g["expert_count"].numpy())
+    assert rel_l2(torch.from_numpy(out), g["out"]) < 1e-6
+    xn = np.zeros((S, D), np.float32)
+    clib.oracle_layer_norm(_p(a["x"]), _p(a["ff_gamma"]), _p(a["ff_beta"]), C.c_float(float(g["eps"])), S, D, _p(xn))
+    np.testing.assert_allclose(xn, g["xn"].numpy(), rtol=1e-5, atol=1e-6)

@@ -49,3 +49,31 @@ def test_grouped_equals_dense_per_token(oracle, synth):
         h = oracle.activation(x[s] @ w.W1[e].t() + w.b1[e], oracle.ACT_SILU)
         dense[s] = x[s] + 0.5 * r["score"][s, 0] * (h @ w.W2[e].t() + w.b2[e])
     assert rel_l2(r["out"], dense) < 1e-6
+
+
+def test_block_matches_reference(oracle):
+    """norm_ff -> 3M MoE -> residual + ff_scale * y -> norm_final, with the LayerNorms, eps and ff_scale of the
+    reference's own FmoeConformerLayer (layer/fmoe_transformer.py:54-65, 144-166)."""
+    g = load_golden("case_block_3m.npz")
+    r = oracle.moe_block_forward(g["x"], g["embed"], g["Wr"], None, g["W1"], g["b1"], g["W2"], g["b2"],
+                                 norm_ff=(g["ff_gamma"], g["ff_beta"]), norm_final=(g["final_gamma"], g["final_beta"]),
+                                 eps=float(g["eps"]), ff_scale=float(g["ff_scale"]))
+    torch.testing.assert_close(r["xn"], g["xn"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(r["idx"].view(-1), g["gate_idx"])
+    assert torch.equal(r["counts"], g["expert_count"])
+    torch.testing.assert_close(r["score"].view(-1), g["gate_value"], rtol=1e-5, atol=1e-7)
+    assert rel_l2(r["pre_norm_out"], g["pre_norm"]) < 1e-6
+    assert rel_l2(r["out"], g["out"]) < 1e-6
+    # the fixture is usable for bf16 parity with exact routing: every token's top-1 margin dwarfs a bf16 rounding of xn
+    top = torch.topk(r["logits"].double(), 2, dim=-1).values
+    assert float((top[:, 0] - top[:, 1]).min()) > 1e-2
+
+
+def test_layer_norm_is_torch_layer_norm(oracle):
+    torch.manual_seed(0)
+    x = torch.randn(19, 96) * 3 + 1
+    ln = torch.nn.LayerNorm(96, eps=1e-12)
+    with torch.no_grad():
+        ln.weight.normal_(1.0, 0.2)
+        ln.bias.normal_(0.0, 0.1)
+        torch.testing.assert_close(oracle.layer_norm(x, ln.weight, ln.bias, 1e-12), ln(x), rtol=1e-5, atol=1e-6)
