@@ -91,7 +91,7 @@ int env_int(const char* name, int dflt) {
 
 // Tunables: environment default, overridable at run time through b200moe_config() (tests flip them per case).
 namespace {
-std::atomic<int> g_pdl{-1}, g_pdl_trig{-1}, g_prefetch{-1}, g_route{-1};
+std::atomic<int> g_pdl{-1}, g_pdl_trig{-1}, g_prefetch{-1}, g_route{-1}, g_ln_fuse{-1};
 int knob(std::atomic<int>& v, const char* env, int dflt) {
   int cur = v.load(std::memory_order_relaxed);
   if (cur < 0) {
@@ -109,6 +109,7 @@ int knob(std::atomic<int>& v, const char* env, int dflt) {
 int pdl_mask() { return knob(g_pdl, "B200MOE_PDL", kPdlGate | kPdlFfn | kPdlLn); }
 int pdl_trigger() { return knob(g_pdl_trig, "B200MOE_PDL_TRIG", kPdlFfn); }
 int route_mode() { return knob(g_route, "B200MOE_ROUTE", 1); }
+int ln_fuse_mode() { return knob(g_ln_fuse, "B200MOE_LN_FUSE", 1); }
 
 int prefetch_mode() { return knob(g_prefetch, "B200MOE_PREFETCH", 0); }
 
@@ -159,6 +160,7 @@ int b200moe_config(const char* key, int value) {
   else if (k == "pdl") g_pdl.store(value);
   else if (k == "pdl_trig") g_pdl_trig.store(value);
   else if (k == "prefetch") g_prefetch.store(value);
+  else if (k == "ln_fuse") g_ln_fuse.store(value);
   else return fail(B200MOE_ERR_ARG, "config: unknown key '%s'", key);
   return B200MOE_OK;
 }
@@ -333,7 +335,38 @@ int b200moe_combine(const void* ybuf, const int* mapping, const float* score, co
   return B200MOE_OK;
 }
 
+namespace {
+// norm_ff fused into the route kernel (block call); null gamma = the layer alone
+struct LnFuse {
+  const float* gamma;
+  const float* beta;
+  float eps;
+};
+
+bool takes_route_kernel(const b200moe_layer_args* a) {
+  const int Demb = a->embed ? a->Demb : 0;
+  return a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype) &&
+         route_supported(a->B * a->T, a->D, Demb, a->E, a->top_k, a->dtype);
+}
+}  // namespace
+
+static int forward_impl(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cudaStream_t stream, const LnFuse* ln,
+                        const LnFuse* ln_out);
+
 int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return forward_impl(a, ws, ws_bytes, stream, nullptr, nullptr);
+}
+
+// ln: norm_ff fused into the route kernel (the caller has checked takes_route_kernel); ln_out: norm_final behind the
+// residual add -- inside the combine kernel for top-k > 1, as a row pass over `out` behind the fused top-1 epilogue.
+// Measured and dropped, both for norm_final inside the expert kernel (cfg3, us per block, same box as the row pass):
+//   per group -- every second-GEMM tile bumps its group's flag, waits for the D / 128 sibling tiles, normalises its
+//     share of the rows from L2: 45.0 vs 39.8 (sibling skew; the extra live state spilled registers in the epilogue and
+//     cost the bare layer 1.4 us);
+//   at the kernel's end behind a grid-wide barrier, all warps normalising from L2: 42.2 vs 41.2-42.7.  The row pass is
+//     not the cost; what any of these lose is the overlap of the next layer's route prologue with this kernel's tail.
+static int forward_impl(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cudaStream_t stream, const LnFuse* ln,
+                        const LnFuse* ln_out) {
   if (!a) return fail(B200MOE_ERR_ARG, "forward: null args");
   const int S = a->B * a->T;
   if (a->B < 0 || a->T < 0) return fail(B200MOE_ERR_ARG, "forward: bad B/T");
@@ -374,7 +407,8 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
     StageScope t(0, stream);
     e = launch_route(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->gate_mode,
                      a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf,
-                     fused ? a->out : nullptr, a->residual, stream);
+                     fused ? a->out : nullptr, a->residual, stream, nullptr, false, ln ? ln->gamma : nullptr,
+                     ln ? ln->beta : nullptr, ln ? ln->eps : 0.0f);
     if (e != cudaSuccess) return cuda_fail(e, "forward/route");
   } else {
   {
@@ -444,8 +478,13 @@ int b200moe_forward(const b200moe_layer_args* a, void* ws, size_t ws_bytes, cuda
   if (!fused) {
     StageScope t(3, stream);
     e = launch_combine(w.ybuf, w.mapping, a->keep_expert_output ? nullptr : score, a->residual, a->ff_scale, S, a->D,
-                       a->top_k, a->dtype, a->out, stream);
+                       a->top_k, a->dtype, a->out, stream, ln_out ? ln_out->gamma : nullptr,
+                       ln_out ? ln_out->beta : nullptr, ln_out ? ln_out->eps : 0.0f);
     if (e != cudaSuccess) return cuda_fail(e, "forward/combine");
+  } else if (ln_out) {
+    StageScope t(3, stream);
+    e = launch_layernorm(a->out, ln_out->gamma, ln_out->beta, ln_out->eps, S, a->D, a->dtype, a->out, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "forward/norm_final");
   }
   return B200MOE_OK;
 }
@@ -552,8 +591,18 @@ int b200moe_ep_forward(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws,
   return b200moe_ep_forward_stages(c, a, ws, ws_bytes, 7, stream);
 }
 
+static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes, int stages,
+                           cudaStream_t stream, const LnFuse* ln_in, const LnFuse* ln_out);
+
 int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes, int stages,
                               cudaStream_t stream) {
+  return ep_forward_impl(c, a, ws, ws_bytes, stages, stream, nullptr, nullptr);
+}
+
+// ln_in: norm_ff fused into the route kernel (the caller has checked that the route kernel is taken);
+// ln_out: norm_final fused into the combine kernel
+static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes, int stages,
+                           cudaStream_t stream, const LnFuse* ln_in, const LnFuse* ln_out) {
   if (!c || !a) return fail(B200MOE_ERR_ARG, "ep_forward: null argument");
   const EpPeers& ep = c->peers;
   const int S = a->B * a->T;
@@ -593,7 +642,7 @@ int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, vo
     StageScope t(0, stream);
     e = launch_route(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->gate_mode, 0, idx,
                      score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf, nullptr, nullptr, stream, &ep,
-                     fold_wait);
+                     fold_wait, ln_in ? ln_in->gamma : nullptr, ln_in ? ln_in->beta : nullptr, ln_in ? ln_in->eps : 0.0f);
     if (e != cudaSuccess) return cuda_fail(e, "ep_forward/route");
   }
   if (S > 0 && (stages & 1) && !route) {
@@ -655,7 +704,8 @@ int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, vo
   if (stages & 4) {
     StageScope t(3, stream);
     e = launch_ep_combine(ep, w.mapping, a->keep_expert_output ? nullptr : score, a->residual, a->ff_scale, S, a->D,
-                          a->top_k, a->out, stream);
+                          a->top_k, a->out, stream, ln_out ? ln_out->gamma : nullptr, ln_out ? ln_out->beta : nullptr,
+                          ln_out ? ln_out->eps : 0.0f);
   }
   if (e != cudaSuccess) return cuda_fail(e, "ep_forward/combine");
   return B200MOE_OK;
@@ -879,21 +929,18 @@ int b200moe_block_forward(const b200moe_block_args* b, void* ws, size_t ws_bytes
   const size_t layer_ws = b200moe_workspace_bytes(S, a.E, a.D, a.H, a.top_k);
   int rc = plan_block(b, layer_ws, ws, ws_bytes, &plan, "block_forward");
   if (rc != B200MOE_OK) return rc;
-  if (plan.xn) {
+  const LnFuse lin{b->norm_ff_gamma, b->norm_ff_beta, b->eps}, lout{b->norm_final_gamma, b->norm_final_beta, b->eps};
+  // small bf16 batches: the route kernel normalises the rows it has just fetched; otherwise a row pass in front
+  const bool fuse_in = plan.xn != nullptr && ln_fuse_mode() != 0 && takes_route_kernel(&a);
+  if (fuse_in) plan.layer.x = a.x;
+  if (plan.xn && !fuse_in) {
     if (!a.x) return fail(B200MOE_ERR_ARG, "block_forward: null pointer");
     StageScope t(0, stream);
     cudaError_t e = launch_layernorm(a.x, b->norm_ff_gamma, b->norm_ff_beta, b->eps, S, a.D, a.dtype, plan.xn, stream);
     if (e != cudaSuccess) return cuda_fail(e, "block_forward/norm_ff");
   }
-  rc = b200moe_forward(&plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, stream);
-  if (rc != B200MOE_OK) return rc;
-  if (b->norm_final_gamma && S > 0) {
-    StageScope t(3, stream);
-    cudaError_t e = launch_layernorm(a.out, b->norm_final_gamma, b->norm_final_beta, b->eps, S, a.D, a.dtype, a.out,
-                                     stream);
-    if (e != cudaSuccess) return cuda_fail(e, "block_forward/norm_final");
-  }
-  return B200MOE_OK;
+  return forward_impl(&plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, stream, fuse_in ? &lin : nullptr,
+                      (b->norm_final_gamma && S > 0) ? &lout : nullptr);
 }
 
 int b200moe_ep_block_forward(b200moe_ep_ctx* c, const b200moe_block_args* b, void* ws, size_t ws_bytes,
@@ -906,19 +953,17 @@ int b200moe_ep_block_forward(b200moe_ep_ctx* c, const b200moe_block_args* b, voi
   const size_t layer_ws = b200moe_ep_workspace_bytes(c, a.H);
   int rc = plan_block(b, layer_ws, ws, ws_bytes, &plan, "ep_block_forward");
   if (rc != B200MOE_OK) return rc;
-  if (plan.xn) {
+  const LnFuse lin{b->norm_ff_gamma, b->norm_ff_beta, b->eps}, lout{b->norm_final_gamma, b->norm_final_beta, b->eps};
+  const bool fuse_in = plan.xn != nullptr && ln_fuse_mode() != 0 && takes_route_kernel(&a);
+  if (fuse_in) plan.layer.x = a.x;
+  if (plan.xn && !fuse_in) {
     if (!a.x) return fail(B200MOE_ERR_ARG, "ep_block_forward: null pointer");
     cudaError_t e = launch_layernorm(a.x, b->norm_ff_gamma, b->norm_ff_beta, b->eps, S, a.D, a.dtype, plan.xn, stream);
     if (e != cudaSuccess) return cuda_fail(e, "ep_block_forward/norm_ff");
   }
-  rc = b200moe_ep_forward_stages(c, &plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, 7, stream);
-  if (rc != B200MOE_OK) return rc;
-  if (b->norm_final_gamma && S > 0) {
-    cudaError_t e = launch_layernorm(a.out, b->norm_final_gamma, b->norm_final_beta, b->eps, S, a.D, a.dtype, a.out,
-                                     stream);
-    if (e != cudaSuccess) return cuda_fail(e, "ep_block_forward/norm_final");
-  }
-  return B200MOE_OK;
+  // norm_final rides in the combine kernel (it runs even for a rank without tokens: the flags must be consumed)
+  return ep_forward_impl(c, &plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, 7, stream,
+                         fuse_in ? &lin : nullptr, b->norm_final_gamma ? &lout : nullptr);
 }
 
 }  // extern "C"

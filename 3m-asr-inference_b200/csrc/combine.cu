@@ -8,6 +8,7 @@
 //   x ff_scale, + residual                                trainer_3m_fix/layer/fmoe_transformer.py:155-158
 // HBM-bound: one warp per token row, 128-bit loads and stores, fp32 accumulation.
 #include "common.cuh"
+#include "ln_device.cuh"
 #include "ptx.cuh"
 
 namespace b200moe {
@@ -88,10 +89,57 @@ struct Vec8<float> {
 template <typename T>
 __global__ void __launch_bounds__(kCombineThreads)
 combine_kernel(const T* __restrict__ ybuf, const int* __restrict__ mapping, const float* __restrict__ score,
-               const T* __restrict__ residual, float ff_scale, int S, int D, int top_k, T* __restrict__ out) {
+               const T* __restrict__ residual, float ff_scale, int S, int D, int top_k, T* __restrict__ out,
+               const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = kCombineThreads / 32;
+  if (ln_gamma != nullptr) {
+    // norm_final fused behind the residual add (fmoe_transformer.py:164-166): the warp holds the whole row
+    const int nvec = D >> 3;
+    for (int s = blockIdx.x * warps_per_block + warp; s < S; s += gridDim.x * warps_per_block) {
+      float o[kLnMaxVec][8];
+#pragma unroll
+      for (int k = 0; k < kLnMaxVec; ++k) {
+        const int v = k * 32 + lane;
+        if (v >= nvec) continue;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+        for (int j = 0; j < top_k; ++j) {
+          const int row = mapping[s * top_k + j];
+          if (row < 0) continue;
+          const float w = score ? score[s * top_k + j] : 1.0f;
+          Vec8<T> y;
+          y.load(ybuf + static_cast<size_t>(row) * D + v * 8);
+          float f[8];
+          y.to_f(f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+        }
+        if (residual) {
+          Vec8<T> r;
+          r.load(residual + static_cast<size_t>(s) * D + v * 8);
+          r.to_f(o[k]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[k][i] = fmaf(ff_scale, acc[i], o[k][i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[k][i] = ff_scale * acc[i];
+        }
+      }
+      ln_row_registers(o, D, lane, ln_gamma, ln_beta, ln_eps);
+#pragma unroll
+      for (int k = 0; k < kLnMaxVec; ++k) {
+        const int v = k * 32 + lane;
+        if (v >= nvec) continue;
+        Vec8<T> ov;
+        ov.from_f(o[k]);
+        ov.store(out + static_cast<size_t>(s) * D + v * 8);
+      }
+    }
+    return;
+  }
   for (int s = blockIdx.x * warps_per_block + warp; s < S; s += gridDim.x * warps_per_block) {
     for (int v = lane; v < D / 8; v += 32) {
       float acc[8];
@@ -147,9 +195,11 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const T* __restrict__ sr
 }  // namespace
 
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
-                           float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream) {
+                           float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream,
+                           const float* ln_gamma, const float* ln_beta, float ln_eps) {
   if (S == 0) return cudaSuccess;
   if (D % 8 != 0 || top_k < 1) return cudaErrorInvalidValue;
+  if (ln_gamma != nullptr && (!layernorm_supported(D) || ln_beta == nullptr)) return cudaErrorInvalidValue;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -158,7 +208,7 @@ cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* sc
 #define B200MOE_COMBINE(T)                                                                                     \
   combine_kernel<T><<<grid, kCombineThreads, 0, stream>>>(static_cast<const T*>(ybuf), mapping, score,         \
                                                           static_cast<const T*>(residual), ff_scale, S, D,     \
-                                                          top_k, static_cast<T*>(out))
+                                                          top_k, static_cast<T*>(out), ln_gamma, ln_beta, ln_eps)
   switch (dtype) {
     case B200MOE_F32:
       B200MOE_COMBINE(float);

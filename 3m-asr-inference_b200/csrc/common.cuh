@@ -167,7 +167,8 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          int B, int T, int D, int Demb, int E, int gate_mode, int keep_expert_output, int* idx,
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream,
-                         const EpPeers* ep = nullptr, bool ep_fold_wait = false);
+                         const EpPeers* ep = nullptr, bool ep_fold_wait = false, const float* ln_gamma = nullptr,
+                         const float* ln_beta = nullptr, float ln_eps = 0.0f);
 
 // ffn.cu
 struct FfnLaunch {
@@ -206,8 +207,10 @@ void set_ffn_trace(void* dev_buf, int records_per_cta);
 cudaError_t launch_ep_wait_build(const EpPeers& ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax,
                                  cudaStream_t stream);
 // Waits until every expert rank has returned this rank's rows, then out = residual + ff_scale * sum_k score * ret_y[mapping].
+// ln_gamma / ln_beta non-null: LayerNorm over the D features of every output row on top (norm_final).
 cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float* score, const void* residual,
-                              float ff_scale, int S, int D, int top_k, void* out, cudaStream_t stream);
+                              float ff_scale, int S, int D, int top_k, void* out, cudaStream_t stream,
+                              const float* ln_gamma = nullptr, const float* ln_beta = nullptr, float ln_eps = 0.0f);
 
 // layernorm.cu
 // out[s, :] = LayerNorm(in[s, :]) * gamma + beta over D features (biased variance, eps inside the root); in == out allowed.
@@ -217,7 +220,8 @@ cudaError_t launch_layernorm(const void* in, const float* gamma, const float* be
 
 // combine.cu
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
-                           float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream);
+                           float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream,
+                           const float* ln_gamma = nullptr, const float* ln_beta = nullptr, float ln_eps = 0.0f);
 cudaError_t launch_pack_bf16(const void* src, int src_dtype, bf16* dst, size_t n, cudaStream_t stream);
 cudaError_t launch_pack_tf32(const float* src, float* dst, size_t n, cudaStream_t stream);  // round to nearest TF32
 
@@ -232,6 +236,7 @@ void count_launch(int n = 1);
 int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN, bit 3 LayerNorm: kernel launched with the PDL attribute
 int pdl_trigger();   // same bits: kernel executes griddepcontrol.launch_dependents at its start
 int prefetch_mode();
+int ln_fuse_mode(); // B200MOE_LN_FUSE: 1 (default) = the block's norm_ff runs inside the route kernel, 0 = as a row pass in front
 int route_mode();   // B200MOE_ROUTE: 1 (default) = fused gate + dispatch kernel for small batches, 0 = separate kernels
 constexpr int kPdlGate = 1, kPdlDispatch = 2, kPdlFfn = 4, kPdlLn = 8;
 

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "ep_device.cuh"
+#include "ln_device.cuh"
 #include "ptx.cuh"
 
 namespace b200moe {
@@ -47,7 +48,8 @@ __device__ __forceinline__ void bf16x8_to_f(const uint4& v, float (&o)[8]) {
 // with ordinary (L2-coherent) loads after the acquire, never through the read-only path.
 __global__ void __launch_bounds__(256)
 ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float* __restrict__ score,
-                  const bf16* __restrict__ residual, float ff_scale, int S, int D, int top_k, bf16* __restrict__ out) {
+                  const bf16* __restrict__ residual, float ff_scale, int S, int D, int top_k, bf16* __restrict__ out,
+                  const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps) {
   // Programmatic dependent launch, both ways.  (1) The next layer's route kernel may start now: it only touches
   // constants (embed, router) until its own griddepcontrol.wait, which returns when this grid has completed.  (2) This
   // kernel itself never calls griddepcontrol.wait although it is launched early: everything it consumes from the FFN
@@ -66,6 +68,54 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
   const bf16* ret_y = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.ret_y);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x / 32;
+  if (ln_gamma != nullptr) {
+    // norm_final fused behind the residual add (fmoe_transformer.py:164-166): the warp holds the whole row
+    const int nvec = D >> 3;
+    for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
+      float o[kLnMaxVec][8];
+#pragma unroll
+      for (int k = 0; k < kLnMaxVec; ++k) {
+        const int v = k * 32 + lane;
+        if (v >= nvec) continue;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+        for (int j = 0; j < top_k; ++j) {
+          const int row = mapping[s * top_k + j];
+          if (row < 0) continue;
+          const float w = score ? score[s * top_k + j] : 1.0f;
+          const uint4 y = *reinterpret_cast<const uint4*>(ret_y + static_cast<size_t>(row) * D + v * 8);
+          float f[8];
+          bf16x8_to_f(y, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+        }
+        if (residual) {
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(residual + static_cast<size_t>(s) * D + v * 8));
+          bf16x8_to_f(r, o[k]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[k][i] = fmaf(ff_scale, acc[i], o[k][i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[k][i] = ff_scale * acc[i];
+        }
+      }
+      ln_row_registers(o, D, lane, ln_gamma, ln_beta, ln_eps);
+#pragma unroll
+      for (int k = 0; k < kLnMaxVec; ++k) {
+        const int v = k * 32 + lane;
+        if (v >= nvec) continue;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 pk = __floats2bfloat162_rn(o[k][2 * i], o[k][2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(s) * D + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    return;
+  }
   for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
     for (int v = lane; v < D / 8; v += 32) {
       float acc[8];
@@ -113,13 +163,16 @@ cudaError_t launch_ep_wait_build(const EpPeers& ep, int bn, GroupRec* groups, in
 }
 
 cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float* score, const void* residual,
-                              float ff_scale, int S, int D, int top_k, void* out, cudaStream_t stream) {
+                              float ff_scale, int S, int D, int top_k, void* out, cudaStream_t stream,
+                              const float* ln_gamma, const float* ln_beta, float ln_eps) {
   if (D % 8 != 0) return cudaErrorInvalidValue;
+  if (ln_gamma != nullptr && (!layernorm_supported(D) || ln_beta == nullptr)) return cudaErrorInvalidValue;
   int blocks = (S + 7) / 8;
   if (blocks < 1) blocks = 1;  // the wait on the return flags must happen even for a rank without tokens
   if (blocks > 4 * 148) blocks = 4 * 148;
   cudaError_t e = launch_kernel(ep_combine_kernel, dim3(blocks), dim3(256), 0, stream, kPdlFfn, ep, mapping, score,
-                                static_cast<const bf16*>(residual), ff_scale, S, D, top_k, static_cast<bf16*>(out));
+                                static_cast<const bf16*>(residual), ff_scale, S, D, top_k, static_cast<bf16*>(out),
+                                ln_gamma, ln_beta, ln_eps);
   count_launch();
   return e;
 }

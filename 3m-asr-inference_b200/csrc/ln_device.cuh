@@ -1,58 +1,104 @@
-// LayerNorm over one token row held by ONE warp in registers: lane l owns the 8-element vectors l, l + 32, ... of the
-// row (kLnMaxVec of them at most, i.e. D <= 1024).  Semantics of torch.nn.LayerNorm as the 3M-ASR blocks use it
+// LayerNorm over token rows held by ONE warp in registers: lane l owns the 8-element vectors l, l + 32, ... of a row
+// (kVec of them at most).  Semantics of torch.nn.LayerNorm as the 3M-ASR blocks use it
 // (trainer_3m_fix/layer/fmoe_transformer.py:54-65: eps = 1e-12, biased variance, fp32 gamma / beta); the TensorRT
 // plugin that replaces it computes the same thing in fp32 (TRTAPI++/plugin/layer_norm_plugin/layer_norm_kernel.cu).
 // Two passes over the registers (mean, then the centred sum of squares): no E[x^2] - mu^2 cancellation.
+// R rows are processed together so that their shuffle reductions overlap; the arithmetic of one row does not depend on
+// R or kVec (partial sums run over the lane's valid vectors in increasing order, then a xor-shuffle tree), so every
+// kernel that normalises through this file produces the same bits for the same row.
 #pragma once
 #include "common.cuh"
 
 namespace b200moe {
 
-constexpr int kLnMaxVec = 4;
+constexpr int kLnMaxVec = 4;  // D <= 1024
 
-__device__ __forceinline__ float warp_sum(float v) {
+// gamma / beta of the vectors a lane owns: the same for every row, loaded once
+template <int kVec>
+struct LnAffine {
+  float g[kVec][8];
+  float b[kVec][8];
+  __device__ __forceinline__ void load(const float* __restrict__ gamma, const float* __restrict__ beta, int D, int lane) {
+    const int nvec = D >> 3;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+    for (int k = 0; k < kVec; ++k) {
+      if (k * 32 + lane < nvec) {
+        const int f0 = (k * 32 + lane) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + f0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + f0) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + f0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + f0) + 1);
+        g[k][0] = g0.x; g[k][1] = g0.y; g[k][2] = g0.z; g[k][3] = g0.w;
+        g[k][4] = g1.x; g[k][5] = g1.y; g[k][6] = g1.z; g[k][7] = g1.w;
+        b[k][0] = b0.x; b[k][1] = b0.y; b[k][2] = b0.z; b[k][3] = b0.w;
+        b[k][4] = b1.x; b[k][5] = b1.y; b[k][6] = b1.z; b[k][7] = b1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[k][i] = b[k][i] = 0.0f;
+      }
+    }
+  }
+};
+
+// v[r][k][i]: element (k * 32 + lane) * 8 + i of row r; vectors with (k * 32 + lane) * 8 >= D are ignored.
+template <int kVec, int R>
+__device__ __forceinline__ void ln_rows_registers(float (&v)[R][kVec][8], int D, int lane, const LnAffine<kVec>& a,
+                                                  float eps) {
+  const int nvec = D >> 3;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  float s[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    s[r] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kVec; ++k)
+      if (k * 32 + lane < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[r] += v[r][k][i];
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  float q[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    s[r] *= inv_d;  // mean
+    q[r] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kVec; ++k)
+      if (k * 32 + lane < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[r][k][i] - s[r];
+          q[r] = fmaf(d, d, q[r]);
+        }
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float rstd = rsqrtf(q[r] * inv_d + eps);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k)
+      if (k * 32 + lane < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[r][k][i] = fmaf((v[r][k][i] - s[r]) * rstd, a.g[k][i], a.b[k][i]);
+      }
+  }
 }
 
-// v[k][i]: element (k * 32 + lane) * 8 + i of the row; vectors with (k * 32 + lane) * 8 >= D are ignored.
+// one row, up to kLnMaxVec vectors per lane (the row-pass kernels)
 __device__ __forceinline__ void ln_row_registers(float (&v)[kLnMaxVec][8], int D, int lane,
                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                  float eps) {
-  const int nvec = D >> 3;
-  float s = 0.0f;
-#pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k)
-    if (k * 32 + lane < nvec) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[k][i];
-    }
-  const float mean = warp_sum(s) / static_cast<float>(D);
-  float q = 0.0f;
-#pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k)
-    if (k * 32 + lane < nvec) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = v[k][i] - mean;
-        q = fmaf(d, d, q);
-      }
-    }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
-#pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k)
-    if (k * 32 + lane < nvec) {
-      const int f0 = (k * 32 + lane) * 8;
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + f0));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + f0) + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + f0));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + f0) + 1);
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[k][i] = fmaf((v[k][i] - mean) * rstd, g[i], b[i]);
-    }
+  LnAffine<kLnMaxVec> a;
+  a.load(gamma, beta, D, lane);
+  ln_rows_registers<kLnMaxVec, 1>(reinterpret_cast<float (&)[1][kLnMaxVec][8]>(v), D, lane, a, eps);
 }
 
 }  // namespace b200moe

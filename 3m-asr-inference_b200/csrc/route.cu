@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "ep_device.cuh"
+#include "ln_device.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
 
@@ -45,6 +46,56 @@ constexpr int kRSlot = kRSlotA + kRSlotB;   // 96 KiB
 constexpr int kRSlots = 2;
 constexpr int kRThreads = 256;
 constexpr uint32_t kRTmemCols = 64;         // 2 accumulator buffers x 32 token columns
+constexpr int kLnWarps = 4;                 // warps 2, 3, 6, 7 normalise the token rows when norm_ff is fused in
+
+// The x operand in the ring: [k-block][32 rows][64 bf16], 128-byte swizzle (the 16-byte chunk c of row r sits at chunk
+// c ^ (r & 7)).  A warp normalises kRowsPerLnWarp rows together; lane l owns the 8-element vectors l and l + 32 of each
+// row (D <= 512 here), exactly like layernorm_rows_kernel, so both produce the same bits.
+constexpr int kRowsPerLnWarp = kTok / kLnWarps;  // 8
+constexpr int kRouteLnVec = 2;
+
+__device__ __forceinline__ void ln_rows_in_ring(uint8_t* sx, int r0, int D, int lane, const LnAffine<kRouteLnVec>& aff,
+                                                float eps) {
+  const int nvec = D >> 3;
+  float v[kRowsPerLnWarp][kRouteLnVec][8];
+#pragma unroll
+  for (int i = 0; i < kRowsPerLnWarp; ++i) {
+    const int r = r0 + i;
+#pragma unroll
+    for (int k = 0; k < kRouteLnVec; ++k) {
+      const int vec = k * 32 + lane;
+      if (vec < nvec) {
+        const uint4 w4 =
+            *reinterpret_cast<const uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4));
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[i][k][2 * j] = __uint_as_float(w[j] << 16);
+          v[i][k][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        }
+      }
+    }
+  }
+  ln_rows_registers<kRouteLnVec, kRowsPerLnWarp>(v, D, lane, aff, eps);
+#pragma unroll
+  for (int i = 0; i < kRowsPerLnWarp; ++i) {
+    const int r = r0 + i;
+#pragma unroll
+    for (int k = 0; k < kRouteLnVec; ++k) {
+      const int vec = k * 32 + lane;
+      if (vec < nvec) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 pk = __floats2bfloat162_rn(v[i][k][2 * j], v[i][k][2 * j + 1]);
+          w[j] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        *reinterpret_cast<uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
 
 struct RouteParams {
   // gate
@@ -76,6 +127,11 @@ struct RouteParams {
   unsigned long long* bar;
   unsigned nonce;
   int ep_fold_wait;
+  // norm_ff fused in front of the router (block call): the 32 token rows of a tile are normalised in shared memory
+  // between the TMA that brings them and the MMAs that read them; null = off
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
   uint4* trace;  // debug timeline: 16 records per CTA {event, clock64 lo, hi, -}; slots 14 / 15 hold %globaltimer
 };
 
@@ -129,8 +185,9 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kRSlots + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kRSlots + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kRSlots + 4);
-  uint8_t* misc = smem_raw + (tmem_slot - smem_base) + 16;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(misc - 16);
+  auto ln_bar = [&](int s) { return tmem_slot + 16u + 8u * s; };  // LayerNorm warps -> MMA issuer
+  uint8_t* misc = smem_raw + (tmem_slot - smem_base) + 32;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(misc - 32);
   float* s_br = reinterpret_cast<float*>(misc);               // [32]
   float* s_hi = s_br + 32;                                     // [32][33]
   float* s_lo = s_hi + 32 * 33;                                // [32][33]
@@ -172,6 +229,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
       ptx::mbar_init(tempty_bar(s), 2);
+      ptx::mbar_init(ln_bar(s), kLnWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -232,6 +290,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         for (int part = 0; part < n_parts; ++part) {
           const int nkb = (n_parts == 2 && part == 0) ? kb_e : kb_x;
           ptx::mbar_wait(full_bar(slot), phase);
+          if (p.ln_gamma != nullptr && part == n_parts - 1) ptx::mbar_wait(ln_bar(slot), phase);  // rows normalised
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + slot * kRSlot;
           for (int j = 0; j < nkb; ++j) {
@@ -248,6 +307,31 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             slot = 0;
             phase ^= 1u;
           }
+        }
+      }
+    }
+  } else if (p.ln_gamma != nullptr && (warp == 2 || warp == 3 || warp >= 6)) {
+    // norm_ff (fmoe_transformer.py:145-148) on the tile's 32 token rows, in place in the ring, 8 rows per warp.  The
+    // MMAs of the x part and the row copies of phase 2 then read normalised rows; `x` in global memory stays as it is
+    // (it is the residual).
+    const int lw = (warp & 1) | ((warp >> 2) << 1);  // warps 2, 3, 6, 7 -> 0 .. 3
+    LnAffine<kRouteLnVec> aff;                       // constants: fetched while the tile is still on its way
+    aff.load(p.ln_gamma, p.ln_beta, p.D, lane);
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int part = 0; part < n_parts; ++part) {
+        if (part == n_parts - 1) {
+          ptx::mbar_wait(full_bar(slot), phase);  // the TMA's bytes are there
+          uint8_t* sx = smem_raw + slot * kRSlot + kRSlotA;
+          ln_rows_in_ring(sx, lw * kRowsPerLnWarp, p.D, lane, aff, p.ln_eps);
+          ptx::fence_proxy_async_all();  // generic-proxy writes -> the tensor cores' (async proxy) reads
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ln_bar(slot));
+        }
+        if (++slot == kRSlots) {
+          slot = 0;
+          phase ^= 1u;
         }
       }
     }
@@ -469,6 +553,39 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                     (static_cast<size_t>(ep.rank) * ep.cap + slot) * p.D;
         }
       }
+      if (p.ln_gamma != nullptr) {
+        // more tiles than SMs: the ring has moved on, the rows come from global memory and are normalised again on
+        // the way (same lane <-> vector assignment as in the ring, hence the same bits the router saw)
+        const int nvec = p.D >> 3;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (d[r] < 0) continue;  // (warp-uniform)
+          float v[kLnMaxVec][8];
+#pragma unroll
+          for (int k = 0; k < kLnMaxVec; ++k)
+            if (k * 32 + lane < nvec) {
+              const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(src[r]) + k * 32 + lane);
+              const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[k][2 * i] = __uint_as_float(w[i] << 16);
+                v[k][2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+              }
+            }
+          ln_row_registers(v, p.D, lane, p.ln_gamma, p.ln_beta, p.ln_eps);
+#pragma unroll
+          for (int k = 0; k < kLnMaxVec; ++k)
+            if (k * 32 + lane < nvec) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 pk = __floats2bfloat162_rn(v[k][2 * i], v[k][2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&pk);
+              }
+              reinterpret_cast<uint4*>(drow[r])[k * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+      } else
       for (int v = lane; v < p.D / 8; v += 32) {
         uint4 regs[4];
 #pragma unroll
@@ -601,7 +718,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          int B, int T, int D, int Demb, int E, int gate_mode, int keep_expert_output, int* idx,
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream, const EpPeers* ep,
-                         bool ep_fold_wait) {
+                         bool ep_fold_wait, const float* ln_gamma, const float* ln_beta, float ln_eps) {
   const int S = B * T;
   if (embed == nullptr) Demb = 0;
   if (!route_supported(S, D, Demb, E, 1, B200MOE_BF16)) return cudaErrorInvalidValue;
@@ -655,10 +772,13 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   if (nonce == 0) nonce = g_route_nonce.fetch_add(1, std::memory_order_relaxed) & 0x00ffffffu;
   p.nonce = nonce;
   p.ep_fold_wait = ep_fold_wait ? 1 : 0;
+  p.ln_gamma = (ln_gamma != nullptr && ln_beta != nullptr) ? ln_gamma : nullptr;
+  p.ln_beta = ln_beta;
+  p.ln_eps = ln_eps;
   p.trace = static_cast<uint4*>(g_route_trace);
   EpPeers epv{};
   if (ep) epv = *ep;
-  const size_t smem = kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 16 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 64);
+  const size_t smem = kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 32 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 64);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(route_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

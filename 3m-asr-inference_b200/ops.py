@@ -56,7 +56,7 @@ def launch_count() -> int:
 
 
 def config(key: str, value: int) -> None:
-    """Run-time tunables ("route", "pdl", "pdl_trig", "prefetch"); see include/b200moe.h."""
+    """Run-time tunables ("route", "pdl", "pdl_trig", "prefetch", "ln_fuse"); see include/b200moe.h."""
     _lib.check(_lib.load().b200moe_config(key.encode(), int(value)), "b200moe_config")
 
 
