@@ -52,46 +52,50 @@ constexpr int kLnWarps = 4;                 // warps 2, 3, 6, 7 normalise the to
 // c ^ (r & 7)).  A warp normalises kRowsPerLnWarp rows together; lane l owns the 8-element vectors l and l + 32 of each
 // row (D <= 512 here), exactly like layernorm_rows_kernel, so both produce the same bits.
 constexpr int kRowsPerLnWarp = kTok / kLnWarps;  // 8
+constexpr int kLnBatch = 4;                       // rows a warp normalises together (registers: 16 floats per row)
 constexpr int kRouteLnVec = 2;
 
 __device__ __forceinline__ void ln_rows_in_ring(uint8_t* sx, int r0, int D, int lane, const LnAffine<kRouteLnVec>& aff,
                                                 float eps) {
   const int nvec = D >> 3;
-  float v[kRowsPerLnWarp][kRouteLnVec][8];
+#pragma unroll 1
+  for (int rb = r0; rb < r0 + kRowsPerLnWarp; rb += kLnBatch) {
+    float v[kLnBatch][kRouteLnVec][8];
 #pragma unroll
-  for (int i = 0; i < kRowsPerLnWarp; ++i) {
-    const int r = r0 + i;
+    for (int i = 0; i < kLnBatch; ++i) {
+      const int r = rb + i;
 #pragma unroll
-    for (int k = 0; k < kRouteLnVec; ++k) {
-      const int vec = k * 32 + lane;
-      if (vec < nvec) {
-        const uint4 w4 =
-            *reinterpret_cast<const uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4));
-        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+      for (int k = 0; k < kRouteLnVec; ++k) {
+        const int vec = k * 32 + lane;
+        if (vec < nvec) {
+          const uint4 w4 =
+              *reinterpret_cast<const uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4));
+          const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[i][k][2 * j] = __uint_as_float(w[j] << 16);
-          v[i][k][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+          for (int j = 0; j < 4; ++j) {
+            v[i][k][2 * j] = __uint_as_float(w[j] << 16);
+            v[i][k][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+          }
         }
       }
     }
-  }
-  ln_rows_registers<kRouteLnVec, kRowsPerLnWarp>(v, D, lane, aff, eps);
+    ln_rows_registers<kRouteLnVec, kLnBatch>(v, D, lane, aff, eps);
 #pragma unroll
-  for (int i = 0; i < kRowsPerLnWarp; ++i) {
-    const int r = r0 + i;
+    for (int i = 0; i < kLnBatch; ++i) {
+      const int r = rb + i;
 #pragma unroll
-    for (int k = 0; k < kRouteLnVec; ++k) {
-      const int vec = k * 32 + lane;
-      if (vec < nvec) {
-        uint32_t w[4];
+      for (int k = 0; k < kRouteLnVec; ++k) {
+        const int vec = k * 32 + lane;
+        if (vec < nvec) {
+          uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 pk = __floats2bfloat162_rn(v[i][k][2 * j], v[i][k][2 * j + 1]);
-          w[j] = *reinterpret_cast<uint32_t*>(&pk);
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 pk = __floats2bfloat162_rn(v[i][k][2 * j], v[i][k][2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&pk);
+          }
+          *reinterpret_cast<uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4)) =
-            make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -169,7 +173,9 @@ __device__ __forceinline__ unsigned grid_arrive(unsigned long long* st, unsigned
   }
 }
 
-template <bool kEp>
+// kLn: the block's norm_ff is fused in (its own instantiation: the LayerNorm code doubles the kernel's registers and
+// instruction footprint, which cost the plain kernel 1.2-1.9 us per layer when it was a run-time switch)
+template <bool kEp, bool kLn>
 __global__ void __launch_bounds__(kRThreads, 1)
 route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_e,
              const __grid_constant__ CUtensorMap tm_wx, const __grid_constant__ CUtensorMap tm_we, const RouteParams p,
@@ -229,7 +235,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
       ptx::mbar_init(tempty_bar(s), 2);
-      ptx::mbar_init(ln_bar(s), kLnWarps);
+      if (kLn) ptx::mbar_init(ln_bar(s), kLnWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -290,7 +296,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         for (int part = 0; part < n_parts; ++part) {
           const int nkb = (n_parts == 2 && part == 0) ? kb_e : kb_x;
           ptx::mbar_wait(full_bar(slot), phase);
-          if (p.ln_gamma != nullptr && part == n_parts - 1) ptx::mbar_wait(ln_bar(slot), phase);  // rows normalised
+          if (kLn && part == n_parts - 1) ptx::mbar_wait(ln_bar(slot), phase);  // rows normalised
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + slot * kRSlot;
           for (int j = 0; j < nkb; ++j) {
@@ -310,7 +316,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         }
       }
     }
-  } else if (p.ln_gamma != nullptr && (warp == 2 || warp == 3 || warp >= 6)) {
+  } else if (kLn && (warp == 2 || warp == 3 || warp >= 6)) {
     // norm_ff (fmoe_transformer.py:145-148) on the tile's 32 token rows, in place in the ring, 8 rows per warp.  The
     // MMAs of the x part and the row copies of phase 2 then read normalised rows; `x` in global memory stays as it is
     // (it is the residual).
@@ -553,7 +559,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                     (static_cast<size_t>(ep.rank) * ep.cap + slot) * p.D;
         }
       }
-      if (p.ln_gamma != nullptr) {
+      if constexpr (kLn) {
         // more tiles than SMs: the ring has moved on, the rows come from global memory and are normalised again on
         // the way (same lane <-> vector assignment as in the ring, hence the same bits the router saw)
         const int nvec = p.D >> 3;
@@ -781,22 +787,23 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   const size_t smem = kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 32 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 64);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(route_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    const int bytes = static_cast<int>(smem);
+    cudaError_t e = cudaFuncSetAttribute(route_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(route_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem));
+      e = cudaFuncSetAttribute(route_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(route_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(route_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int n_tiles = (S + kTok - 1) / kTok;
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-  cudaError_t e;
-  if (ep)
-    e = launch_kernel(route_kernel<true>, dim3(grid), dim3(kRThreads), smem, stream, kPdlGate, tx, te, twx, twe, p, epv);
-  else
-    e = launch_kernel(route_kernel<false>, dim3(grid), dim3(kRThreads), smem, stream, kPdlGate, tx, te, twx, twe, p,
-                      epv);
+  const bool ln = p.ln_gamma != nullptr;
+  auto kernel = ep ? (ln ? route_kernel<true, true> : route_kernel<true, false>)
+                   : (ln ? route_kernel<false, true> : route_kernel<false, false>);
+  cudaError_t e = launch_kernel(kernel, dim3(grid), dim3(kRThreads), smem, stream, kPdlGate, tx, te, twx, twe, p, epv);
   count_launch();
   return e;
 }

@@ -244,3 +244,55 @@ def test_ep_block_single_rank(ops, oracle, synth):
     assert float((rows <= 2e-2).float().mean()) > 0.97            # all rows but re-routed near-ties
     assert rel_l2(out.float().cpu()[rows <= 2e-2], ref["out"][rows <= 2e-2]) <= BF16_REL_L2
     ctx.close()
+
+
+def test_block_post_norm_wiring(ops, oracle, synth):
+    """normalize_before = False (fmoe_transformer.py:160-166): no norm in front, norm_ff behind the residual add and, for
+    blocks with a convolution module, norm_final after that."""
+    layer = pkg("layer")
+    E, D, H, Demb, B, T = 8, 256, 512, 256, 2, 33
+    w = synth.make_weights(101, E, D, H, Demb, random_bias=True)
+    x, emb = synth.make_activations(102, B * T, D, Demb, w)
+    block = torch.nn.Module()
+    block.feed_forward = layer.LocalFmoeCatEmbedFeedForward(D, Demb, num_experts=E, hidden_units=H,
+                                                            activation=layer.Swish())
+    block.norm_ff = torch.nn.LayerNorm(D, eps=1e-12)
+    block.norm_final = torch.nn.LayerNorm(D, eps=1e-12)
+    block.conv_module = torch.nn.Identity()
+    block.ff_scale, block.normalize_before = 1.0, False
+    nf, nl = make_norm(D, 103), make_norm(D, 104)
+    with torch.no_grad():
+        block.feed_forward.router_weights.copy_(w.Wr)
+        block.feed_forward.experts.w_1.weight.copy_(w.W1); block.feed_forward.experts.w_1.bias.copy_(w.b1)
+        block.feed_forward.experts.w_2.weight.copy_(w.W2); block.feed_forward.experts.w_2.bias.copy_(w.b2)
+        block.norm_ff.weight.copy_(nf[0]); block.norm_ff.bias.copy_(nf[1])
+        block.norm_final.weight.copy_(nl[0]); block.norm_final.bias.copy_(nl[1])
+    block = block.cuda()
+    with torch.no_grad():
+        y = layer.feed_forward_block(block, x.cuda().bfloat16().view(B, T, D), emb.cuda().bfloat16().view(B, T, Demb))
+    r = oracle.moe_forward(x, emb, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=1.0)
+    assert torch.equal(r["idx"], r["idx"])   # (routing is on the raw input here: synth's margins apply, no near-ties)
+    want = oracle.layer_norm(oracle.layer_norm(r["out"], nf[0], nf[1]), nl[0], nl[1])
+    assert rel_l2(y.float().cpu().view(B * T, D), want) <= BF16_REL_L2
+
+
+def test_block_fp16_activations(ops, oracle, synth):
+    """fp16 activations take the SIMT gate and the separate LayerNorm row passes."""
+    E, D, H, Demb, S = 16, 256, 512, 256, 200
+    w = synth.make_weights(111, E, D, H, Demb, random_bias=True)
+    x, emb = synth.make_activations(112, S, D, Demb, w)
+    x = (x * 2.0 + 0.3).half().float()
+    nf, nl = make_norm(D, 113), make_norm(D, 114)
+    experts = ops.pack_experts(w.W1.cuda(), w.b1.cuda(), w.W2.cuda(), w.b2.cuda())
+    xd, ed = x.cuda().half(), emb.cuda().half()
+    res = ops.moe_layer(xd, ed, w.Wr.cuda(), None, experts, residual=xd, ff_scale=0.5, return_routing=True,
+                        norm_ff=cu(nf), norm_final=cu(nl))
+    xn_gpu = ops.layernorm(xd, nf[0].cuda(), nf[1].cuda()).float().cpu()
+    r = oracle.moe_forward(xn_gpu, emb.half().float(), w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
+    top = torch.topk(r["logits"].double(), 2, dim=-1).values
+    clear = (top[:, 0] - top[:, 1]) >= 1e-4
+    assert torch.equal(res.idx.cpu().long()[clear], r["idx"][clear])
+    same = (res.idx.cpu().long() == r["idx"]).all(-1)
+    want = oracle.layer_norm(r["out"], nl[0], nl[1])
+    assert float(same.float().mean()) > 0.99
+    assert rel_l2(res.out.float().cpu()[same], want[same]) <= BF16_REL_L2
