@@ -86,7 +86,7 @@ struct Vec8<float> {
   }
 };
 
-template <typename T>
+template <typename T, bool kLn, int kVec>
 __global__ void __launch_bounds__(kCombineThreads)
 combine_kernel(const T* __restrict__ ybuf, const int* __restrict__ mapping, const float* __restrict__ score,
                const T* __restrict__ residual, float ff_scale, int S, int D, int top_k, T* __restrict__ out,
@@ -94,13 +94,13 @@ combine_kernel(const T* __restrict__ ybuf, const int* __restrict__ mapping, cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = kCombineThreads / 32;
-  if (ln_gamma != nullptr) {
+  if constexpr (kLn) {
     // norm_final fused behind the residual add (fmoe_transformer.py:164-166): the warp holds the whole row
     const int nvec = D >> 3;
     for (int s = blockIdx.x * warps_per_block + warp; s < S; s += gridDim.x * warps_per_block) {
-      float o[kLnMaxVec][8];
+      float o[kVec][8];
 #pragma unroll
-      for (int k = 0; k < kLnMaxVec; ++k) {
+      for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
         if (v >= nvec) continue;
         float acc[8];
@@ -128,9 +128,9 @@ combine_kernel(const T* __restrict__ ybuf, const int* __restrict__ mapping, cons
           for (int i = 0; i < 8; ++i) o[k][i] = ff_scale * acc[i];
         }
       }
-      ln_row_registers(o, D, lane, ln_gamma, ln_beta, ln_eps);
+      ln_row_registers<kVec>(o, D, lane, ln_gamma, ln_beta, ln_eps);
 #pragma unroll
-      for (int k = 0; k < kLnMaxVec; ++k) {
+      for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
         if (v >= nvec) continue;
         Vec8<T> ov;
@@ -205,10 +205,19 @@ cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* sc
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = (S + kCombineThreads / 32 - 1) / (kCombineThreads / 32);
   if (grid > sms * 8) grid = sms * 8;
-#define B200MOE_COMBINE(T)                                                                                     \
-  combine_kernel<T><<<grid, kCombineThreads, 0, stream>>>(static_cast<const T*>(ybuf), mapping, score,         \
-                                                          static_cast<const T*>(residual), ff_scale, S, D,     \
-                                                          top_k, static_cast<T*>(out), ln_gamma, ln_beta, ln_eps)
+#define B200MOE_COMBINE_LN(T, LN, VEC)                                                                              \
+  combine_kernel<T, LN, VEC><<<grid, kCombineThreads, 0, stream>>>(static_cast<const T*>(ybuf), mapping, score,           \
+                                                              static_cast<const T*>(residual), ff_scale, S, D,      \
+                                                              top_k, static_cast<T*>(out), ln_gamma, ln_beta, ln_eps)
+#define B200MOE_COMBINE(T)                 \
+  do {                                     \
+    if (ln_gamma == nullptr)               \
+      B200MOE_COMBINE_LN(T, false, 1);     \
+    else if (D <= 512)                     \
+      B200MOE_COMBINE_LN(T, true, 2);      \
+    else                                   \
+      B200MOE_COMBINE_LN(T, true, 4);      \
+  } while (0)
   switch (dtype) {
     case B200MOE_F32:
       B200MOE_COMBINE(float);
@@ -223,6 +232,7 @@ cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* sc
       return cudaErrorInvalidValue;
   }
 #undef B200MOE_COMBINE
+#undef B200MOE_COMBINE_LN
   count_launch();
   return cudaGetLastError();
 }

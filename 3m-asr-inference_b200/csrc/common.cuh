@@ -236,7 +236,7 @@ void count_launch(int n = 1);
 int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN, bit 3 LayerNorm: kernel launched with the PDL attribute
 int pdl_trigger();   // same bits: kernel executes griddepcontrol.launch_dependents at its start
 int prefetch_mode();
-int ln_fuse_mode(); // B200MOE_LN_FUSE: 1 (default) = the block's norm_ff runs inside the route kernel, 0 = as a row pass in front
+int ln_fuse_mode(); // B200MOE_LN_FUSE: 1 = the block's norm_ff runs inside the route kernel, 0 (default) = as a row pass in front
 int route_mode();   // B200MOE_ROUTE: 1 (default) = fused gate + dispatch kernel for small batches, 0 = separate kernels
 constexpr int kPdlGate = 1, kPdlDispatch = 2, kPdlFfn = 4, kPdlLn = 8;
 

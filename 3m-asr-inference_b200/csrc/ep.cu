@@ -46,6 +46,8 @@ __device__ __forceinline__ void bf16x8_to_f(const uint4& v, float (&o)[8]) {
 
 // One warp per token row.  ret_y was written by other GPUs during this kernel's lifetime at the latest, so it is read
 // with ordinary (L2-coherent) loads after the acquire, never through the read-only path.
+// kLn: norm_final fused in (own instantiation: holding a whole row per warp triples the registers)
+template <bool kLn, int kVec>
 __global__ void __launch_bounds__(256)
 ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float* __restrict__ score,
                   const bf16* __restrict__ residual, float ff_scale, int S, int D, int top_k, bf16* __restrict__ out,
@@ -68,13 +70,13 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
   const bf16* ret_y = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.ret_y);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x / 32;
-  if (ln_gamma != nullptr) {
+  if constexpr (kLn) {
     // norm_final fused behind the residual add (fmoe_transformer.py:164-166): the warp holds the whole row
     const int nvec = D >> 3;
     for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
-      float o[kLnMaxVec][8];
+      float o[kVec][8];
 #pragma unroll
-      for (int k = 0; k < kLnMaxVec; ++k) {
+      for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
         if (v >= nvec) continue;
         float acc[8];
@@ -100,9 +102,9 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
           for (int i = 0; i < 8; ++i) o[k][i] = ff_scale * acc[i];
         }
       }
-      ln_row_registers(o, D, lane, ln_gamma, ln_beta, ln_eps);
+      ln_row_registers<kVec>(o, D, lane, ln_gamma, ln_beta, ln_eps);
 #pragma unroll
-      for (int k = 0; k < kLnMaxVec; ++k) {
+      for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
         if (v >= nvec) continue;
         uint32_t w[4];
@@ -170,7 +172,10 @@ cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float
   int blocks = (S + 7) / 8;
   if (blocks < 1) blocks = 1;  // the wait on the return flags must happen even for a rank without tokens
   if (blocks > 4 * 148) blocks = 4 * 148;
-  cudaError_t e = launch_kernel(ep_combine_kernel, dim3(blocks), dim3(256), 0, stream, kPdlFfn, ep, mapping, score,
+  cudaError_t e = launch_kernel(ln_gamma == nullptr ? ep_combine_kernel<false, 1>
+                                                     : (D <= 512 ? ep_combine_kernel<true, 2> : ep_combine_kernel<true, kLnMaxVec>),
+                                dim3(blocks),
+                                dim3(256), 0, stream, kPdlFfn, ep, mapping, score,
                                 static_cast<const bf16*>(residual), ff_scale, S, D, top_k, static_cast<bf16*>(out),
                                 ln_gamma, ln_beta, ln_eps);
   count_launch();

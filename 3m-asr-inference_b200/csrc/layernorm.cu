@@ -70,7 +70,7 @@ __device__ __forceinline__ void store8<float>(float* p, const float (&o)[8]) {
   reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
-template <typename T>
+template <typename T, int kVec>
 __global__ void __launch_bounds__(kLnThreads)
 layernorm_rows_kernel(const T* in, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int S,
                       int D, T* out) {
@@ -82,15 +82,15 @@ layernorm_rows_kernel(const T* in, const float* __restrict__ gamma, const float*
   const int wpb = kLnThreads / 32;
   const int nvec = D >> 3;
   for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
-    float v[kLnMaxVec][8];
+    float v[kVec][8];
     const T* src = in + static_cast<size_t>(s) * D;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k)
+    for (int k = 0; k < kVec; ++k)
       if (k * 32 + lane < nvec) load8<T>(src + (k * 32 + lane) * 8, v[k]);
-    ln_row_registers(v, D, lane, gamma, beta, eps);
+    ln_row_registers<kVec>(v, D, lane, gamma, beta, eps);
     T* dst = out + static_cast<size_t>(s) * D;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k)
+    for (int k = 0; k < kVec; ++k)
       if (k * 32 + lane < nvec) store8<T>(dst + (k * 32 + lane) * 8, v[k]);
   }
 }
@@ -106,22 +106,25 @@ cudaError_t launch_layernorm(const void* in, const float* gamma, const float* be
   int grid = (S + kLnThreads / 32 - 1) / (kLnThreads / 32);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
   cudaError_t e;
+#define B200MOE_LN_LAUNCH(T)                                                                                          \
+  e = D <= 512 ? launch_kernel(layernorm_rows_kernel<T, 2>, dim3(grid), dim3(kLnThreads), 0, stream, kPdlLn,           \
+                               static_cast<const T*>(in), gamma, beta, eps, S, D, static_cast<T*>(out))                \
+               : launch_kernel(layernorm_rows_kernel<T, kLnMaxVec>, dim3(grid), dim3(kLnThreads), 0, stream, kPdlLn,   \
+                               static_cast<const T*>(in), gamma, beta, eps, S, D, static_cast<T*>(out))
   switch (dtype) {
     case B200MOE_F32:
-      e = launch_kernel(layernorm_rows_kernel<float>, dim3(grid), dim3(kLnThreads), 0, stream, kPdlLn,
-                        static_cast<const float*>(in), gamma, beta, eps, S, D, static_cast<float*>(out));
+      B200MOE_LN_LAUNCH(float);
       break;
     case B200MOE_F16:
-      e = launch_kernel(layernorm_rows_kernel<__half>, dim3(grid), dim3(kLnThreads), 0, stream, kPdlLn,
-                        static_cast<const __half*>(in), gamma, beta, eps, S, D, static_cast<__half*>(out));
+      B200MOE_LN_LAUNCH(__half);
       break;
     case B200MOE_BF16:
-      e = launch_kernel(layernorm_rows_kernel<bf16>, dim3(grid), dim3(kLnThreads), 0, stream, kPdlLn,
-                        static_cast<const bf16*>(in), gamma, beta, eps, S, D, static_cast<bf16*>(out));
+      B200MOE_LN_LAUNCH(bf16);
       break;
     default:
       return cudaErrorInvalidValue;
   }
+#undef B200MOE_LN_LAUNCH
   count_launch();
   return e;
 }

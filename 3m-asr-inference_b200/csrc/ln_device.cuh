@@ -92,13 +92,49 @@ __device__ __forceinline__ void ln_rows_registers(float (&v)[R][kVec][8], int D,
   }
 }
 
-// one row, up to kLnMaxVec vectors per lane (the row-pass kernels)
-__device__ __forceinline__ void ln_row_registers(float (&v)[kLnMaxVec][8], int D, int lane,
-                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                 float eps) {
-  LnAffine<kLnMaxVec> a;
-  a.load(gamma, beta, D, lane);
-  ln_rows_registers<kLnMaxVec, 1>(reinterpret_cast<float (&)[1][kLnMaxVec][8]>(v), D, lane, a, eps);
+// One row, kVec vectors per lane (the row-pass and combine kernels: kVec = 2 for D <= 512, else kLnMaxVec).  gamma / beta
+// are fetched when they are applied, not held across the reductions: these kernels want many resident warps, not ILP.
+template <int kVec>
+__device__ __forceinline__ void ln_row_registers(float (&v)[kVec][8], int D, int lane, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float eps) {
+  const int nvec = D >> 3;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kVec; ++k)
+    if (k * 32 + lane < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[k][i];
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  s *= inv_d;  // mean
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kVec; ++k)
+    if (k * 32 + lane < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[k][i] - s;
+        q = fmaf(d, d, q);
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * inv_d + eps);
+#pragma unroll
+  for (int k = 0; k < kVec; ++k)
+    if (k * 32 + lane < nvec) {
+      const int f0 = (k * 32 + lane) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + f0));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + f0) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + f0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + f0) + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[k][i] = fmaf((v[k][i] - s) * rstd, g[i], b[i]);
+    }
 }
 
 }  // namespace b200moe

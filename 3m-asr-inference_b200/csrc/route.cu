@@ -578,7 +578,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                 v[k][2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
               }
             }
-          ln_row_registers(v, p.D, lane, p.ln_gamma, p.ln_beta, p.ln_eps);
+          ln_row_registers<kLnMaxVec>(v, p.D, lane, p.ln_gamma, p.ln_beta, p.ln_eps);
 #pragma unroll
           for (int k = 0; k < kLnMaxVec; ++k)
             if (k * 32 + lane < nvec) {

@@ -254,11 +254,12 @@ int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int
  * semantics: biased variance over the D features, y = (x - mean) * rsqrt(var + eps) * gamma + beta, statistics in fp32,
  * the normalised input rounded to `dtype` (what the reference's LayerNorm plugin hands to the next graph layer).
  * D: multiple of 8, at most 1024.  ws: b200moe_block_workspace_bytes (the layer's workspace + one [S, D] buffer).
- * Where the norms run: norm_ff inside the fused gate + dispatch kernel for bf16 batches of up to 2 * 32 * 148 tokens
- * (the 32 token rows of a tile are normalised in shared memory between the TMA that fetches them and the router MMAs;
- * the scattered rows are the normalised ones, `x` itself stays as the residual), otherwise as a row pass in front;
- * norm_final inside the combine kernel when there is one (top_k > 1, expert parallelism), otherwise as a row pass over
- * `out` behind the expert kernel.  All of them share one register-level routine and give identical bits. */
+ * Where the norms run: norm_ff as a row pass in front of the gate (default), or -- b200moe_config("ln_fuse", 1), bf16
+ * batches of up to 2 * 32 * 148 tokens -- inside the fused gate + dispatch kernel (the 32 token rows of a tile are
+ * normalised in shared memory between the TMA that fetches them and the router MMAs; the scattered rows are the
+ * normalised ones, `x` itself stays as the residual; measured ~1 us slower per block than the row pass); norm_final
+ * inside the combine kernel when there is one (top_k > 1, expert parallelism), otherwise as a row pass over `out`
+ * behind the expert kernel.  All of them share one register-level routine and give identical bits. */
 typedef struct b200moe_block_args {
   b200moe_layer_args layer;
   const float* norm_ff_gamma;
@@ -281,8 +282,8 @@ int b200moe_layernorm(const void* in, const float* gamma, const float* beta, flo
 
 /* Run-time tunables (each also has an environment default, B200MOE_<KEY>): "route" 1/0 fused gate + dispatch kernel for
  * small batches; "pdl" / "pdl_trig" bit masks (1 gate, 2 dispatch, 4 expert FFN, 8 LayerNorm) for programmatic dependent launch;
- * "prefetch" 0/1/2 L2 prefetch of the expert weights from the gate kernel; "ln_fuse" 1/0 the block's norm_ff inside the
- * fused gate + dispatch kernel or as a row pass in front.  Results do not depend on any of them. */
+ * "prefetch" 0/1/2 L2 prefetch of the expert weights from the gate kernel; "ln_fuse" 0/1 the block's norm_ff as a
+ * row pass in front (default) or inside the fused gate + dispatch kernel.  Results do not depend on any of them. */
 int b200moe_config(const char* key, int value);
 
 /* Optional per-stage device timing with CUDA events around each stage of b200moe_forward (eager launches only, not
