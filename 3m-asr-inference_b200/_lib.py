@@ -36,7 +36,7 @@ class LayerArgs(C.Structure):
 class BlockArgs(C.Structure):
     """struct b200moe_block_args"""
     _fields_ = [("layer", LayerArgs), ("norm_ff_gamma", _vp), ("norm_ff_beta", _vp), ("norm_final_gamma", _vp),
-                ("norm_final_beta", _vp), ("eps", _f)]
+                ("norm_final_beta", _vp), ("eps", _f), ("Wr_packed_ln", _vp)]
 
 
 # name -> (restype, argtypes); every symbol include/b200moe.h declares
@@ -73,6 +73,8 @@ SIGNATURES = {
     "b200moe_ep_forward": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _vp]),
     "b200moe_ep_forward_stages": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _i, _vp]),
     "b200moe_ep_status": (_i, [_vp, C.POINTER(_i)]),
+    "b200moe_router_ln_pack_bytes": (_sz, [_i]),
+    "b200moe_pack_router_ln": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b200moe_block_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "b200moe_block_forward": (_i, [C.POINTER(BlockArgs), _vp, _sz, _vp]),
     "b200moe_ep_block_workspace_bytes": (_sz, [_vp, _i]),

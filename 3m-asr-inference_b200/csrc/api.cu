@@ -109,10 +109,9 @@ int knob(std::atomic<int>& v, const char* env, int dflt) {
 int pdl_mask() { return knob(g_pdl, "B200MOE_PDL", kPdlGate | kPdlFfn | kPdlLn); }
 int pdl_trigger() { return knob(g_pdl_trig, "B200MOE_PDL_TRIG", kPdlFfn); }
 int route_mode() { return knob(g_route, "B200MOE_ROUTE", 1); }
-// norm_ff inside the route kernel is kept as an option but is not the default: measured on cfg3 it costs 39.2 us per
-// block against 38.0 us with the row pass in front (60.6 vs 59.7 us on 2 GPUs) -- the LayerNorm sits between the arrival
-// of the x tile and the router MMAs, while a separate kernel overlaps the route kernel's constant-only prologue.
-int ln_fuse_mode() { return knob(g_ln_fuse, "B200MOE_LN_FUSE", 0); }
+// 1: when the caller supplies the pre-scaled router (b200moe_block_args.Wr_packed_ln) the block's norm_ff is folded into
+// the route kernel; 0: always the row pass in front.
+int ln_fuse_mode() { return knob(g_ln_fuse, "B200MOE_LN_FUSE", 1); }
 
 int prefetch_mode() { return knob(g_prefetch, "B200MOE_PREFETCH", 0); }
 
@@ -233,6 +232,18 @@ int b200moe_gate(const void* x, const void* embed, const float* Wr, const float*
 
 size_t b200moe_router_pack_bytes(int R) { return R > 0 ? router_pack_bytes(R) : 0; }
 
+size_t b200moe_router_ln_pack_bytes(int R) { return R > 0 ? router_ln_pack_bytes(R) : 0; }
+
+int b200moe_pack_router_ln(const float* Wr, int R, int E, int D, const float* gamma, const float* beta, void* packed,
+                           cudaStream_t stream) {
+  if (!Wr || !packed || !gamma || !beta) return fail(B200MOE_ERR_ARG, "pack_router_ln: null pointer");
+  if (E < 1 || E > 32 || R < 1 || D < 1 || D > R)
+    return fail(B200MOE_ERR_ARG, "pack_router_ln: needs 1 <= E <= 32 and 1 <= D <= R (got E=%d, R=%d, D=%d)", E, R, D);
+  cudaError_t e = launch_pack_router_ln(Wr, R, E, D, gamma, beta, packed, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pack_router_ln");
+  return B200MOE_OK;
+}
+
 int b200moe_pack_router(const float* Wr, int R, int E, void* packed, cudaStream_t stream) {
   if (!Wr || !packed) return fail(B200MOE_ERR_ARG, "pack_router: null pointer");
   if (E < 1 || E > 32 || R < 1) return fail(B200MOE_ERR_ARG, "pack_router: needs 1 <= E <= 32 (got E=%d, R=%d)", E, R);
@@ -344,7 +355,12 @@ struct LnFuse {
   const float* gamma;
   const float* beta;
   float eps;
+  const void* packed;  // norm_ff only: the pre-scaled router of b200moe_pack_router_ln (replaces Wr_packed)
 };
+
+const float* ln_consts(const LnFuse* ln, int R) {
+  return reinterpret_cast<const float*>(static_cast<const uint8_t*>(ln->packed) + static_cast<size_t>(64) * R * sizeof(bf16));
+}
 
 bool takes_route_kernel(const b200moe_layer_args* a) {
   const int Demb = a->embed ? a->Demb : 0;
@@ -408,10 +424,10 @@ static int forward_impl(const b200moe_layer_args* a, void* ws, size_t ws_bytes, 
   if (route) {
     // small batch: gate and dispatch as one kernel (grid barrier instead of a kernel boundary)
     StageScope t(0, stream);
-    e = launch_route(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->gate_mode,
-                     a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf,
-                     fused ? a->out : nullptr, a->residual, stream, nullptr, false, ln ? ln->gamma : nullptr,
-                     ln ? ln->beta : nullptr, ln ? ln->eps : 0.0f);
+    e = launch_route(a->x, a->embed, ln ? ln->packed : a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E,
+                     a->gate_mode, a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out,
+                     w.xbuf, fused ? a->out : nullptr, a->residual, stream, nullptr, false, ln ? ln->gamma : nullptr,
+                     ln ? ln->beta : nullptr, ln ? ln->eps : 0.0f, ln ? ln_consts(ln, a->D + Demb) : nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "forward/route");
   } else {
   {
@@ -643,9 +659,10 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
   const bool route = tc_gate && route_supported(S, a->D, Demb, a->E, a->top_k, a->dtype);
   if (route && (stages & 1)) {
     StageScope t(0, stream);
-    e = launch_route(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->gate_mode, 0, idx,
-                     score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf, nullptr, nullptr, stream, &ep,
-                     fold_wait, ln_in ? ln_in->gamma : nullptr, ln_in ? ln_in->beta : nullptr, ln_in ? ln_in->eps : 0.0f);
+    e = launch_route(a->x, a->embed, ln_in ? ln_in->packed : a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb,
+                     a->E, a->gate_mode, 0, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf, nullptr,
+                     nullptr, stream, &ep, fold_wait, ln_in ? ln_in->gamma : nullptr, ln_in ? ln_in->beta : nullptr,
+                     ln_in ? ln_in->eps : 0.0f, ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "ep_forward/route");
   }
   if (S > 0 && (stages & 1) && !route) {
@@ -932,9 +949,10 @@ int b200moe_block_forward(const b200moe_block_args* b, void* ws, size_t ws_bytes
   const size_t layer_ws = b200moe_workspace_bytes(S, a.E, a.D, a.H, a.top_k);
   int rc = plan_block(b, layer_ws, ws, ws_bytes, &plan, "block_forward");
   if (rc != B200MOE_OK) return rc;
-  const LnFuse lin{b->norm_ff_gamma, b->norm_ff_beta, b->eps}, lout{b->norm_final_gamma, b->norm_final_beta, b->eps};
+  const LnFuse lin{b->norm_ff_gamma, b->norm_ff_beta, b->eps, b->Wr_packed_ln};
+  const LnFuse lout{b->norm_final_gamma, b->norm_final_beta, b->eps, nullptr};
   // small bf16 batches: the route kernel normalises the rows it has just fetched; otherwise a row pass in front
-  const bool fuse_in = plan.xn != nullptr && ln_fuse_mode() != 0 && takes_route_kernel(&a);
+  const bool fuse_in = plan.xn != nullptr && ln_fuse_mode() != 0 && b->Wr_packed_ln != nullptr && takes_route_kernel(&a);
   if (fuse_in) plan.layer.x = a.x;
   if (plan.xn && !fuse_in) {
     if (!a.x) return fail(B200MOE_ERR_ARG, "block_forward: null pointer");
@@ -956,8 +974,9 @@ int b200moe_ep_block_forward(b200moe_ep_ctx* c, const b200moe_block_args* b, voi
   const size_t layer_ws = b200moe_ep_workspace_bytes(c, a.H);
   int rc = plan_block(b, layer_ws, ws, ws_bytes, &plan, "ep_block_forward");
   if (rc != B200MOE_OK) return rc;
-  const LnFuse lin{b->norm_ff_gamma, b->norm_ff_beta, b->eps}, lout{b->norm_final_gamma, b->norm_final_beta, b->eps};
-  const bool fuse_in = plan.xn != nullptr && ln_fuse_mode() != 0 && takes_route_kernel(&a);
+  const LnFuse lin{b->norm_ff_gamma, b->norm_ff_beta, b->eps, b->Wr_packed_ln};
+  const LnFuse lout{b->norm_final_gamma, b->norm_final_beta, b->eps, nullptr};
+  const bool fuse_in = plan.xn != nullptr && ln_fuse_mode() != 0 && b->Wr_packed_ln != nullptr && takes_route_kernel(&a);
   if (fuse_in) plan.layer.x = a.x;
   if (plan.xn && !fuse_in) {
     if (!a.x) return fail(B200MOE_ERR_ARG, "ep_block_forward: null pointer");

@@ -168,7 +168,12 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream,
                          const EpPeers* ep = nullptr, bool ep_fold_wait = false, const float* ln_gamma = nullptr,
-                         const float* ln_beta = nullptr, float ln_eps = 0.0f);
+                         const float* ln_beta = nullptr, float ln_eps = 0.0f, const float* ln_c = nullptr);
+// Router packed for the route kernel's fused norm_ff: like launch_pack_router, with the x rows (k >= R - D) scaled by
+// gamma, followed by c1[32] = gamma^T Wr_x and c0[32] = beta^T Wr_x (fp32).  router_ln_pack_bytes(R) bytes.
+size_t router_ln_pack_bytes(int R);
+cudaError_t launch_pack_router_ln(const float* Wr, int R, int E, int D, const float* gamma, const float* beta,
+                                  void* packed, cudaStream_t stream);
 
 // ffn.cu
 struct FfnLaunch {
@@ -236,7 +241,8 @@ void count_launch(int n = 1);
 int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN, bit 3 LayerNorm: kernel launched with the PDL attribute
 int pdl_trigger();   // same bits: kernel executes griddepcontrol.launch_dependents at its start
 int prefetch_mode();
-int ln_fuse_mode(); // B200MOE_LN_FUSE: 1 = the block's norm_ff runs inside the route kernel, 0 (default) = as a row pass in front
+int ln_fuse_mode(); // B200MOE_LN_FUSE: 1 (default) = the block's norm_ff is folded into the route kernel when the caller supplies
+                    // the pre-scaled router, 0 = always a row pass in front
 int route_mode();   // B200MOE_ROUTE: 1 (default) = fused gate + dispatch kernel for small batches, 0 = separate kernels
 constexpr int kPdlGate = 1, kPdlDispatch = 2, kPdlFfn = 4, kPdlLn = 8;
 

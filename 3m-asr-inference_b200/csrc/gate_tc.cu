@@ -288,7 +288,59 @@ pack_router_kernel(const float* __restrict__ Wr, int R, int E, bf16* __restrict_
   }
 }
 
+// norm_ff folded into the router (route.cu, kLn): rows k >= R - D of Wr are scaled by gamma[k - (R - D)] before the hi / lo
+// split; block 0 then appends c1[e] = sum_k (hi + lo)[k, e] over those rows (what the tensor cores will actually multiply)
+// and c0[e] = sum_k beta[k] * Wr_x[k, e].
+__global__ void __launch_bounds__(256)
+pack_router_ln_kernel(const float* __restrict__ Wr, int R, int E, int D, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, bf16* __restrict__ packed, float* __restrict__ c) {
+  const int n = 64 * R;
+  const int kx = R - D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int row = i / R;
+    const int k = i - row * R;
+    const int e = row & 31;
+    float v = 0.0f;
+    if (e < E) {
+      float w = Wr[static_cast<size_t>(k) * E + e];
+      if (k >= kx) w *= gamma[k - kx];
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      v = row < 32 ? hi : (w - hi);
+    }
+    packed[i] = __float2bfloat16_rn(v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 64) {
+    const int e = threadIdx.x & 31;
+    double acc = 0.0;
+    if (e < E) {
+      for (int k = kx; k < R; ++k) {
+        const float w0 = Wr[static_cast<size_t>(k) * E + e];
+        if (threadIdx.x < 32) {
+          const float w = w0 * gamma[k - kx];
+          const float hi = __bfloat162float(__float2bfloat16_rn(w));
+          const float lo = __bfloat162float(__float2bfloat16_rn(w - hi));
+          acc += static_cast<double>(hi) + static_cast<double>(lo);
+        } else {
+          acc += static_cast<double>(beta[k - kx]) * static_cast<double>(w0);
+        }
+      }
+    }
+    c[threadIdx.x] = static_cast<float>(acc);  // [0, 32): c1, [32, 64): c0
+  }
+}
+
 }  // namespace
+
+size_t router_ln_pack_bytes(int R) { return static_cast<size_t>(64) * R * sizeof(bf16) + 64 * sizeof(float); }
+
+cudaError_t launch_pack_router_ln(const float* Wr, int R, int E, int D, const float* gamma, const float* beta,
+                                  void* packed, cudaStream_t stream) {
+  if (E > 32 || R < 1 || D < 1 || D > R) return cudaErrorInvalidValue;
+  float* c = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + static_cast<size_t>(64) * R * sizeof(bf16));
+  pack_router_ln_kernel<<<64, 256, 0, stream>>>(Wr, R, E, D, gamma, beta, static_cast<bf16*>(packed), c);
+  count_launch();
+  return cudaGetLastError();
+}
 
 bool gate_tc_supported(int D, int Demb, int E, int top_k, int dtype) {
   return dtype == B200MOE_BF16 && E <= 32 && top_k <= 8 && D % kBlkK == 0 && Demb % kBlkK == 0 && D > 0;

@@ -41,37 +41,37 @@ struct LnAffine {
 };
 
 // v[r][k][i]: element (k * 32 + lane) * 8 + i of row r; vectors with (k * 32 + lane) * 8 >= D are ignored.
+// Statistics only: mean[r] and rstd[r] = rsqrt(var + eps), the same on every lane.
 template <int kVec, int R>
-__device__ __forceinline__ void ln_rows_registers(float (&v)[R][kVec][8], int D, int lane, const LnAffine<kVec>& a,
-                                                  float eps) {
+__device__ __forceinline__ void ln_rows_stats(const float (&v)[R][kVec][8], int D, int lane, float eps, float (&mean)[R],
+                                              float (&rstd)[R]) {
   const int nvec = D >> 3;
   const float inv_d = 1.0f / static_cast<float>(D);
-  float s[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    s[r] = 0.0f;
+    mean[r] = 0.0f;
 #pragma unroll
     for (int k = 0; k < kVec; ++k)
       if (k * 32 + lane < nvec) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[r] += v[r][k][i];
+        for (int i = 0; i < 8; ++i) mean[r] += v[r][k][i];
       }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+    for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
   float q[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    s[r] *= inv_d;  // mean
+    mean[r] *= inv_d;
     q[r] = 0.0f;
 #pragma unroll
     for (int k = 0; k < kVec; ++k)
       if (k * 32 + lane < nvec) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float d = v[r][k][i] - s[r];
+          const float d = v[r][k][i] - mean[r];
           q[r] = fmaf(d, d, q[r]);
         }
       }
@@ -81,13 +81,27 @@ __device__ __forceinline__ void ln_rows_registers(float (&v)[R][kVec][8], int D,
 #pragma unroll
     for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
 #pragma unroll
+  for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(q[r] * inv_d + eps);
+}
+
+// one element: THE expression every kernel uses, so that all of them agree to the bit
+__device__ __forceinline__ float ln_apply(float v, float mean, float rstd, float g, float b) {
+  return fmaf((v - mean) * rstd, g, b);
+}
+
+template <int kVec, int R>
+__device__ __forceinline__ void ln_rows_registers(float (&v)[R][kVec][8], int D, int lane, const LnAffine<kVec>& a,
+                                                  float eps) {
+  const int nvec = D >> 3;
+  float mean[R], rstd[R];
+  ln_rows_stats<kVec, R>(v, D, lane, eps, mean, rstd);
+#pragma unroll
   for (int r = 0; r < R; ++r) {
-    const float rstd = rsqrtf(q[r] * inv_d + eps);
 #pragma unroll
     for (int k = 0; k < kVec; ++k)
       if (k * 32 + lane < nvec) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[r][k][i] = fmaf((v[r][k][i] - s[r]) * rstd, a.g[k][i], a.b[k][i]);
+        for (int i = 0; i < 8; ++i) v[r][k][i] = ln_apply(v[r][k][i], mean[r], rstd[r], a.g[k][i], a.b[k][i]);
       }
   }
 }
@@ -98,30 +112,8 @@ template <int kVec>
 __device__ __forceinline__ void ln_row_registers(float (&v)[kVec][8], int D, int lane, const float* __restrict__ gamma,
                                                  const float* __restrict__ beta, float eps) {
   const int nvec = D >> 3;
-  const float inv_d = 1.0f / static_cast<float>(D);
-  float s = 0.0f;
-#pragma unroll
-  for (int k = 0; k < kVec; ++k)
-    if (k * 32 + lane < nvec) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[k][i];
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  s *= inv_d;  // mean
-  float q = 0.0f;
-#pragma unroll
-  for (int k = 0; k < kVec; ++k)
-    if (k * 32 + lane < nvec) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = v[k][i] - s;
-        q = fmaf(d, d, q);
-      }
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q * inv_d + eps);
+  float mean[1], rstd[1];
+  ln_rows_stats<kVec, 1>(reinterpret_cast<const float (&)[1][kVec][8]>(v), D, lane, eps, mean, rstd);
 #pragma unroll
   for (int k = 0; k < kVec; ++k)
     if (k * 32 + lane < nvec) {
@@ -133,7 +125,7 @@ __device__ __forceinline__ void ln_row_registers(float (&v)[kVec][8], int D, int
       const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[k][i] = fmaf((v[k][i] - s) * rstd, g[i], b[i]);
+      for (int i = 0; i < 8; ++i) v[k][i] = ln_apply(v[k][i], mean[0], rstd[0], g[i], b[i]);
     }
 }
 

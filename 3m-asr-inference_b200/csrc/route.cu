@@ -48,15 +48,24 @@ constexpr int kRThreads = 256;
 constexpr uint32_t kRTmemCols = 64;         // 2 accumulator buffers x 32 token columns
 constexpr int kLnWarps = 4;                 // warps 2, 3, 6, 7 normalise the token rows when norm_ff is fused in
 
+// norm_ff fused into the router ALGEBRAICALLY (kLn).  With mu, r the mean and reciprocal standard deviation of a token row,
+//   LN(x) . Wr_x = r * ( x . W' - mu * c1 ) + c0,    W' = diag(gamma) Wr_x,  c1 = gamma^T Wr_x,  c0 = beta^T Wr_x,
+// so the router MMAs run on the RAW rows against a pre-scaled router (b200moe_pack_router_ln) the moment the tile lands,
+// into an accumulator of their own, while four otherwise idle warps compute mu and r from the same tile; the arg-max
+// epilogue combines the embed accumulator, the x accumulator, mu, r, c1 and c0.  Normalising the rows in place in front of
+// the MMAs instead put ~2.8 us of arithmetic (4 warps, 16 K elements) on the critical path of every tile.
+// The rows the experts consume are normalised (and rounded to bf16) in place by the same warps once the MMAs have read
+// the tile, off the critical path (CTAs with a second tile re-read and normalise the rows from global memory instead).
+//
 // The x operand in the ring: [k-block][32 rows][64 bf16], 128-byte swizzle (the 16-byte chunk c of row r sits at chunk
-// c ^ (r & 7)).  A warp normalises kRowsPerLnWarp rows together; lane l owns the 8-element vectors l and l + 32 of each
-// row (D <= 512 here), exactly like layernorm_rows_kernel, so both produce the same bits.
+// c ^ (r & 7)).  Lane l owns the 8-element vectors l and l + 32 of a row (D <= 512 here) exactly like
+// layernorm_rows_kernel, so the statistics have the same bits.
 constexpr int kRowsPerLnWarp = kTok / kLnWarps;  // 8
-constexpr int kLnBatch = 4;                       // rows a warp normalises together (registers: 16 floats per row)
+constexpr int kLnBatch = 4;                       // rows a warp reduces together
 constexpr int kRouteLnVec = 2;
 
-__device__ __forceinline__ void ln_rows_in_ring(uint8_t* sx, int r0, int D, int lane, const LnAffine<kRouteLnVec>& aff,
-                                                float eps) {
+__device__ __forceinline__ void ln_stats_in_ring(const uint8_t* sx, int r0, int D, int lane, float eps, float* s_mu,
+                                                 float* s_rs) {
   const int nvec = D >> 3;
 #pragma unroll 1
   for (int rb = r0; rb < r0 + kRowsPerLnWarp; rb += kLnBatch) {
@@ -79,23 +88,48 @@ __device__ __forceinline__ void ln_rows_in_ring(uint8_t* sx, int r0, int D, int 
         }
       }
     }
-    ln_rows_registers<kRouteLnVec, kLnBatch>(v, D, lane, aff, eps);
+    float mean[kLnBatch], rstd[kLnBatch];
+    ln_rows_stats<kRouteLnVec, kLnBatch>(v, D, lane, eps, mean, rstd);
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < kLnBatch; ++i) {
-      const int r = rb + i;
+      for (int i = 0; i < kLnBatch; ++i) {
+        s_mu[rb + i] = mean[i];
+        s_rs[rb + i] = rstd[i];
+      }
+    }
+  }
+}
+
+// Normalise kRowsPerLnWarp rows in place in the ring (statistics already known); same expression as everywhere else.
+__device__ __forceinline__ void ln_apply_in_ring(uint8_t* sx, int r0, int D, int lane, const float* s_mu,
+                                                 const float* s_rs, const float* s_gamma, const float* s_beta) {
+  const int nvec = D >> 3;
+#pragma unroll 2
+  for (int i = 0; i < kRowsPerLnWarp; ++i) {
+    const int r = r0 + i;
+    const float mu = s_mu[r], rs = s_rs[r];
 #pragma unroll
-      for (int k = 0; k < kRouteLnVec; ++k) {
-        const int vec = k * 32 + lane;
-        if (vec < nvec) {
-          uint32_t w[4];
+    for (int k = 0; k < kRouteLnVec; ++k) {
+      const int vec = k * 32 + lane;
+      if (vec < nvec) {
+        uint4* cell = reinterpret_cast<uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4));
+        const uint4 w4 = *cell;
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + vec * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(s_gamma + vec * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_beta + vec * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_beta + vec * 8 + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t o[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 pk = __floats2bfloat162_rn(v[i][k][2 * j], v[i][k][2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&pk);
-          }
-          *reinterpret_cast<uint4*>(sx + (vec >> 3) * kRBBlk + r * 128 + (((vec & 7) ^ (r & 7)) << 4)) =
-              make_uint4(w[0], w[1], w[2], w[3]);
+        for (int u = 0; u < 4; ++u) {
+          const float v0 = ln_apply(__uint_as_float(w[u] << 16), mu, rs, g[2 * u], b[2 * u]);
+          const float v1 = ln_apply(__uint_as_float(w[u] & 0xffff0000u), mu, rs, g[2 * u + 1], b[2 * u + 1]);
+          __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+          o[u] = *reinterpret_cast<uint32_t*>(&pk);
         }
+        *cell = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
   }
@@ -131,10 +165,10 @@ struct RouteParams {
   unsigned long long* bar;
   unsigned nonce;
   int ep_fold_wait;
-  // norm_ff fused in front of the router (block call): the 32 token rows of a tile are normalised in shared memory
-  // between the TMA that brings them and the MMAs that read them; null = off
+  // norm_ff fused into the router (block call, route_kernel<.., kLn = true>); null = off
   const float* ln_gamma;
   const float* ln_beta;
+  const float* ln_c;   // c1[32], c0[32] behind the pre-scaled packed router (b200moe_pack_router_ln)
   float ln_eps;
   uint4* trace;  // debug timeline: 16 records per CTA {event, clock64 lo, hi, -}; slots 14 / 15 hold %globaltimer
 };
@@ -206,6 +240,15 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   int* s_exp = s_dst + 32;                                     // [32]
   int* s_part = s_exp + 32;                                    // [8][2][32]
   int* s_lastp = s_part + 512;                                 // [1]
+  // kLn only (the host sizes the allocation accordingly)
+  float* s_hx = reinterpret_cast<float*>(s_lastp + 6);         // [32][33]  x-part accumulator, hi rows (16 B aligned)
+  float* s_lx = s_hx + 32 * 33;                                // [32][33]  ... lo rows
+  float* s_mu = s_lx + 32 * 33;                                // [2][32]   per accumulator stage: row means
+  float* s_rs = s_mu + 64;                                     // [2][32]   ... reciprocal standard deviations
+  float* s_c1 = s_rs + 64;                                     // [32]
+  float* s_c0 = s_c1 + 32;                                     // [32]
+  float* s_gamma = s_c0 + 32;                                  // [D]
+  float* s_beta = s_gamma + kHalfKb * kRK;                     // [D]
 
   if (threadIdx.x == 0) {
     rtrace_sync(p, 14);
@@ -239,8 +282,19 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 2) ptx::tmem_alloc<kRTmemCols>(tmem_slot);
+  if (warp == 2) ptx::tmem_alloc<kLn ? 2 * kRTmemCols : kRTmemCols>(tmem_slot);
   if (warp == 3) s_br[lane] = (p.br != nullptr && lane < E) ? p.br[lane] : 0.0f;
+  if constexpr (kLn) {
+    // constants of the layer: may be fetched before the wait for the previous kernel
+    if (warp == 4) {
+      s_c1[lane] = p.ln_c[lane];
+      s_c0[lane] = p.ln_c[32 + lane];
+    }
+    for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
+      s_gamma[i] = p.ln_gamma[i];
+      s_beta[i] = p.ln_beta[i];
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -292,11 +346,12 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         const uint32_t aphase = (it >> 1) & 1;
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * kTok;
         for (int part = 0; part < n_parts; ++part) {
           const int nkb = (n_parts == 2 && part == 0) ? kb_e : kb_x;
+          // kLn: the x part accumulates on its own (columns 32..63 of the stage's 64), it is rescaled per token later
+          const bool own_acc = kLn && part == n_parts - 1;
+          const uint32_t tmem_d = tmem_base + as * (kLn ? 2 * kTok : kTok) + (own_acc ? kTok : 0);
           ptx::mbar_wait(full_bar(slot), phase);
-          if (kLn && part == n_parts - 1) ptx::mbar_wait(ln_bar(slot), phase);  // rows normalised
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + slot * kRSlot;
           for (int j = 0; j < nkb; ++j) {
@@ -305,7 +360,8 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             const uint64_t b_desc = ptx::make_kmajor_sw128_desc(sa + kRSlotA + j * kRBBlk);
 #pragma unroll
             for (int k = 0; k < kRK / 16; ++k)
-              ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (part | j | k) != 0 ? 1u : 0u);
+              ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc,
+                               ((own_acc ? 0 : part) | j | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(empty_bar(slot));
           if (part == n_parts - 1) ptx::umma_commit(tfull_bar(as));
@@ -317,23 +373,28 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       }
     }
   } else if (kLn && (warp == 2 || warp == 3 || warp >= 6)) {
-    // norm_ff (fmoe_transformer.py:145-148) on the tile's 32 token rows, in place in the ring, 8 rows per warp.  The
-    // MMAs of the x part and the row copies of phase 2 then read normalised rows; `x` in global memory stays as it is
-    // (it is the residual).
+    // norm_ff's statistics (fmoe_transformer.py:145-148) of the tile's 32 token rows, 8 rows per warp, while the MMAs run
     const int lw = (warp & 1) | ((warp >> 2) << 1);  // warps 2, 3, 6, 7 -> 0 .. 3
-    LnAffine<kRouteLnVec> aff;                       // constants: fetched while the tile is still on its way
-    aff.load(p.ln_gamma, p.ln_beta, p.D, lane);
     int slot = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       for (int part = 0; part < n_parts; ++part) {
         if (part == n_parts - 1) {
-          ptx::mbar_wait(full_bar(slot), phase);  // the TMA's bytes are there
-          uint8_t* sx = smem_raw + slot * kRSlot + kRSlotA;
-          ln_rows_in_ring(sx, lw * kRowsPerLnWarp, p.D, lane, aff, p.ln_eps);
-          ptx::fence_proxy_async_all();  // generic-proxy writes -> the tensor cores' (async proxy) reads
+          ptx::mbar_wait(full_bar(slot), phase);  // the TMA's bytes are there (a CTA has at most two tiles: the stage
+                                                  // it & 1 of s_mu / s_rs is not in use any more)
+          ln_stats_in_ring(smem_raw + slot * kRSlot + kRSlotA, lw * kRowsPerLnWarp, p.D, lane, p.ln_eps,
+                           s_mu + (it & 1) * 32, s_rs + (it & 1) * 32);
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(ln_bar(slot));
+          if (lane == 0) ptx::mbar_arrive(ln_bar(it & 1));  // release.cta: the softmax warp waits on it
+          if (n_tiles <= static_cast<int>(gridDim.x)) {
+            // One tile per CTA: the ring keeps the tile until phase 2 copies the rows out.  Once the MMAs have read
+            // it (accumulator complete), normalise the rows in place -- while the arg-max epilogue and the wait for the
+            // other CTAs' histograms run -- so that phase 2 is the plain copy it is without a LayerNorm.
+            ptx::mbar_wait(tfull_bar(it & 1), (it >> 1) & 1);
+            ln_apply_in_ring(smem_raw + slot * kRSlot + kRSlotA, lw * kRowsPerLnWarp, p.D, lane, s_mu + (it & 1) * 32,
+                             s_rs + (it & 1) * 32, s_gamma, s_beta);
+          }
         }
         if (++slot == kRSlots) {
           slot = 0;
@@ -354,13 +415,23 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       ptx::tc_fence_after();
       if (q == 0 && lane == 0 && it == 0) rtrace(p, 3);
       uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kTok, r);
-      ptx::tmem_ld_wait();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * (kLn ? 2 * kTok : kTok);
+      if (!kLn || n_parts == 2) {  // (kLn without an embed part: the first accumulator was never written)
+        ptx::tmem_ld_32x32b_x32(tacc, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dstm[lane * 33 + j] = __uint_as_float(r[j]);
+      }
+      if constexpr (kLn) {
+        float* dstx = q == 0 ? s_hx : s_lx;
+        ptx::tmem_ld_32x32b_x32(tacc + kTok, r);  // the x part's own accumulator
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dstx[lane * 33 + j] = __uint_as_float(r[j]);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dstm[lane * 33 + j] = __uint_as_float(r[j]);
       if (q == 0) s_hist[lane] = 0;
       ptx::named_bar_sync(1, 64);
       if (q == 0) {
@@ -369,10 +440,24 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         bool valid = tok < p.S;
         if (valid && p.x_len != nullptr) valid = (tok % p.T) < p.x_len[tok / p.T];
         float l[32];
+        if constexpr (kLn) {
+          // logits = embed part + r * (x . W' - mu * c1) + c0  (see ln_stats_in_ring)
+          ptx::mbar_wait(ln_bar(as), aphase);  // acquire.cta: the statistics warps' s_mu / s_rs of this tile
+          const float mu = s_mu[as * 32 + lane], rs = s_rs[as * 32 + lane];
+          const bool has_e = n_parts == 2;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          l[e] = s_hi[e * 33 + lane] + s_lo[e * 33 + lane] + s_br[e];
-          if (e >= E) l[e] = -CUDART_INF_F;
+          for (int e = 0; e < 32; ++e) {
+            const float le = has_e ? s_hi[e * 33 + lane] + s_lo[e * 33 + lane] : 0.0f;
+            const float lx = s_hx[e * 33 + lane] + s_lx[e * 33 + lane];
+            l[e] = le + fmaf(rs, fmaf(-mu, s_c1[e], lx), s_c0[e]) + s_br[e];
+            if (e >= E) l[e] = -CUDART_INF_F;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            l[e] = s_hi[e * 33 + lane] + s_lo[e * 33 + lane] + s_br[e];
+            if (e >= E) l[e] = -CUDART_INF_F;
+          }
         }
         float bv = l[0];
         int bi = 0;
@@ -528,6 +613,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                  (static_cast<size_t>(ep.rank) * ep.cap + slot) * p.D;
         }
         const uint8_t* sx = smem_raw + (n_parts - 1) * kRSlot + kRSlotA + r * 128 + ((ch ^ (r & 7)) << 4);
+        // (kLn: the statistics warps have normalised the rows in place by now)
 #pragma unroll 4
         for (int j = 0; j < kb_x; ++j)
           reinterpret_cast<uint4*>(drow)[j * 8 + ch] = *reinterpret_cast<const uint4*>(sx + j * kRBBlk);
@@ -699,7 +785,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<kRTmemCols>(tmem_base);
+    ptx::tmem_dealloc<kLn ? 2 * kRTmemCols : kRTmemCols>(tmem_base);
   }
   if (threadIdx.x == 0) {
     rtrace(p, 10);
@@ -724,7 +810,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          int B, int T, int D, int Demb, int E, int gate_mode, int keep_expert_output, int* idx,
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream, const EpPeers* ep,
-                         bool ep_fold_wait, const float* ln_gamma, const float* ln_beta, float ln_eps) {
+                         bool ep_fold_wait, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* ln_c) {
   const int S = B * T;
   if (embed == nullptr) Demb = 0;
   if (!route_supported(S, D, Demb, E, 1, B200MOE_BF16)) return cudaErrorInvalidValue;
@@ -778,23 +864,28 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   if (nonce == 0) nonce = g_route_nonce.fetch_add(1, std::memory_order_relaxed) & 0x00ffffffu;
   p.nonce = nonce;
   p.ep_fold_wait = ep_fold_wait ? 1 : 0;
-  p.ln_gamma = (ln_gamma != nullptr && ln_beta != nullptr) ? ln_gamma : nullptr;
+  // kLn: `wr_packed` is the pre-scaled router of b200moe_pack_router_ln and ln_c its c1 / c0 tail
+  p.ln_gamma = (ln_gamma != nullptr && ln_beta != nullptr && ln_c != nullptr) ? ln_gamma : nullptr;
   p.ln_beta = ln_beta;
+  p.ln_c = ln_c;
   p.ln_eps = ln_eps;
   p.trace = static_cast<uint4*>(g_route_trace);
   EpPeers epv{};
   if (ep) epv = *ep;
-  const size_t smem = kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 32 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 64);
+  const size_t smem_plain = kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 32 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 64);
+  // kLn: x-part accumulator copies, statistics, c1 / c0, gamma / beta
+  const size_t smem_ln = smem_plain + 4 * (2 * 32 * 33 + 4 * 32 + 2 * 32 + 2 * kHalfKb * kRK);
+  const size_t smem = p.ln_gamma != nullptr ? smem_ln : smem_plain;
   static bool attr_set = false;
   if (!attr_set) {
-    const int bytes = static_cast<int>(smem);
+    const int bytes = static_cast<int>(smem_plain), bytes_ln = static_cast<int>(smem_ln);
     cudaError_t e = cudaFuncSetAttribute(route_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(route_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(route_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      e = cudaFuncSetAttribute(route_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_ln);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(route_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      e = cudaFuncSetAttribute(route_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_ln);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

@@ -121,7 +121,7 @@ class EpContext:
                 gate_mode: int = ops.GATE_3M, act_type: int = ops.ACT_SILU, ff_scale: float = 1.0,
                 keep_expert_output: bool = False, out: Optional[torch.Tensor] = None,
                 Wr_packed: Optional[torch.Tensor] = None, return_routing: bool = False, stages: int = 7,
-                routing_bufs=None, norm_ff=None, norm_final=None, eps: float = 1e-12):
+                routing_bufs=None, norm_ff=None, norm_final=None, eps: float = 1e-12, Wr_packed_ln=None):
         """x [S, D] bf16: this rank's tokens.  experts: this rank's `num_local_expert` experts.  Wr [R, E_total].
         norm_ff / norm_final = (gamma, beta) fp32 [D]: the block's LayerNorms either side of the layer (ops.moe_layer)."""
         block = norm_ff is not None or norm_final is not None
@@ -129,7 +129,7 @@ class EpContext:
         if block and stages != 7:
             raise ValueError("the block call runs all stages at once")
         dev = ops._need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out,
-                             Wr_packed, *norms)
+                             Wr_packed, Wr_packed_ln, *norms)
         if x.dtype != torch.bfloat16:
             raise TypeError("the expert-parallel path takes bf16 activations")
         S, D = x.shape
@@ -163,7 +163,8 @@ class EpContext:
             b = _lib.BlockArgs(layer=a, norm_ff_gamma=p(norm_ff[0]) if norm_ff else None,
                                norm_ff_beta=p(norm_ff[1]) if norm_ff else None,
                                norm_final_gamma=p(norm_final[0]) if norm_final else None,
-                               norm_final_beta=p(norm_final[1]) if norm_final else None, eps=float(eps))
+                               norm_final_beta=p(norm_final[1]) if norm_final else None, eps=float(eps),
+                               Wr_packed_ln=p(Wr_packed_ln) if norm_ff else None)
             _lib.check(_lib.load().b200moe_ep_block_forward(self._ctx, C.byref(b), p(ws), ws.numel(), ops._stream()),
                        "b200moe_ep_block_forward")
         else:

@@ -96,6 +96,19 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
             self._wrp_key = key
         return self._wrp
 
+    def _router_packed_ln(self, wr, norm_ff):
+        """Pre-scaled router for the folded norm_ff, refreshed when the router or the norm's parameters change."""
+        if norm_ff is None or wr.shape[1] > 32 or not wr.is_cuda:
+            return None
+        w = self.router_weights
+        key = (w.data_ptr(), w._version, norm_ff.weight.data_ptr(), norm_ff.weight._version, norm_ff.bias.data_ptr(),
+               norm_ff.bias._version, str(w.device))
+        if getattr(self, "_wrln_key", None) != key:
+            self._wrln = ops.pack_router_ln(wr, norm_ff.weight.detach().float().contiguous(),
+                                            norm_ff.bias.detach().float().contiguous())
+            self._wrln_key = key
+        return self._wrln
+
     def forward(self, inputs: torch.Tensor, embed: Optional[torch.Tensor], mask: Optional[torch.Tensor] = None, *,
                 residual: Optional[torch.Tensor] = None, ff_scale: float = 1.0, return_routing: bool = False,
                 norm_ff: Optional[torch.nn.LayerNorm] = None, norm_final: Optional[torch.nn.LayerNorm] = None):
@@ -117,6 +130,8 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
             if len(eps) != 1:
                 raise ValueError("norm_ff and norm_final must share eps (the reference uses 1e-12 for both)")
             norms["eps"] = eps.pop()
+            if norm_ff is not None and inputs.dtype == torch.bfloat16:
+                norms["Wr_packed_ln"] = self._router_packed_ln(self._router()[0], norm_ff)
         x = inputs.contiguous()
         e = None if embed is None else embed.contiguous()
         Wr, br = self._router()

@@ -149,6 +149,21 @@ def pack_router(Wr: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_router_ln(Wr: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
+    """Router packed for the folded norm_ff (b200moe_block_args.Wr_packed_ln): the last D = len(gamma) rows of the fp32
+    router [R, E] (the x part of the concat) scaled by gamma, bf16 hi/lo K-major, plus c1 = gamma^T Wr_x, c0 = beta^T Wr_x."""
+    _need_cuda(Wr, gamma, beta)
+    R, E = Wr.shape
+    D = gamma.numel()
+    if Wr.dtype != torch.float32 or gamma.dtype != torch.float32 or beta.dtype != torch.float32:
+        raise TypeError("router weights, gamma and beta must be fp32")
+    lib = _lib.load()
+    out = torch.empty(int(lib.b200moe_router_ln_pack_bytes(R)), dtype=torch.uint8, device=Wr.device)
+    _lib.check(lib.b200moe_pack_router_ln(_ptr(Wr), R, E, D, _ptr(gamma), _ptr(beta), _ptr(out), _stream()),
+               "b200moe_pack_router_ln")
+    return out
+
+
 def gate_tc_usable(x_dtype, D: int, Demb: int, E: int, top_k: int) -> bool:
     return x_dtype == torch.bfloat16 and E <= 32 and top_k <= 8 and D % 64 == 0 and Demb % 64 == 0
 
@@ -281,18 +296,20 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
               return_routing: bool = False, ws: Optional[torch.Tensor] = None,
               Wr_packed: Optional[torch.Tensor] = None, compute: int = COMPUTE_BF16,
               norm_ff: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-              norm_final: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-12) -> LayerOut:
+              norm_final: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-12,
+              Wr_packed_ln: Optional[torch.Tensor] = None) -> LayerOut:
     """The fused layer: out = (residual) + ff_scale * sum_k score_k * FFN_{e_k}(x).  x [S, D] or [B, T, D].
     compute=COMPUTE_TF32: fp32 activations, `experts` from fp32_experts() (tensor cores in TF32, fp32 intermediates).
     norm_ff / norm_final = (gamma, beta) fp32 [D]: the Conformer block's LayerNorms either side of the layer
-    (fmoe_transformer.py:144-166):  out = norm_final(residual + ff_scale * MoE(norm_ff(x), embed))."""
+    (fmoe_transformer.py:144-166):  out = norm_final(residual + ff_scale * MoE(norm_ff(x), embed)).
+    Wr_packed_ln = pack_router_ln(Wr, *norm_ff): lets norm_ff be folded into the fused gate + dispatch kernel."""
     block = norm_ff is not None or norm_final is not None
     norms = [t for pair in (norm_ff, norm_final) if pair is not None for t in pair]
     for t in norms:
         if t.dtype != torch.float32 or not t.is_contiguous():
             raise TypeError("LayerNorm gamma / beta must be contiguous fp32 tensors")
     dev = _need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out,
-                     Wr_packed, *norms)
+                     Wr_packed, Wr_packed_ln, *norms)
     shape = x.shape
     if x.dim() == 3:
         B, T, D = x.shape
@@ -330,7 +347,8 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
         b = _lib.BlockArgs(layer=a, norm_ff_gamma=_ptr(norm_ff[0]) if norm_ff else None,
                            norm_ff_beta=_ptr(norm_ff[1]) if norm_ff else None,
                            norm_final_gamma=_ptr(norm_final[0]) if norm_final else None,
-                           norm_final_beta=_ptr(norm_final[1]) if norm_final else None, eps=float(eps))
+                           norm_final_beta=_ptr(norm_final[1]) if norm_final else None, eps=float(eps),
+                           Wr_packed_ln=_ptr(Wr_packed_ln) if norm_ff else None)
         _lib.check(lib.b200moe_block_forward(ctypes.byref(b), _ptr(ws), ws.numel(), _stream()),
                    "b200moe_block_forward")
     else:

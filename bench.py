@@ -242,6 +242,8 @@ def main():
                                  0.1 * torch.randn(D, generator=gen_shared, device=dev)),
                      "norm_final": (1.0 + 0.1 * torch.randn(D, generator=gen_shared, device=dev),
                                     0.1 * torch.randn(D, generator=gen_shared, device=dev))}
+            if not tf32:
+                norms["Wr_packed_ln"] = ops.pack_router_ln(Wr, *norms["norm_ff"])
         layers.append((Wr, experts, ops.pack_router(Wr), norms))
 
     # ---- synthetic activations: pinned host copies (for e2e) and device-resident copies (for value)

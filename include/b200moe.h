@@ -254,12 +254,15 @@ int b200moe_softmax_topk_enqueue(const void* logits, const int* mask, int B, int
  * semantics: biased variance over the D features, y = (x - mean) * rsqrt(var + eps) * gamma + beta, statistics in fp32,
  * the normalised input rounded to `dtype` (what the reference's LayerNorm plugin hands to the next graph layer).
  * D: multiple of 8, at most 1024.  ws: b200moe_block_workspace_bytes (the layer's workspace + one [S, D] buffer).
- * Where the norms run: norm_ff as a row pass in front of the gate (default), or -- b200moe_config("ln_fuse", 1), bf16
- * batches of up to 2 * 32 * 148 tokens -- inside the fused gate + dispatch kernel (the 32 token rows of a tile are
- * normalised in shared memory between the TMA that fetches them and the router MMAs; the scattered rows are the
- * normalised ones, `x` itself stays as the residual; measured ~1 us slower per block than the row pass); norm_final
- * inside the combine kernel when there is one (top_k > 1, expert parallelism), otherwise as a row pass over `out`
- * behind the expert kernel.  All of them share one register-level routine and give identical bits. */
+ * Where the norms run.  norm_ff: as a row pass in front of the gate; or, when Wr_packed_ln is given (bf16 batches of up
+ * to 2 * 32 * 148 tokens), folded into the fused gate + dispatch kernel algebraically: with mu, r the mean and
+ * reciprocal standard deviation of a row,  LN(x) . Wr_x = r * (x . diag(gamma) Wr_x - mu * gamma^T Wr_x) + beta^T Wr_x,
+ * so the router MMAs run on the raw rows against the pre-scaled router while idle warps compute mu and r, the arg-max
+ * epilogue combines them, and the rows handed to the experts are normalised (and rounded to bf16) as they are scattered;
+ * `x` itself stays as the residual.  The router then sees norm_ff(x) in fp32 rather than rounded to bf16 -- closer to
+ * the fp32 reference; tokens whose two best logits differ by less than that rounding may route differently between the
+ * two variants.  norm_final: inside the combine kernel when there is one (top_k > 1, expert parallelism), otherwise
+ * as a row pass over `out` behind the expert kernel.  All of them share one register-level routine. */
 typedef struct b200moe_block_args {
   b200moe_layer_args layer;
   const float* norm_ff_gamma;
@@ -267,6 +270,9 @@ typedef struct b200moe_block_args {
   const float* norm_final_gamma;
   const float* norm_final_beta;
   float eps;
+  /* optional: b200moe_pack_router_ln(Wr, gamma = norm_ff_gamma, beta = norm_ff_beta); lets norm_ff be folded into the
+   * fused gate + dispatch kernel (see below); NULL = norm_ff as a row pass in front */
+  const void* Wr_packed_ln;
 } b200moe_block_args;
 
 size_t b200moe_block_workspace_bytes(int S, int E, int D, int H, int top_k);
@@ -275,6 +281,11 @@ int b200moe_block_forward(const b200moe_block_args* args, void* ws, size_t ws_by
 size_t b200moe_ep_block_workspace_bytes(const b200moe_ep_ctx* ctx, int H);
 int b200moe_ep_block_forward(b200moe_ep_ctx* ctx, const b200moe_block_args* args, void* ws, size_t ws_bytes,
                              cudaStream_t stream);
+/* Router packing for the folded norm_ff: like b200moe_pack_router with the last D rows of Wr [R, E] (the x part of the
+ * concat) scaled by gamma, followed by c1 = gamma^T Wr_x and c0 = beta^T Wr_x (32 floats each). */
+size_t b200moe_router_ln_pack_bytes(int R);
+int b200moe_pack_router_ln(const float* Wr, int R, int E, int D, const float* gamma, const float* beta, void* packed,
+                           cudaStream_t stream);
 /* The LayerNorm alone (LayerNormPluginDynamic, TRTAPI++/plugin/layer_norm_plugin/layer_norm_kernel.cu, with the eps the
  * plugin drops): out [S, D] = LN(in [S, D]); in == out allowed. */
 int b200moe_layernorm(const void* in, const float* gamma, const float* beta, float eps, int S, int D, int dtype,
@@ -282,8 +293,8 @@ int b200moe_layernorm(const void* in, const float* gamma, const float* beta, flo
 
 /* Run-time tunables (each also has an environment default, B200MOE_<KEY>): "route" 1/0 fused gate + dispatch kernel for
  * small batches; "pdl" / "pdl_trig" bit masks (1 gate, 2 dispatch, 4 expert FFN, 8 LayerNorm) for programmatic dependent launch;
- * "prefetch" 0/1/2 L2 prefetch of the expert weights from the gate kernel; "ln_fuse" 0/1 the block's norm_ff as a
- * row pass in front (default) or inside the fused gate + dispatch kernel.  Results do not depend on any of them. */
+ * "prefetch" 0/1/2 L2 prefetch of the expert weights from the gate kernel; "ln_fuse" 1/0 fold the block's norm_ff into
+ * the fused gate + dispatch kernel when Wr_packed_ln is given, or always run it as a row pass in front.  Results do not depend on any of them. */
 int b200moe_config(const char* key, int value);
 
 /* Optional per-stage device timing with CUDA events around each stage of b200moe_forward (eager launches only, not

@@ -20,7 +20,7 @@ BF16_REL_L2 = 1e-2
 @pytest.fixture(autouse=True, params=[1, 0], ids=["route", "split"])
 def route_mode(request, ops):
     ops.config("route", request.param)
-    yield
+    yield request.param
     ops.config("route", 1)
 
 
@@ -60,7 +60,7 @@ def test_layernorm_kernel(ops, oracle, dtype, D):
                       torch.zeros(2048, device="cuda"))
 
 
-def test_block_golden(ops, oracle):
+def test_block_golden(ops, oracle, route_mode):
     """The vectors made with the reference's FmoeConformerLayer members, through the CUDA path in bf16."""
     g = load_golden("case_block_3m.npz")
     experts = ops.pack_experts(g["W1"].cuda(), g["b1"].cuda(), g["W2"].cuda(), g["b2"].cuda())
@@ -76,6 +76,15 @@ def test_block_golden(ops, oracle):
     pre = ops.moe_layer(x, emb, Wr, None, experts, residual=x, ff_scale=float(g["ff_scale"]),
                         Wr_packed=ops.pack_router(Wr), norm_ff=cu(nf), eps=float(g["eps"]))
     assert rel_l2(pre.out.float().cpu(), g["pre_norm"]) <= BF16_REL_L2
+    # norm_ff folded into the route kernel (router on fp32 norm_ff(x)): the fixture's margins keep routing exact
+    wln = ops.pack_router_ln(Wr, nf[0].cuda(), nf[1].cuda())
+    resf = ops.moe_layer(x, emb, Wr, None, experts, residual=x, ff_scale=float(g["ff_scale"]), return_routing=True,
+                         Wr_packed=ops.pack_router(Wr), norm_ff=cu(nf), norm_final=cu(nl), eps=float(g["eps"]),
+                         Wr_packed_ln=wln)
+    assert torch.equal(resf.idx.cpu().view(-1).long(), g["gate_idx"])
+    assert torch.equal(resf.counts.cpu().long(), g["expert_count"])
+    torch.testing.assert_close(resf.score.cpu().view(-1), g["gate_value"], rtol=2e-3, atol=1e-5)
+    assert rel_l2(resf.out.float().cpu(), g["out"]) <= BF16_REL_L2
     # fp32 activations: the SIMT gate and the generic dispatch path behind the same norms
     res32 = ops.moe_layer(g["x"].cuda(), g["embed"].cuda(), Wr, None, experts, residual=g["x"].cuda(),
                           ff_scale=float(g["ff_scale"]), return_routing=True, norm_ff=cu(nf), norm_final=cu(nl),
@@ -85,7 +94,9 @@ def test_block_golden(ops, oracle):
 
 
 def run_block_case(ops, oracle, synth, S, *, E=32, D=512, H=1024, Demb=512, norm_ff=True, norm_final=True, top_k=1,
-                   gate_mode=None, seed=31):
+                   gate_mode=None, seed=31, folded=False):
+    """folded: hand the pre-scaled router to the call, so that norm_ff is folded into the fused gate + dispatch kernel
+    (the router then sees norm_ff(x) in fp32, not rounded to bf16: bar (1) does not apply, bar (2) gets tighter)."""
     gate_mode = ops.GATE_3M if gate_mode is None else gate_mode
     demb = Demb if gate_mode == ops.GATE_3M else 0
     w = synth.make_weights(seed, E, D, H, demb, random_bias=True, router_bias=(gate_mode != ops.GATE_3M))
@@ -99,19 +110,41 @@ def run_block_case(ops, oracle, synth, S, *, E=32, D=512, H=1024, Demb=512, norm
     xd = x.cuda().bfloat16()
     ed = None if emb is None else emb.cuda().bfloat16()
     packed = ops.pack_router(Wr) if E <= 32 else None
+    wln = ops.pack_router_ln(Wr, nf[0].cuda(), nf[1].cuda()) if (folded and norm_ff) else None
     res = ops.moe_layer(xd, ed, Wr, br, experts, residual=xd, ff_scale=0.5, top_k=top_k, gate_mode=gate_mode,
-                        return_routing=True, Wr_packed=packed, norm_ff=cu(nf), norm_final=cu(nl))
+                        return_routing=True, Wr_packed=packed, norm_ff=cu(nf), norm_final=cu(nl), Wr_packed_ln=wln)
     ogate = oracle.GATE_3M if gate_mode == ops.GATE_3M else oracle.GATE_NAIVE
-    # (1) the oracle on the GPU's own normalised input: routing must be bit-exact (near-ties of 1e-4 aside)
-    xn_gpu = ops.layernorm(xd, nf[0].cuda(), nf[1].cuda()).float().cpu() if norm_ff else x
+    got_idx = res.idx.cpu().long()
+    if top_k > 1:
+        got_idx = torch.sort(got_idx, 1).values
+    if not folded:
+        check_same_input_bar(ops, oracle, res, got_idx, x, xd, emb, w, nf, nl, top_k, ogate)
+    # (2) the pure fp32 chain: agreeing rows within tolerance, disagreeing rows are near-ties of that chain
+    r2 = oracle.moe_block_forward(x, emb, w.Wr, w.br, w.W1, w.b1, w.W2, w.b2, norm_ff=nf, norm_final=nl, ff_scale=0.5,
+                                  top_k=top_k, gate_mode=ogate)
+    ref2 = torch.sort(r2["idx"], 1).values if top_k > 1 else r2["idx"]
+    agree = (got_idx == ref2).all(-1)
+    assert float(agree.float().mean()) > (0.995 if folded else 0.97)
+    top2 = torch.topk(r2["logits"].double(), top_k + 1, dim=-1).values
+    margin2 = (top2[:, :-1] - top2[:, 1:]).min(-1).values
+    # rounding norm_ff(x) to bf16 moves a logit by up to ~1e-2; the folded router only by its own fp32 round-off
+    assert float(margin2[~agree].max() if bool((~agree).any()) else 0.0) < (1e-3 if folded else 2e-2)
+    err = rel_l2(res.out.float().cpu()[agree], r2["out"][agree])
+    assert err <= BF16_REL_L2
+    return err
+
+
+def check_same_input_bar(ops, oracle, res, got_idx, x, xd, emb, w, nf, nl, top_k, ogate):
+    """(1) the oracle on the GPU's own normalised input: routing must be bit-exact (near-ties of 1e-4 aside)."""
+    xn_gpu = ops.layernorm(xd, nf[0].cuda(), nf[1].cuda()).float().cpu() if nf is not None else x
     r1 = oracle.moe_forward(xn_gpu, emb, w.Wr, w.br, w.W1, w.b1, w.W2, w.b2, top_k=top_k, gate_mode=ogate,
                             residual=x, ff_scale=0.5)
     top = torch.topk(r1["logits"].double(), top_k + 1, dim=-1).values
     clear = (top[:, :-1] - top[:, 1:]).min(-1).values >= 1e-4
     assert float(clear.float().mean()) > 0.995
-    got_idx, ref_idx = res.idx.cpu().long(), r1["idx"]
+    ref_idx = r1["idx"]
     if top_k > 1:
-        got_idx, ref_idx = torch.sort(got_idx, 1).values, torch.sort(ref_idx, 1).values
+        ref_idx = torch.sort(ref_idx, 1).values
     assert torch.equal(got_idx[clear], ref_idx[clear]), "expert assignment on the same normalised input"
     if bool(clear.all()):
         assert torch.equal(res.counts.cpu().long(), r1["counts"])
@@ -120,18 +153,6 @@ def run_block_case(ops, oracle, synth, S, *, E=32, D=512, H=1024, Demb=512, norm
     out1 = r1["out"] if nl is None else oracle.layer_norm(r1["out"], nl[0], nl[1])
     same = (got_idx == ref_idx).all(-1)
     assert rel_l2(res.out.float().cpu()[same], out1[same]) <= BF16_REL_L2
-    # (2) the pure fp32 chain: agreeing rows within tolerance, disagreeing rows are near-ties of that chain
-    r2 = oracle.moe_block_forward(x, emb, w.Wr, w.br, w.W1, w.b1, w.W2, w.b2, norm_ff=nf, norm_final=nl, ff_scale=0.5,
-                                  top_k=top_k, gate_mode=ogate)
-    ref2 = torch.sort(r2["idx"], 1).values if top_k > 1 else r2["idx"]
-    agree = (got_idx == ref2).all(-1)
-    assert float(agree.float().mean()) > 0.97
-    top2 = torch.topk(r2["logits"].double(), top_k + 1, dim=-1).values
-    margin2 = (top2[:, :-1] - top2[:, 1:]).min(-1).values
-    assert float(margin2[~agree].max() if bool((~agree).any()) else 0.0) < 2e-2
-    err = rel_l2(res.out.float().cpu()[agree], r2["out"][agree])
-    assert err <= BF16_REL_L2
-    return err
 
 
 @pytest.mark.parametrize("S", [1, 50, 3200, 6000])
@@ -140,17 +161,34 @@ def test_block_cfg3_shape(ops, oracle, synth, S):
     run_block_case(ops, oracle, synth, S)
 
 
-@pytest.mark.parametrize("S", [50, 1234, 6000])
-@pytest.mark.parametrize("fuse", [1, 0])
-def test_block_norm_ff_in_route_kernel_equals_row_pass(ops, oracle, synth, fuse, S):
-    """norm_ff inside the fused gate + dispatch kernel (an option, b200moe_config("ln_fuse", 1)) and as a separate row
-    pass (the default) give the same bits: both are held to the same-input bit-exact routing bar.  6000 tokens: more
-    32-token tiles than SMs, the kernel re-normalises the rows it has to re-read."""
-    ops.config("ln_fuse", fuse)
+@pytest.mark.parametrize("S", [50, 1234, 3200, 6000])
+def test_block_norm_ff_folded_into_route_kernel(ops, oracle, synth, S, route_mode):
+    """With the pre-scaled router (ops.pack_router_ln) norm_ff is folded into the fused gate + dispatch kernel: router
+    MMAs on the raw rows, row statistics on the side, logits = e-part + r (x.W' - mu c1) + c0, rows normalised as they
+    are scattered.  6000 tokens: more 32-token tiles than SMs, the kernel re-normalises the rows it re-reads."""
+    if route_mode == 0:
+        pytest.skip("the fused gate + dispatch kernel is switched off in this parametrisation")
+    run_block_case(ops, oracle, synth, S, seed=61, folded=True)
+    run_block_case(ops, oracle, synth, S, seed=62, folded=True, norm_final=False)
+
+
+def test_block_folded_knob_off_is_the_row_pass(ops, oracle, synth):
+    """ln_fuse = 0: the pre-scaled router is ignored and the call is bit-identical to the one without it."""
+    E, D, H, Demb, S = 32, 512, 1024, 512, 777
+    w = synth.make_weights(63, E, D, H, Demb, random_bias=True)
+    x, emb = synth.make_activations(64, S, D, Demb, w)
+    nf, nl = make_norm(D, 65), make_norm(D, 66)
+    experts = ops.pack_experts(w.W1.cuda(), w.b1.cuda(), w.W2.cuda(), w.b2.cuda())
+    Wr = w.Wr.cuda()
+    xd, ed = (x * 2 + 0.3).cuda().bfloat16(), emb.cuda().bfloat16()
+    kw = dict(residual=xd, ff_scale=0.5, Wr_packed=ops.pack_router(Wr), norm_ff=cu(nf), norm_final=cu(nl))
+    plain = ops.moe_layer(xd, ed, Wr, None, experts, **kw).out.clone()
+    ops.config("ln_fuse", 0)
     try:
-        run_block_case(ops, oracle, synth, S, seed=61)
+        off = ops.moe_layer(xd, ed, Wr, None, experts, Wr_packed_ln=ops.pack_router_ln(Wr, *cu(nf)), **kw).out
+        assert torch.equal(off, plain)
     finally:
-        ops.config("ln_fuse", 0)
+        ops.config("ln_fuse", 1)
 
 
 def test_block_padding_rows(ops, oracle, synth):
@@ -234,10 +272,11 @@ def test_ep_block_single_rank(ops, oracle, synth):
     Wr = w.Wr.cuda()
     xd, ed = x.cuda().bfloat16(), emb.cuda().bfloat16()
     ctx = ep_mod.EpContext.simulate(1, E, D, S, torch.device("cuda"))[0]
+    wln = ops.pack_router_ln(Wr, nf[0].cuda(), nf[1].cuda())
     out = ctx.forward(xd, ed, Wr, None, experts, residual=xd, ff_scale=0.5, Wr_packed=ops.pack_router(Wr),
-                      norm_ff=cu(nf), norm_final=cu(nl))
+                      norm_ff=cu(nf), norm_final=cu(nl), Wr_packed_ln=wln)
     one = ops.moe_layer(xd, ed, Wr, None, experts, residual=xd, ff_scale=0.5, Wr_packed=ops.pack_router(Wr),
-                        norm_ff=cu(nf), norm_final=cu(nl)).out
+                        norm_ff=cu(nf), norm_final=cu(nl), Wr_packed_ln=wln).out
     torch.cuda.synchronize()
     assert ctx.status() == 0
     # same routing, same kernels; the expert output makes the return trip in bf16 before the residual add and the norm

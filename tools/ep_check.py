@@ -94,12 +94,14 @@ def main():
     gen = torch.Generator().manual_seed(4321)
     nf = tuple((t.to(dev)) for t in (1.0 + 0.2 * torch.randn(D, generator=gen), 0.1 * torch.randn(D, generator=gen)))
     nl = tuple((t.to(dev)) for t in (1.0 + 0.2 * torch.randn(D, generator=gen), 0.1 * torch.randn(D, generator=gen)))
+    wln = ops.pack_router_ln(Wr, *nf)   # norm_ff folded into the route kernel on both sides
     cur = ref_cur = xd
     first = None
     for li in range(6):
-        cur = ctx.forward(cur, ed, Wr, None, mine, residual=cur, ff_scale=0.5, Wr_packed=Wrp, norm_ff=nf, norm_final=nl)
+        cur = ctx.forward(cur, ed, Wr, None, mine, residual=cur, ff_scale=0.5, Wr_packed=Wrp, norm_ff=nf, norm_final=nl,
+                          Wr_packed_ln=wln)
         ref_cur = ops.moe_layer(ref_cur, ed, Wr, None, full, residual=ref_cur, ff_scale=0.5, Wr_packed=Wrp, norm_ff=nf,
-                                norm_final=nl).out
+                                norm_final=nl, Wr_packed_ln=wln).out
         if li == 0:
             first = float((cur.float() - ref_cur.float()).norm() / ref_cur.float().norm())
     torch.cuda.synchronize()

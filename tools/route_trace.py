@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Timeline of the fused gate + dispatch kernel (GPU box only): python tools/route_trace.py [S]"""
+"""Timeline of the fused gate + dispatch kernel (GPU box only): python tools/route_trace.py [S] [ln]
+(`ln`: with the block's norm_ff fused into the kernel, b200moe_config("ln_fuse", 1))"""
 import importlib
 import os
 import sys
@@ -16,6 +17,7 @@ EV = ["start", "setup_done", "tma_issued", "acc_ready", "idx_written", "barrier_
 
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 3200
+    ln = len(sys.argv) > 2 and sys.argv[2] == "ln"
     ops = importlib.import_module(PKG + ".ops")
     lib = importlib.import_module(PKG + "._lib").load()
     E, D, H, Demb = 32, 512, 1024, 512
@@ -31,14 +33,20 @@ def main():
     x = torch.randn(S, D, generator=g, device=dev).bfloat16()
     emb = torch.randn(S, Demb, generator=g, device=dev).bfloat16()
     out = torch.empty_like(x)
+    kw = {}
+    if ln:
+        kw = {"norm_ff": (torch.ones(D, device=dev) * 1.1, torch.zeros(D, device=dev) + 0.05)}
+        layers = [(Wr, ex, wp, ops.pack_router_ln(Wr, *kw["norm_ff"])) for Wr, ex, wp in layers]
+    else:
+        layers = [(Wr, ex, wp, None) for Wr, ex, wp in layers]
     for _ in range(3):
-        for Wr, ex, wp in layers:
-            ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
+        for Wr, ex, wp, wln in layers:
+            ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp, Wr_packed_ln=wln, **kw)
     torch.cuda.synchronize()
     buf = torch.zeros(148 * 16, 4, dtype=torch.int32, device=dev)
     lib.b200moe_debug_route_trace(buf.data_ptr())
-    Wr, ex, wp = layers[1]
-    ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
+    Wr, ex, wp, wln = layers[1]
+    ops.moe_layer(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp, Wr_packed_ln=wln, **kw)
     torch.cuda.synchronize()
     lib.b200moe_debug_route_trace(None)
     analyze(buf.cpu().numpy().astype(np.int64).reshape(148, 16, 4), S)
