@@ -284,17 +284,6 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   }
   if (warp == 2) ptx::tmem_alloc<kLn ? 2 * kRTmemCols : kRTmemCols>(tmem_slot);
   if (warp == 3) s_br[lane] = (p.br != nullptr && lane < E) ? p.br[lane] : 0.0f;
-  if constexpr (kLn) {
-    // constants of the layer: may be fetched before the wait for the previous kernel
-    if (warp == 4) {
-      s_c1[lane] = p.ln_c[lane];
-      s_c0[lane] = p.ln_c[32 + lane];
-    }
-    for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
-      s_gamma[i] = p.ln_gamma[i];
-      s_beta[i] = p.ln_beta[i];
-    }
-  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -375,6 +364,13 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   } else if (kLn && (warp == 2 || warp == 3 || warp >= 6)) {
     // norm_ff's statistics (fmoe_transformer.py:145-148) of the tile's 32 token rows, 8 rows per warp, while the MMAs run
     const int lw = (warp & 1) | ((warp >> 2) << 1);  // warps 2, 3, 6, 7 -> 0 .. 3
+    // gamma / beta into shared memory while the tile is on its way.  Every one of the four warps writes the whole
+    // vectors (identical values), so that none of them depends on another one's stores.
+    for (int i = lane * 4; i < p.D; i += 128) {
+      *reinterpret_cast<float4*>(s_gamma + i) = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + i));
+      *reinterpret_cast<float4*>(s_beta + i) = __ldg(reinterpret_cast<const float4*>(p.ln_beta + i));
+    }
+    __syncwarp();
     int slot = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -407,6 +403,13 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const int q = warp & 3;
     float* dstm = q == 0 ? s_hi : s_lo;
     int it = 0;
+    if constexpr (kLn) {
+      if (q == 0) {  // constants of the layer, read back by this warp only
+        s_c1[lane] = p.ln_c[lane];
+        s_c0[lane] = p.ln_c[32 + lane];
+        __syncwarp();
+      }
+    }
     ptx::pdl_wait();  // idx / score / histogram words may still be read by the previous layer's kernels
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
