@@ -304,6 +304,11 @@ def moe_layer(x: torch.Tensor, embed: Optional[torch.Tensor], Wr: torch.Tensor, 
     (fmoe_transformer.py:144-166):  out = norm_final(residual + ff_scale * MoE(norm_ff(x), embed)).
     Wr_packed_ln = pack_router_ln(Wr, *norm_ff): lets norm_ff be folded into the fused gate + dispatch kernel."""
     block = norm_ff is not None or norm_final is not None
+    if Wr_packed_ln is not None:
+        R = (0 if embed is None else embed.shape[-1]) + x.shape[-1]
+        if norm_ff is None or Wr_packed_ln.dtype != torch.uint8 or \
+                Wr_packed_ln.numel() != int(_lib.load().b200moe_router_ln_pack_bytes(R)):
+            raise ValueError("Wr_packed_ln must come from pack_router_ln(Wr, *norm_ff) for this router")
     norms = [t for pair in (norm_ff, norm_final) if pair is not None for t in pair]
     for t in norms:
         if t.dtype != torch.float32 or not t.is_contiguous():

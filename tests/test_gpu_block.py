@@ -347,3 +347,32 @@ def test_block_fp16_activations(ops, oracle, synth):
     want = oracle.layer_norm(r["out"], nl[0], nl[1])
     assert float(same.float().mean()) > 0.99
     assert rel_l2(res.out.float().cpu()[same], want[same]) <= BF16_REL_L2
+
+
+def test_pack_router_ln_contents(ops):
+    """b200moe_pack_router_ln: bf16 hi / lo rows of the router with its x rows scaled by gamma, then c1 and c0."""
+    torch.manual_seed(9)
+    Demb, D, E = 128, 192, 20
+    Wr = torch.randn(Demb + D, E) * 0.05
+    gamma, beta = make_norm(D, 121)
+    buf = ops.pack_router_ln(Wr.cuda(), gamma.cuda(), beta.cuda()).cpu()
+    R = Demb + D
+    packed = buf[: 64 * R * 2].view(torch.bfloat16).view(64, R).float()
+    c = buf[64 * R * 2:].view(torch.float32)
+    assert c.numel() == 64
+    Ws = Wr.clone()
+    Ws[Demb:] *= gamma[:, None]
+    hi = Ws.bfloat16().float()
+    lo = (Ws - hi).bfloat16().float()
+    assert torch.equal(packed[:E], hi.t()) and torch.equal(packed[32:32 + E], lo.t())
+    assert float(packed[E:32].abs().max()) == 0.0 and float(packed[32 + E:].abs().max()) == 0.0
+    c1 = (hi[Demb:].double() + lo[Demb:].double()).sum(0)
+    c0 = (beta[:, None].double() * Wr[Demb:].double()).sum(0)
+    torch.testing.assert_close(c[:E].double(), c1, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(c[32:32 + E].double(), c0, rtol=1e-6, atol=1e-7)
+    assert float(c[E:32].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        x = torch.zeros(8, D, device="cuda", dtype=torch.bfloat16)
+        ops.moe_layer(x, None, Wr.cuda(), None, ops.PackedExperts(torch.zeros(E, 128, D, device="cuda", dtype=torch.bfloat16),
+                                                                 None, torch.zeros(E, D, 128, device="cuda", dtype=torch.bfloat16), None),
+                      norm_ff=(gamma.cuda(), beta.cuda()), Wr_packed_ln=torch.zeros(10, dtype=torch.uint8, device="cuda"))
