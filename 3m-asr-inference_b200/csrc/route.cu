@@ -21,6 +21,8 @@
 //   phase 2 (per 32-token chunk): prefix over the histograms -> offsets, stable ranks by match_any, mapping / pos /
 //     row_score, 128-bit row copies into expert order (or, under expert parallelism, into the owner GPU's receive buffer).
 //     CTA 0 publishes counts / offsets / the FFN group table.
+//   route_kernel<.., kLn = true>: the Conformer block's norm_ff (trainer_3m_fix/layer/fmoe_transformer.py:145-148) folded
+//     into the router algebraically, see ln_stats_in_ring below.
 #include <atomic>
 
 #include <math_constants.h>
@@ -46,7 +48,7 @@ constexpr int kRSlot = kRSlotA + kRSlotB;   // 96 KiB
 constexpr int kRSlots = 2;
 constexpr int kRThreads = 256;
 constexpr uint32_t kRTmemCols = 64;         // 2 accumulator buffers x 32 token columns
-constexpr int kLnWarps = 4;                 // warps 2, 3, 6, 7 normalise the token rows when norm_ff is fused in
+constexpr int kLnWarps = 4;                 // warps 2, 3, 6, 7: row statistics and in-place normalisation when norm_ff is folded in
 
 // norm_ff fused into the router ALGEBRAICALLY (kLn).  With mu, r the mean and reciprocal standard deviation of a token row,
 //   LN(x) . Wr_x = r * ( x . W' - mu * c1 ) + c0,    W' = diag(gamma) Wr_x,  c1 = gamma^T Wr_x,  c0 = beta^T Wr_x,
@@ -225,7 +227,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kRSlots + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kRSlots + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kRSlots + 4);
-  auto ln_bar = [&](int s) { return tmem_slot + 16u + 8u * s; };  // LayerNorm warps -> MMA issuer
+  auto ln_bar = [&](int s) { return tmem_slot + 16u + 8u * s; };  // statistics warps -> softmax warp, per accumulator stage
   uint8_t* misc = smem_raw + (tmem_slot - smem_base) + 32;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(misc - 32);
   float* s_br = reinterpret_cast<float*>(misc);               // [32]
