@@ -59,6 +59,9 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
   // raised by the last CTA of its FFN kernel after every CTA's system-scope fence), mapping / score / seq were written
   // by this layer's route kernel, which completed before the FFN kernel could pass its own wait.
   ptx::pdl_launch_dependents();
+  // (kLn) gamma / beta are constants of the layer: fetched before the wait for the return flags
+  LnAffine<kVec> aff;
+  if constexpr (kLn) aff.load(ln_gamma, ln_beta, D, threadIdx.x & 31);
   int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
   const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ret_flag);
   if (threadIdx.x < ep.world) {
@@ -74,7 +77,7 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
     // norm_final fused behind the residual add (fmoe_transformer.py:164-166): the warp holds the whole row
     const int nvec = D >> 3;
     for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
-      float o[kVec][8];
+      float o[1][kVec][8];
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
@@ -94,15 +97,15 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
         }
         if (residual) {
           const uint4 r = __ldg(reinterpret_cast<const uint4*>(residual + static_cast<size_t>(s) * D + v * 8));
-          bf16x8_to_f(r, o[k]);
+          bf16x8_to_f(r, o[0][k]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[k][i] = fmaf(ff_scale, acc[i], o[k][i]);
+          for (int i = 0; i < 8; ++i) o[0][k][i] = fmaf(ff_scale, acc[i], o[0][k][i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[k][i] = ff_scale * acc[i];
+          for (int i = 0; i < 8; ++i) o[0][k][i] = ff_scale * acc[i];
         }
       }
-      ln_row_registers<kVec>(o, D, lane, ln_gamma, ln_beta, ln_eps);
+      ln_rows_registers<kVec, 1>(o, D, lane, aff, ln_eps);
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
@@ -110,7 +113,7 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 pk = __floats2bfloat162_rn(o[k][2 * i], o[k][2 * i + 1]);
+          __nv_bfloat162 pk = __floats2bfloat162_rn(o[0][k][2 * i], o[0][k][2 * i + 1]);
           w[i] = *reinterpret_cast<uint32_t*>(&pk);
         }
         *reinterpret_cast<uint4*>(out + static_cast<size_t>(s) * D + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -77,21 +77,25 @@ layernorm_rows_kernel(const T* in, const float* __restrict__ gamma, const float*
   // `in` may be the output of the kernel in front (programmatic dependent launch): nothing is read before the wait.
   // The kernel behind may start its own prologue at once (its wait returns when this grid has completed).
   ptx::pdl_launch_dependents();
-  ptx::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // gamma / beta are constants of the layer: fetched before the wait for the producer of `in`, so that their latency
+  // (the second dependent L2 round trip of a one-row-per-warp kernel) is off the chain
+  LnAffine<kVec> aff;
+  aff.load(gamma, beta, D, lane);
+  ptx::pdl_wait();
   const int wpb = kLnThreads / 32;
   const int nvec = D >> 3;
   for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
-    float v[kVec][8];
+    float v[1][kVec][8];
     const T* src = in + static_cast<size_t>(s) * D;
 #pragma unroll
     for (int k = 0; k < kVec; ++k)
-      if (k * 32 + lane < nvec) load8<T>(src + (k * 32 + lane) * 8, v[k]);
-    ln_row_registers<kVec>(v, D, lane, gamma, beta, eps);
+      if (k * 32 + lane < nvec) load8<T>(src + (k * 32 + lane) * 8, v[0][k]);
+    ln_rows_registers<kVec, 1>(v, D, lane, aff, eps);
     T* dst = out + static_cast<size_t>(s) * D;
 #pragma unroll
     for (int k = 0; k < kVec; ++k)
-      if (k * 32 + lane < nvec) store8<T>(dst + (k * 32 + lane) * 8, v[k]);
+      if (k * 32 + lane < nvec) store8<T>(dst + (k * 32 + lane) * 8, v[0][k]);
   }
 }
 
