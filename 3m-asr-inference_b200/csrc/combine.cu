@@ -97,8 +97,10 @@ combine_kernel(const T* __restrict__ ybuf, const int* __restrict__ mapping, cons
   if constexpr (kLn) {
     // norm_final fused behind the residual add (fmoe_transformer.py:164-166): the warp holds the whole row
     const int nvec = D >> 3;
+    LnAffine<kVec> aff;  // constants of the layer, fetched once per warp
+    aff.load(ln_gamma, ln_beta, D, lane);
     for (int s = blockIdx.x * warps_per_block + warp; s < S; s += gridDim.x * warps_per_block) {
-      float o[kVec][8];
+      float o[1][kVec][8];
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
@@ -120,21 +122,21 @@ combine_kernel(const T* __restrict__ ybuf, const int* __restrict__ mapping, cons
         if (residual) {
           Vec8<T> r;
           r.load(residual + static_cast<size_t>(s) * D + v * 8);
-          r.to_f(o[k]);
+          r.to_f(o[0][k]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[k][i] = fmaf(ff_scale, acc[i], o[k][i]);
+          for (int i = 0; i < 8; ++i) o[0][k][i] = fmaf(ff_scale, acc[i], o[0][k][i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[k][i] = ff_scale * acc[i];
+          for (int i = 0; i < 8; ++i) o[0][k][i] = ff_scale * acc[i];
         }
       }
-      ln_row_registers<kVec>(o, D, lane, ln_gamma, ln_beta, ln_eps);
+      ln_rows_registers<kVec, 1>(o, D, lane, aff, ln_eps);
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
         const int v = k * 32 + lane;
         if (v >= nvec) continue;
         Vec8<T> ov;
-        ov.from_f(o[k]);
+        ov.from_f(o[0][k]);
         ov.store(out + static_cast<size_t>(s) * D + v * 8);
       }
     }

@@ -63,6 +63,7 @@ struct FfnParams {
   int top_k;
   int E, D, H, bn, act, fused;
   int stages;
+  int gmax;  // capacity of the group table
   int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
   int kps;  // k-blocks (of 64) per pipeline stage: one TMA instruction per operand brings all of them
   int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
@@ -370,15 +371,20 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   // Everything above touched only kernel parameters and on-chip state, so under programmatic dependent launch it
   // overlaps the tail of the dispatch kernel.  The routing tables, xbuf and every output come after this wait.
   ptx::pdl_wait();
-  const int ng = *p.n_groups;
   // a tile is kCtas x 128 weight rows of one group; this CTA's share is rows (mb * kCtas + rank) * 128 ...
   const int m1 = p.H / (kBlockM * kCtas);
   const int m2 = p.D / (kBlockM * kCtas);
+  const int tile0 = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kCtas == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // The first tile of a CTA is a first-GEMM tile of group tile0 / m1 whenever it lies in the head of the schedule
+  // (decode_tile), whatever the number of groups turns out to be: its table entry is requested together with the group
+  // count instead of one L2 round trip after it.
+  const int g_first = min(tile0 / m1, p.gmax - 1);
+  const GroupRec gr_first = p.groups[g_first];
+  const int ng = *p.n_groups;
   const int m1_flags = p.H / kBlockM;  // every CTA publishes its own 128-row slice of h: flags per group
   const int lag = min(p.lag, ng);
   const int n_tiles = ng * (m1 + m2);
-  const int tile0 = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int tile_step = kCtas == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr int kKel = kTf32 ? kBlockK / 2 : kBlockK;  // elements per 128-byte k-block
   const int kb1 = p.D / (kKel * kps);  // pipeline stages per tile of the first GEMM
   const int kb2 = p.H / (kKel * kps);
@@ -406,7 +412,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       tr.rec(-1, kEvKernelStart);
       for (int t = tile0; t < n_tiles; t += tile_step) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
-        const GroupRec gr = p.groups[tl.g];
+        const GroupRec gr = (t == tile0 && tl.g == g_first) ? gr_first : p.groups[tl.g];
         tr.rec(t, kEvProdTileStart);
         const CUtensorMap* tm_a = tl.phase == 1 ? &tm_w1 : &tm_w2;
         const CUtensorMap* tm_b = tl.phase == 1 ? &tm_x : &tm_h;
@@ -1053,6 +1059,7 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   // phase-2 tiles trail their group's phase-1 tiles by ~3 waves of the grid
   const int m1 = a.H / (kBlockM * ctas);
   p.lag = (3 * (num_sms() / ctas) + m1 - 1) / m1;
+  p.gmax = a.gmax > 0 ? a.gmax : 1;
   if (tf32) return launch_typed<float, 1, true>(a, tw1, tw2, tx, th, p, stream);
   switch (a.out_dtype) {
     case B200MOE_F32:
