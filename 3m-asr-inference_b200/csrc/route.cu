@@ -298,10 +298,18 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       int slot = 0;
       uint32_t phase = 0;
       bool waited = false;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
         for (int part = 0; part < n_parts; ++part) {
           const bool is_e = n_parts == 2 && part == 0;
           const int nkb = is_e ? kb_e : kb_x;
+          if constexpr (kLn) {
+            // The MMAs release a ring slot when THEY have read it, but the statistics warps read the x tile as well
+            // and take longer: a second tile's rows must not land on top of the first tile's before its statistics
+            // are done (ln_bar of that tile; with two K parts the x tiles of consecutive tiles share a slot, and a
+            // CTA has at most two tiles).
+            if (!is_e && it > 0) ptx::mbar_wait(ln_bar((it - 1) & 1), ((it - 1) >> 1) & 1);
+          }
           // Programmatic dependent launch: the embed half of the router GEMM (embed and the router are constants) runs
           // while the previous layer's FFN kernel is still draining; x, its output, is only touched after this wait.
           if (!is_e && !waited) {
