@@ -42,6 +42,7 @@ class BlockArgs(C.Structure):
 # name -> (restype, argtypes); every symbol include/b200moe.h declares
 SIGNATURES = {
     "b200moe_last_error": (C.c_char_p, []),
+    "b200moe_status": (_i, [C.POINTER(C.c_int), _i]),
     "b200moe_version": (_i, []),
     "b200moe_device_supported": (_i, [_i]),
     "b200moe_launch_count": (C.c_ulonglong, []),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "b200moe_plugin_deserialize": (_vp, [_vp, _sz]),
     "b200moe_plugin_destroy": (None, [_vp]),
     "b200moe_plugin_workspace_bytes": (_sz, [_vp, _i]),
+    "b200moe_plugin_invalidate": (_i, [_vp]),
     "b200moe_plugin_enqueue": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "b200moe_softmax_topk_enqueue": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
 }

@@ -125,9 +125,12 @@ struct b200moe_plugin {
   int idim;
   int hidden_units;
   int act_type;
-  // identity of the weights packed into the workspace by the last enqueue
+  // bf16 / fp32 copies of the weights the plugin OWNS (cudaMalloc on the first enqueue, freed by destroy): the scratch
+  // workspace TensorRT hands to enqueue is shared between layers and not preserved between calls, so nothing cached may
+  // live there.  packed_src = the four input pointers the copies were made from.
   const void* packed_src[4];
-  void* packed_ws;
+  void* packed;   // [w1 bf16 | w2 bf16 | b1 fp32 | b2 fp32]; w1 / w2 parts absent when data_type is already bf16
+  int device;
 };
 
 extern "C" {
@@ -143,6 +146,13 @@ int b200moe_device_supported(int dev) {
   cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
   return major == 10 ? 1 : 0;
+}
+
+int b200moe_status(int* host_status, int clear) {
+  if (!host_status) return fail(B200MOE_ERR_ARG, "status: null pointer");
+  cudaError_t e = read_route_status(host_status, clear != 0);
+  if (e != cudaSuccess) return cuda_fail(e, "status");
+  return B200MOE_OK;
 }
 
 int b200moe_debug_route_trace(void* dev_buf) {
@@ -477,7 +487,7 @@ static int forward_impl(const b200moe_layer_args* a, void* ws, size_t ws_bytes, 
   f.tf32 = tf32 ? 1 : 0;
   if (route) {
     f.clear_ptr = w.hist32;
-    f.clear_ints = ((S + 31) / 32) * a->E;
+    f.clear_ints = 2 * ((S + 31) / 32) * a->E;  // 64-bit words
   }
   if (fused) {
     f.fused = 1;
@@ -714,7 +724,7 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
   f.ep = &ep;
   if (route) {
     f.clear_ptr = w.hist32;
-    f.clear_ints = ((S + 31) / 32) * a->E;
+    f.clear_ints = 2 * ((S + 31) / 32) * a->E;  // 64-bit words
   }
   if (stages & 2) {
     StageScope t(2, stream);
@@ -752,7 +762,8 @@ b200moe_plugin* b200moe_plugin_create(int data_type, int num_expert, int idim, i
   p->hidden_units = hidden_units;
   p->act_type = act_type;
   std::memset(p->packed_src, 0, sizeof(p->packed_src));
-  p->packed_ws = nullptr;
+  p->packed = nullptr;
+  p->device = -1;
   return p;
 }
 
@@ -781,22 +792,32 @@ b200moe_plugin* b200moe_plugin_deserialize(const void* host_data, size_t length)
   return b200moe_plugin_create(v[0], v[1], v[2], v[3], v[4]);
 }
 
-void b200moe_plugin_destroy(b200moe_plugin* p) { delete p; }
-
 namespace {
-struct PluginWs {
-  size_t route_bytes;
+void plugin_release(b200moe_plugin* p) {
+  if (p->packed != nullptr) {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (p->device >= 0 && p->device != cur) cudaSetDevice(p->device);
+    cudaFree(p->packed);  // (synchronises with the device: no enqueue of this plugin is still reading it afterwards)
+    if (p->device >= 0 && p->device != cur) cudaSetDevice(cur);
+    p->packed = nullptr;
+  }
+  std::memset(p->packed_src, 0, sizeof(p->packed_src));
+}
+
+// Layout of the plugin-owned weight copies (independent of S).
+struct PluginPack {
   size_t w1_off, w2_off, b1_off, b2_off, total;
 };
-PluginWs plugin_ws_layout(const b200moe_plugin* p, int S) {
-  PluginWs l;
+PluginPack plugin_pack_layout(const b200moe_plugin* p) {
+  PluginPack l;
   const size_t E = p->num_expert, D = p->idim, H = p->hidden_units;
-  l.route_bytes = carve_workspace(nullptr, S, p->num_expert, p->idim, p->hidden_units, 1).bytes;
-  size_t off = align_up(l.route_bytes, 1024);
+  const size_t wbytes = p->data_type == B200MOE_BF16 ? 0 : E * H * D * sizeof(bf16);  // bf16 inputs are used in place
+  size_t off = 0;
   l.w1_off = off;
-  off = align_up(off + E * H * D * sizeof(bf16), 1024);
+  off = align_up(off + wbytes, 1024);
   l.w2_off = off;
-  off = align_up(off + E * H * D * sizeof(bf16), 1024);
+  off = align_up(off + wbytes, 1024);
   l.b1_off = off;
   off = align_up(off + E * H * sizeof(float), 1024);
   l.b2_off = off;
@@ -806,9 +827,21 @@ PluginWs plugin_ws_layout(const b200moe_plugin* p, int S) {
 }
 }  // namespace
 
+void b200moe_plugin_destroy(b200moe_plugin* p) {
+  if (!p) return;
+  plugin_release(p);
+  delete p;
+}
+
+int b200moe_plugin_invalidate(b200moe_plugin* p) {
+  if (!p) return fail(B200MOE_ERR_ARG, "invalidate: null plugin");
+  std::memset(p->packed_src, 0, sizeof(p->packed_src));  // the buffer itself is kept and re-filled by the next enqueue
+  return B200MOE_OK;
+}
+
 size_t b200moe_plugin_workspace_bytes(const b200moe_plugin* p, int S) {
   if (!p || S < 0) return 0;
-  return plugin_ws_layout(p, S).total;
+  return carve_workspace(nullptr, S, p->num_expert, p->idim, p->hidden_units, 1).bytes;
 }
 
 int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate_idx, const void* w1_weight,
@@ -819,31 +852,53 @@ int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate
   if (S == 0) return B200MOE_OK;
   if (!input || !gate_idx || !w1_weight || !w1_bias || !w2_weight || !w2_bias || !output || !workspace)
     return fail(B200MOE_ERR_ARG, "enqueue: null pointer");
-  const PluginWs l = plugin_ws_layout(p, S);
-  if (workspace_bytes < l.total)
-    return fail(B200MOE_ERR_WORKSPACE, "enqueue: workspace %zu B < required %zu B", workspace_bytes, l.total);
+  const size_t need = carve_workspace(nullptr, S, p->num_expert, p->idim, p->hidden_units, 1).bytes;
+  if (workspace_bytes < need)
+    return fail(B200MOE_ERR_WORKSPACE, "enqueue: workspace %zu B < required %zu B", workspace_bytes, need);
   const int E = p->num_expert, D = p->idim, H = p->hidden_units;
-  char* base = static_cast<char*>(workspace);
-  bf16* w1p = reinterpret_cast<bf16*>(base + l.w1_off);
-  bf16* w2p = reinterpret_cast<bf16*>(base + l.w2_off);
-  float* b1p = reinterpret_cast<float*>(base + l.b1_off);
-  float* b2p = reinterpret_cast<float*>(base + l.b2_off);
   // The reference receives its weights as plugin inputs on every enqueue (README.md:225) and streams them as fp32.
-  // Here they are cast to bf16 once and reused while the four pointers and the workspace stay the same.
+  // Here they are cast once into memory the PLUGIN owns and reused while the four pointers stay the same -- never into
+  // the scratch workspace: TensorRT shares that between the layers of an engine, does not preserve it between
+  // enqueues, and its layout here depends on S (b200moe_plugin_invalidate after an in-place weight update).
   const void* src[4] = {w1_weight, w1_bias, w2_weight, w2_bias};
-  if (p->packed_ws != workspace || std::memcmp(p->packed_src, src, sizeof(src)) != 0) {
-    const size_t nw = static_cast<size_t>(E) * H * D;
-    cudaError_t e = launch_pack_bf16(w1_weight, p->data_type, w1p, nw, stream);
-    if (e == cudaSuccess) e = launch_pack_bf16(w2_weight, p->data_type, w2p, nw, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "enqueue/pack");
-    to_f32_kernel<<<64, 256, 0, stream>>>(w1_bias, p->data_type, b1p, static_cast<size_t>(E) * H);
-    to_f32_kernel<<<64, 256, 0, stream>>>(w2_bias, p->data_type, b2p, static_cast<size_t>(E) * D);
+  const PluginPack l = plugin_pack_layout(p);
+  if (p->packed == nullptr || std::memcmp(p->packed_src, src, sizeof(src)) != 0) {
+    if (p->packed == nullptr) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+        return fail(B200MOE_ERR_ARG, "enqueue: the first enqueue of a plugin allocates its weight copies and cannot be "
+                                      "captured into a CUDA graph; run it once eagerly first");
+      cudaError_t e = cudaGetDevice(&p->device);
+      if (e == cudaSuccess) e = cudaMalloc(&p->packed, l.total);
+      if (e != cudaSuccess) {
+        p->packed = nullptr;
+        return cuda_fail(e, "enqueue/cudaMalloc of the packed weights");
+      }
+    }
+    char* pk = static_cast<char*>(p->packed);
+    cudaError_t e = cudaSuccess;
+    if (p->data_type != B200MOE_BF16) {
+      const size_t nw = static_cast<size_t>(E) * H * D;
+      e = launch_pack_bf16(w1_weight, p->data_type, reinterpret_cast<bf16*>(pk + l.w1_off), nw, stream);
+      if (e == cudaSuccess)
+        e = launch_pack_bf16(w2_weight, p->data_type, reinterpret_cast<bf16*>(pk + l.w2_off), nw, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "enqueue/pack");
+    }
+    to_f32_kernel<<<64, 256, 0, stream>>>(w1_bias, p->data_type, reinterpret_cast<float*>(pk + l.b1_off),
+                                          static_cast<size_t>(E) * H);
+    to_f32_kernel<<<64, 256, 0, stream>>>(w2_bias, p->data_type, reinterpret_cast<float*>(pk + l.b2_off),
+                                          static_cast<size_t>(E) * D);
     count_launch(2);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "enqueue/bias");
     std::memcpy(p->packed_src, src, sizeof(src));
-    p->packed_ws = workspace;
   }
+  char* pk = static_cast<char*>(p->packed);
+  const bool in_place = p->data_type == B200MOE_BF16;
+  const bf16* w1p = in_place ? static_cast<const bf16*>(w1_weight) : reinterpret_cast<const bf16*>(pk + l.w1_off);
+  const bf16* w2p = in_place ? static_cast<const bf16*>(w2_weight) : reinterpret_cast<const bf16*>(pk + l.w2_off);
+  const float* b1p = reinterpret_cast<const float*>(pk + l.b1_off);
+  const float* b2p = reinterpret_cast<const float*>(pk + l.b2_off);
   RouteWs w = carve_workspace(workspace, S, E, D, H, 1);
   const int bn = choose_bn(S, E);
   const int gmax = max_groups(S, E, bn);

@@ -75,7 +75,8 @@ struct EpPeers {
 // Device-side routing state produced by dispatch and consumed by the FFN kernel. Lives in the workspace.
 struct RouteWs {
   int* chunk_hist;   // [kMaxChunks, E] per-dispatch-chunk expert counts (count kernel)
-  int* hist32;       // [ceil(S/32), E] per-32-token expert counts (tensor-core gate)
+  int* hist32;       // [ceil(S/32), E] per-32-token expert counts (tensor-core gate: plain ints; route kernel: the same
+                     //   region as 64-bit self-validating words, hence sized for 8 bytes per entry)
   int* counts;       // [E]
   int* offsets;      // [E + 1]
   int* mapping;      // [Sk]   entry -> expert-order row (-1 = dropped)
@@ -106,7 +107,7 @@ inline RouteWs carve_workspace(void* base, int S, int E, int D, int H, int top_k
     return base ? static_cast<char*>(base) + o : static_cast<char*>(nullptr);
   };
   w.chunk_hist = reinterpret_cast<int*>(take(sizeof(int) * kMaxChunks * E));
-  w.hist32 = reinterpret_cast<int*>(take(sizeof(int) * ((static_cast<size_t>(S) + 31) / 32) * E));
+  w.hist32 = reinterpret_cast<int*>(take(sizeof(long long) * ((static_cast<size_t>(S) + 31) / 32) * E));
   w.counts = reinterpret_cast<int*>(take(sizeof(int) * E));
   w.offsets = reinterpret_cast<int*>(take(sizeof(int) * (E + 1)));
   w.mapping = reinterpret_cast<int*>(take(sizeof(int) * Sk));
@@ -162,6 +163,7 @@ int choose_bn(int Sk, int E);
 // route.cu: gate + dispatch in one launch for small batches (bf16, E <= 32, top-1); same outputs as launch_gate_tc
 // followed by launch_dispatch.
 bool route_supported(int S, int D, int Demb, int E, int top_k, int dtype);
+cudaError_t read_route_status(int* host_status, bool clear);  // synchronous read of the device status word
 void set_route_trace(void* dev_buf);  // debug: 16 records of 16 B per CTA, see tools/route_trace.py
 cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed, const float* br, const int* x_len,
                          int B, int T, int D, int Demb, int E, int gate_mode, int keep_expert_output, int* idx,

@@ -54,14 +54,16 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
                   const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps) {
   // Programmatic dependent launch, both ways.  (1) The next layer's route kernel may start now: it only touches
   // constants (embed, router) until its own griddepcontrol.wait, which returns when this grid has completed.  (2) This
-  // kernel itself never calls griddepcontrol.wait although it is launched early: everything it consumes from the FFN
-  // kernels -- of this rank and of the peers alike -- is covered by the return flags below (this rank's own flag is
-  // raised by the last CTA of its FFN kernel after every CTA's system-scope fence), mapping / score / seq were written
-  // by this layer's route kernel, which completed before the FFN kernel could pass its own wait.
+  // kernel is itself launched early (the FFN kernel releases its dependents at its start) and does its own
+  // griddepcontrol.wait before it reads anything an earlier kernel wrote: seq, mapping and score come from this layer's
+  // route / dispatch kernel, whose stores are only guaranteed visible through the chain of completed grids (a stale seq
+  // would let the flag wait pass on the previous layer's flags).  This rank's own return flag is raised by the last CTA
+  // of the FFN grid, so the wait costs nothing the flags would not have cost.
   ptx::pdl_launch_dependents();
-  // (kLn) gamma / beta are constants of the layer: fetched before the wait for the return flags
+  // (kLn) gamma / beta are constants of the layer: fetched before the waits
   LnAffine<kVec> aff;
   if constexpr (kLn) aff.load(ln_gamma, ln_beta, D, threadIdx.x & 31);
+  ptx::pdl_wait();
   int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
   const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ret_flag);
   if (threadIdx.x < ep.world) {
@@ -70,6 +72,16 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
     if (!ep_wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kEpErrReturnTimeout);
   }
   __syncthreads();
+  // A peer that never delivered (rows out or rows back): the layer's output is POISONED with NaNs rather than built
+  // from stale rows, so that a stalled rank cannot pass for a result; ctrl[3] (b200moe_ep_status) says which wait failed.
+  if (*reinterpret_cast<volatile int*>(&ctrl[3]) != 0) {
+    const size_t n8 = static_cast<size_t>(S) * D / 8;
+    const uint4 nan8 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+      reinterpret_cast<uint4*>(out)[i] = nan8;
+    return;
+  }
   const bf16* ret_y = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.ret_y);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x / 32;

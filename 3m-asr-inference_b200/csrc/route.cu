@@ -24,6 +24,8 @@
 //   route_kernel<.., kLn = true>: the Conformer block's norm_ff (trainer_3m_fix/layer/fmoe_transformer.py:145-148) folded
 //     into the router algebraically, see ln_stats_in_ring below.
 #include <atomic>
+#include <chrono>
+#include <random>
 
 #include <math_constants.h>
 
@@ -49,6 +51,12 @@ constexpr int kRSlots = 2;
 constexpr int kRThreads = 256;
 constexpr uint32_t kRTmemCols = 64;         // 2 accumulator buffers x 32 token columns
 constexpr int kLnWarps = 4;                 // warps 2, 3, 6, 7: row statistics and in-place normalisation when norm_ff is folded in
+constexpr unsigned long long kRouteTimeoutMs = 2000;  // grid-barrier wait before the launch gives up (status word)
+constexpr int kStatusRouteTimeout = 1;
+
+// Device status word of the library's non-EP kernels (b200moe_status): 0 = ok.  A module-scope variable rather than a
+// word in the caller's scratch, which nobody initialises.
+__device__ int g_route_status = 0;
 
 // norm_ff fused into the router ALGEBRAICALLY (kLn).  With mu, r the mean and reciprocal standard deviation of a token row,
 //   LN(x) . Wr_x = r * ( x . W' - mu * c1 ) + c0,    W' = diag(gamma) Wr_x,  c1 = gamma^T Wr_x,  c0 = beta^T Wr_x,
@@ -143,7 +151,7 @@ struct RouteParams {
   const int* x_len;
   int* idx;
   float* score;
-  int* hist32;  // [n_tiles, E]
+  unsigned long long* hist64;  // [n_tiles, E] self-validating words: (launch tag << 8) | count, see the grid barrier
   int S, T, D, Demb, E, gate_mode;
   // dispatch
   const bf16* x;
@@ -166,6 +174,7 @@ struct RouteParams {
   // grid barrier: two 64-bit state words {nonce, count}; see grid_arrive
   unsigned long long* bar;
   unsigned nonce;
+  unsigned long long tag;  // 56 random bits (<< 8) drawn per launch: what makes a histogram word this launch's
   int ep_fold_wait;
   // norm_ff fused into the router (block call, route_kernel<.., kLn = true>); null = off
   const float* ln_gamma;
@@ -495,10 +504,11 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         const unsigned peers = __match_any_sync(0xffffffffu, sel);
         if (sel >= 0 && lane == __ffs(peers) - 1) s_hist[sel] = __popc(peers);
         __syncwarp();
-        // Every histogram word validates itself: (launch tag << 8) | count.  Other CTAs need nothing else from this
-        // tile (idx / score are re-read by this CTA only), so no fence and no release store stand between the arg-max
-        // and the other CTAs seeing the row.
-        if (lane < E) p.hist32[static_cast<size_t>(t) * E + lane] = static_cast<int>((p.nonce << 8) | s_hist[lane]);
+        // Every histogram word validates itself: (56-bit launch tag << 8) | count, one 64-bit store.  Other CTAs need
+        // nothing else from this tile (idx / score are re-read by this CTA only), so no fence and no release store
+        // stand between the arg-max and the other CTAs seeing the row.
+        if (lane < E)
+          p.hist64[static_cast<size_t>(t) * E + lane] = p.tag | static_cast<unsigned long long>(s_hist[lane]);
         if (lane == 0 && it == 0) rtrace(p, 4);
       }
       ptx::named_bar_sync(1, 64);  // s_hi / s_lo / s_hist free for the next tile
@@ -507,8 +517,13 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 
   // ================================================ grid barrier + prefix ================================================
   // There is no counter to contend on and no separate wait: every histogram word carries this launch's tag, every CTA
-  // needs every row for its prefix sums anyway, so it simply re-reads a word until the tag is there.  All CTAs of the
-  // grid are co-resident (grid <= SM count, one CTA per SM), so waiting for the other tiles cannot deadlock.
+  // needs every row for its prefix sums anyway, so it simply re-reads a word until the tag is there.  The workspace is
+  // caller-owned scratch that nobody clears: the tag is 56 RANDOM bits drawn per launch, so that whatever the words
+  // hold beforehand (another layout's mapping / counts, another layer's data, an earlier launch's words) does not pass
+  // for a published tile, and a count above the 32 tokens of a tile is refused as well.  The CTAs of the grid are meant
+  // to be co-resident (grid <= SM count, one CTA per SM); when a foreign kernel holds SMs they become resident as it
+  // drains, and a wait that outlasts the deadline raises the device status word (b200moe_status) instead of trapping:
+  // the launch then completes over whatever counts were seen -- wrong rows, but every index stays in range.
   __syncthreads();
   ptx::pdl_wait();  // (every thread: phase 2 reads and writes the workspace and the row buffers)
   if (threadIdx.x == 0) rtrace(p, 5);
@@ -516,33 +531,38 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const int e = threadIdx.x & 31;
     const int part = threadIdx.x >> 5;  // 8 parts
     const int c_first = blockIdx.x;
-    const unsigned tag = p.nonce & 0x00ffffffu;
-    const unsigned long long deadline = ptx::globaltimer_ns() + 2000000000ull;
+    const unsigned long long tag = p.tag;
+    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * kRouteTimeoutMs;
+    bool gave_up = false;
     int total = 0, before = 0;
     if (e < E)
       for (int r0 = part; r0 < n_tiles; r0 += 8 * 8) {
         // eight rows per batch: the loads are independent and all in flight together (one L2 round trip per batch
         // when the rows are already there), only a word whose tag is still missing is polled on its own
-        unsigned w[8];
+        unsigned long long w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 8 * i;
-          w[i] = r < n_tiles ? static_cast<unsigned>(*(const volatile int*)(p.hist32 + static_cast<size_t>(r) * E + e))
-                             : (tag << 8);
+          w[i] = r < n_tiles ? *(const volatile unsigned long long*)(p.hist64 + static_cast<size_t>(r) * E + e) : tag;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 8 * i;
-          while ((w[i] >> 8) != tag) {
+          while ((w[i] & ~0xffull) != tag || (w[i] & 0xffull) > static_cast<unsigned long long>(kTok)) {
+            if (gave_up || ptx::globaltimer_ns() > deadline) {
+              gave_up = true;
+              w[i] = tag;  // count 0
+              break;
+            }
             __nanosleep(20);
-            if (ptx::globaltimer_ns() > deadline) __trap();  // logic error or foreign process on the SMs: fail, no hang
-            w[i] = static_cast<unsigned>(*(const volatile int*)(p.hist32 + static_cast<size_t>(r) * E + e));
+            w[i] = *(const volatile unsigned long long*)(p.hist64 + static_cast<size_t>(r) * E + e);
           }
-          const int v = static_cast<int>(w[i] & 0xffu);
+          const int v = static_cast<int>(w[i] & 0xffull);
           total += v;
           if (r < c_first) before += v;
         }
       }
+    if (gave_up) atomicExch(&g_route_status, kStatusRouteTimeout);
     s_part[part * 32 + e] = total;
     s_part[256 + part * 32 + e] = before;
   }
@@ -580,7 +600,12 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       if (threadIdx.x < 32) {
         int add = 0;
         if (static_cast<int>(threadIdx.x) < E)
-          for (int r = c - gridDim.x; r < c; ++r) add += p.hist32[static_cast<size_t>(r) * E + threadIdx.x] & 0xff;
+          for (int r = c - gridDim.x; r < c; ++r) {
+            const unsigned long long w = p.hist64[static_cast<size_t>(r) * E + threadIdx.x];
+            // (a word that never arrived counted as 0 in the prefix sums above: keep the two consistent)
+            if ((w & ~0xffull) == p.tag && (w & 0xffull) <= static_cast<unsigned long long>(kTok))
+              add += static_cast<int>(w & 0xffull);
+          }
         s_before[threadIdx.x] += add;
       }
       __syncthreads();
@@ -809,7 +834,32 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 std::atomic<unsigned> g_route_nonce{1};
 void* g_route_trace = nullptr;
 
+// 56 random bits per launch (splitmix64 over a counter seeded from the clock and an address): see the grid barrier.
+unsigned long long next_route_tag() {
+  static std::atomic<unsigned long long> ctr{[] {
+    unsigned long long s = static_cast<unsigned long long>(std::chrono::steady_clock::now().time_since_epoch().count());
+    s ^= static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(&g_route_trace)) << 17;
+    s ^= static_cast<unsigned long long>(std::random_device{}()) << 32;
+    return s;
+  }()};
+  unsigned long long z = ctr.fetch_add(0x9e3779b97f4a7c15ull, std::memory_order_relaxed) + 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  z &= ~0xffull;
+  return z != 0 ? z : 0x5bd1e99500ull;  // never the all-zero tag (cleared words)
+}
+
 }  // namespace
+
+cudaError_t read_route_status(int* host_status, bool clear) {
+  cudaError_t e = cudaMemcpyFromSymbol(host_status, g_route_status, sizeof(int));
+  if (e == cudaSuccess && clear && *host_status != 0) {
+    const int zero = 0;
+    e = cudaMemcpyToSymbol(g_route_status, &zero, sizeof(int));
+  }
+  return e;
+}
 
 void set_route_trace(void* dev_buf) { g_route_trace = dev_buf; }
 
@@ -846,7 +896,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   p.x_len = x_len;
   p.idx = idx;
   p.score = score;
-  p.hist32 = ws.hist32;
+  p.hist64 = reinterpret_cast<unsigned long long*>(ws.hist32);
   p.S = S;
   p.T = T;
   p.D = D;
@@ -876,6 +926,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   unsigned nonce = g_route_nonce.fetch_add(1, std::memory_order_relaxed) & 0x00ffffffu;
   if (nonce == 0) nonce = g_route_nonce.fetch_add(1, std::memory_order_relaxed) & 0x00ffffffu;
   p.nonce = nonce;
+  p.tag = next_route_tag();
   p.ep_fold_wait = ep_fold_wait ? 1 : 0;
   // kLn: `wr_packed` is the pre-scaled router of b200moe_pack_router_ln and ln_c its c1 / c0 tail
   p.ln_gamma = (ln_gamma != nullptr && ln_beta != nullptr && ln_c != nullptr) ? ln_gamma : nullptr;

@@ -14,11 +14,19 @@ class NaiveGate(nn.Module):
         self.gate = nn.Linear(d_model, num_expert * world_size)
         self.top_k = top_k
 
+    def invalidate_packed(self) -> None:
+        self._wr_key = None
+        self._wrp_key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+
     def router_params(self):
         """(Wr [d, E_total] fp32 contiguous, br [E_total]) in the layout the kernels take."""
         w = self.gate.weight
         key = (w.data_ptr(), w._version, str(w.device))
-        if getattr(self, "_wr_key", None) != key:
+        if getattr(self, "_wr_key", None) is None or self._wr_key != key:
             self._wr = w.detach().float().t().contiguous()
             self._wr_key = key
         b = self.gate.bias
@@ -29,7 +37,7 @@ class NaiveGate(nn.Module):
         Wr, _ = self.router_params()
         if Wr.shape[1] > 32 or not Wr.is_cuda:
             return None
-        if getattr(self, "_wrp_key", None) != self._wr_key:
+        if getattr(self, "_wrp_key", None) is None or self._wrp_key != self._wr_key:
             self._wrp = ops.pack_router(Wr)
             self._wrp_key = self._wr_key
         return self._wrp

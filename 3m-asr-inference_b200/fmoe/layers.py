@@ -47,9 +47,16 @@ def activation_code(act) -> int:
 
 
 class PackedExpertCache:
-    """bf16 copies of the expert weights, refreshed when the parameters change (load_state_dict, .to(), optimiser step)."""
+    """bf16 copies of the expert weights, refreshed when the parameters change (load_state_dict, .to(), optimiser step).
+    The key is (data_ptr, _version, device) per parameter.  Writes through `param.data` (p.data.copy_ / fill_ / add_, the
+    idiom of the reference's own FMoELinear init and BMUF sync, utils/fmoe_localComm_bmuf.py) do NOT bump `_version`:
+    after such an update call `invalidate()` here, or `invalidate_packed_weights(model)` for a whole model."""
 
     def __init__(self):
+        self._key = None
+        self._packed = None
+
+    def invalidate(self) -> None:
         self._key = None
         self._packed = None
 
@@ -88,6 +95,16 @@ class FMoE(nn.Module):
         self.ep_group = None  # torch.distributed group of the expert-parallel workers (world_size > 1)
         self.ep_capacity = 8192  # tokens per rank per call the expert-parallel receive buffers are sized for
 
+    def invalidate_packed(self) -> None:
+        """Drop the bf16 / hi-lo packed copies of the expert and router weights (after an in-place `.data` update)."""
+        self._cache.invalidate()
+        if hasattr(self.gate, "invalidate_packed"):
+            self.gate.invalidate_packed()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+
     def _expert_layers(self):
         e = self.experts
         for a, b in (("htoh4", "h4toh"), ("w_1", "w_2"), ("hid_proj", "mem_proj")):
@@ -125,3 +142,11 @@ class FMoE(nn.Module):
         if self.gate_hook:
             self.gate_hook(res.idx.view(-1).long(), res.score.view(-1, 1, self.top_k), None)
         return res.out.reshape(inp.shape)
+
+
+def invalidate_packed_weights(model: nn.Module) -> None:
+    """Walks `model` and drops every cached packed copy (experts, routers, folded-LayerNorm routers).  Needed after
+    weights were changed through `.data` (no autograd version bump); load_state_dict does it on its own."""
+    for m in model.modules():
+        if hasattr(m, "invalidate_packed"):
+            m.invalidate_packed()

@@ -63,6 +63,16 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
         if capacity_factor is not None and capacity_factor > 0:
             raise NotImplementedError("token dropping by capacity is a training-time feature (cf = -1 at inference)")
 
+    def invalidate_packed(self) -> None:
+        """Drop the packed copies of experts and router (weights changed through `.data`: no version bump to key on)."""
+        self._cache.invalidate()
+        self._wrp_key = None
+        self._wrln_key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+
     ep_capacity = 8192   # tokens per rank per call the expert-parallel receive buffers are sized for
 
     def _ep_context(self, n_tokens: int):
@@ -91,7 +101,7 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
             return None
         w = self.router_weights
         key = (w.data_ptr(), w._version, str(w.device))
-        if getattr(self, "_wrp_key", None) != key:
+        if getattr(self, "_wrp_key", None) is None or self._wrp_key != key:
             self._wrp = ops.pack_router(wr)
             self._wrp_key = key
         return self._wrp
@@ -103,7 +113,7 @@ class LocalFmoeCatEmbedFeedForward(torch.nn.Module):
         w = self.router_weights
         key = (w.data_ptr(), w._version, norm_ff.weight.data_ptr(), norm_ff.weight._version, norm_ff.bias.data_ptr(),
                norm_ff.bias._version, str(w.device))
-        if getattr(self, "_wrln_key", None) != key:
+        if getattr(self, "_wrln_key", None) is None or self._wrln_key != key:
             self._wrln = ops.pack_router_ln(wr, norm_ff.weight.detach().float().contiguous(),
                                             norm_ff.bias.detach().float().contiguous())
             self._wrln_key = key

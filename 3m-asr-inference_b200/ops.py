@@ -60,6 +60,15 @@ def config(key: str, value: int) -> None:
     _lib.check(_lib.load().b200moe_config(key.encode(), int(value)), "b200moe_config")
 
 
+def status(clear: bool = True) -> int:
+    """Device status word of the kernels launched so far (synchronous read): 0 ok, 1 = a fused gate + dispatch launch
+    gave up waiting for its grid (include/b200moe.h, b200moe_status)."""
+    import ctypes
+    st = ctypes.c_int(0)
+    _lib.check(_lib.load().b200moe_status(ctypes.byref(st), int(clear)), "b200moe_status")
+    return st.value
+
+
 def profile_enable(on: bool) -> None:
     _lib.check(_lib.load().b200moe_profile_enable(int(on)), "b200moe_profile_enable")
 

@@ -74,6 +74,10 @@ class FMoEExpertPlugin:
         v = struct.unpack("8i", self.serialize())
         return {"data_type": v[0], "num_expert": v[1], "idim": v[2], "hidden_units": v[3], "act_type": v[4]}
 
+    def invalidate(self) -> None:
+        """Weights were updated in place behind the same pointers: the next enqueue re-packs them."""
+        _lib.check(_lib.load().b200moe_plugin_invalidate(self._h), "b200moe_plugin_invalidate")
+
     # -- execution ------------------------------------------------------------------------------------------------------
     def get_workspace_size(self, S: int) -> int:
         return int(_lib.load().b200moe_plugin_workspace_bytes(self._h, S))

@@ -25,8 +25,10 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless its comment says "host";
- *   - memory is caller-owned; no entry point allocates device memory, none synchronises the host, all work is
- *     enqueued on the caller's stream, so every entry point is CUDA-graph capturable;
+ *   - memory is caller-owned; no per-layer entry point allocates device memory, none synchronises the host, all
+ *     work is enqueued on the caller's stream, so every one of them is CUDA-graph capturable (the one exception:
+ *     the FIRST b200moe_plugin_enqueue of a plugin object allocates the plugin's own weight copies);
+ *   - workspaces are pure scratch: they need no initialisation and nothing has to survive in them between calls;
  *   - return value: 0 = ok, negative = error (B200MOE_ERR_*); b200moe_last_error() gives the message of the
  *     calling thread's last failure;
  *   - there is no CPU fallback: on a machine without an sm_100 GPU the compute entry points return
@@ -71,6 +73,12 @@ enum {
 };
 
 const char* b200moe_last_error(void);
+/* Device-side status of the kernels launched so far on the current device (synchronous 4-byte read; call it at a point
+ * where the stream is synchronised anyway): 0 = ok, 1 = a fused gate + dispatch launch gave up waiting for the other
+ * CTAs of its grid (SMs held by a foreign kernel for > 2 s): that layer's output is undefined, nothing was written out
+ * of range and the context stays usable.  clear != 0 resets the word.  (The reference's enqueue has the same int-status
+ * contract but can only ever return 0: fmoe_expert_plugin.cpp:247-268, common/common.h:26-38.) */
+int b200moe_status(int* host_status, int clear);
 int b200moe_version(void);
 /* 1 if device `dev` can run the kernels (compute capability 10.x), 0 if not, negative on CUDA error. */
 int b200moe_device_supported(int dev);
@@ -227,14 +235,19 @@ size_t b200moe_plugin_serialization_size(const b200moe_plugin* p);
 int b200moe_plugin_serialize(const b200moe_plugin* p, void* host_buffer);
 b200moe_plugin* b200moe_plugin_deserialize(const void* host_data, size_t length);
 void b200moe_plugin_destroy(b200moe_plugin* p);
-/* getWorkspaceSize: includes room for the bf16 copy of the weights the first enqueue packs. */
+/* getWorkspaceSize (fmoe_expert_plugin.cpp:224-239): scratch for S tokens.  Pure scratch: nothing is expected to survive
+ * in it between two enqueues, so TensorRT may share it between layers and pass a different S every time. */
 size_t b200moe_plugin_workspace_bytes(const b200moe_plugin* p, int S);
 /* enqueue: the reference's six inputs in the reference's order -- input [S, idim], gate_idx [S] int32,
  * w1_weight [E, H, D], w1_bias [E, H], w2_weight [E, D, H], w2_bias [E, D] (all `data_type` except gate_idx) --
- * and its single un-weighted output [S, idim].  Weights are re-packed only when their pointers change. */
+ * and its single un-weighted output [S, idim].  The bf16 / fp32 copies of the weights live in memory the plugin owns
+ * (cudaMalloc by the first enqueue -- which therefore cannot be captured into a CUDA graph -- freed by destroy) and are
+ * re-made only when one of the four weight pointers changes, or after b200moe_plugin_invalidate (weights updated in
+ * place behind the same pointers, e.g. a TensorRT refit). */
 int b200moe_plugin_enqueue(b200moe_plugin* p, const void* input, const int* gate_idx, const void* w1_weight,
                            const void* w1_bias, const void* w2_weight, const void* w2_bias, int S, void* output,
                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int b200moe_plugin_invalidate(b200moe_plugin* p);
 
 /* ---- companion gate plugin: SoftmaxTopKPluginDynamic (softmax_topk_plugin.cpp:88-136) --------------------------
  * logits [B, T, E] in `data_type`, mask [B] int32 (valid lengths) -> value [B, T] (`data_type`), idx [B, T]

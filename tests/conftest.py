@@ -58,6 +58,19 @@ def load_golden(name: str):
     return out
 
 
+def load_golden_repo_dims(synth):
+    """case_3m_repo_dims.npz (E=32, D=512, H=1024): activations, router and the reference's outputs come from the file,
+    the 128 MiB of expert weights are re-generated from the recorded seed and checked against the recorded checksums."""
+    g = load_golden("case_3m_repo_dims.npz")
+    w = synth.make_weights(int(g["weight_seed"]), 32, 512, 1024, 512, random_bias=True)
+    assert torch.equal(w.Wr, g["Wr"]), "seeded weight stream differs from the one the fixture was made with"
+    for name in ("W1", "W2", "b1", "b2"):
+        assert abs(float(getattr(w, name).double().sum()) - float(g[name + "_sum"])) < 1e-9, name
+    probe = torch.arange(0, 32 * 1024 * 512, 1048573)[:16]
+    assert torch.equal(w.W1.reshape(-1)[probe], g["W1_probe"]) and torch.equal(w.W2.reshape(-1)[probe], g["W2_probe"])
+    return g, w
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.double().cpu()
     b = b.double().cpu()

@@ -189,6 +189,39 @@ def main():
         out=out.numpy(), ff_scale=np.float32(block.ff_scale), eps=np.float64(block.norm_ff.eps))
     print("case_block_3m: counts", local_cnt.tolist())
 
+    # ---------------- case D: the repo's own dimensions (E=32, D=512, embed 512, H=1024), 3M router, Swish experts ----------------
+    # 128 MiB of fp32 expert weights do not belong in a fixture: they are re-generated from the seed by the same
+    # synth.make_weights call in the tests (CPU mt19937 stream), and pinned here by checksums and sample values.
+    E, D, Demb, H, S = 32, 512, 512, 1024, 64
+    w = synth.make_weights(1004, E, D, H, Demb, random_bias=True)
+    x, embed = synth.make_activations(2004, S, D, Demb, w, top_k=1)
+    l1 = layers.FMoELinear(E, D, H, bias=True)
+    l2 = layers.FMoELinear(E, H, D, bias=True)
+    assert tuple(l1.weight.shape) == (E, H, D) and tuple(l2.weight.shape) == (E, D, H)
+    layer = dfsmn.cFSMN_layer(D, Demb, hid_dim=H, mem_dim=D, num_experts=E, rank=0, world_size=1,
+                              capacity_factor=-1, skip_connect=True, rand_init_router=True)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        layer.rooter_weights.copy_(w.Wr)
+        gate_idx, gate_value, _aux, _n = layer.gate(torch.cat([embed, x], dim=-1))
+        expert_fn = expert_fn_factory(w.W1, w.b1, w.W2, w.b2, swish)
+        expert_outputs = dfsmn._fmoe_general_global_forward(x, gate_idx, expert_fn, E, 1, capacity=-1)
+        _pos, local_cnt, _g, fwd_cnt, fwd_bs = F.moe_prepare_forward(gate_idx, E, 1)
+        final = x + 0.5 * expert_outputs * gate_value.unsqueeze(1)
+    torch.set_num_threads(1)
+    probe = torch.arange(0, E * H * D, 1048573)[:16]
+    np.savez_compressed(
+        os.path.join(HERE, "case_3m_repo_dims.npz"),
+        x_bf16=bits(x), embed_bf16=bits(embed), Wr_bf16=bits(w.Wr), weight_seed=np.int64(1004),
+        W1_sum=np.float64(w.W1.double().sum()), W2_sum=np.float64(w.W2.double().sum()),
+        b1_sum=np.float64(w.b1.double().sum()), b2_sum=np.float64(w.b2.double().sum()),
+        W1_probe=w.W1.reshape(-1)[probe].numpy(), W2_probe=w.W2.reshape(-1)[probe].numpy(),
+        gate_idx=gate_idx.numpy().astype(np.int64), gate_value=gate_value.numpy(),
+        expert_count=local_cnt.numpy().astype(np.int64), fwd_batch_size=np.int64(fwd_bs),
+        expert_outputs=expert_outputs.numpy().astype(np.float32), final=final.numpy().astype(np.float32),
+        ff_scale=np.float32(0.5))
+    print("case_3m_repo_dims: counts", local_cnt.tolist())
+
 
 if __name__ == "__main__":
     main()

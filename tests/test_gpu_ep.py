@@ -26,7 +26,8 @@ E, D, H, DEMB = 32, 512, 1024, 512
 
 
 def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=None, random_bias=True, seed=4242,
-              layers=1, keep_expert_output=False, stage_seq=(1, 2, 4)):
+              layers=1, keep_expert_output=False, stage_seq=(1, 2, 4), x_lens=None):
+    """x_lens: per rank an int32 tensor of valid lengths (sizes[r] = len(x_lens[r]) * T_r padded rows) or None."""
     gate_mode = ops.GATE_3M if gate_mode is None else gate_mode
     dev = torch.device("cuda")
     E_local = E // world
@@ -39,6 +40,9 @@ def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=No
     cur = [a[0].cuda().bfloat16() for a in acts]
     emb = [None if a[1] is None else a[1].cuda().bfloat16() for a in acts]
     ref_cur = [a[0] for a in acts]
+    xl = [None] * world if x_lens is None else x_lens
+    Ts = [None if xl[r] is None else sizes[r] // len(xl[r]) for r in range(world)]
+    xl_dev = [None if t is None else t.cuda() for t in xl]
     last = None
     for li, w in enumerate(ws):
         Wr = w.Wr.cuda()
@@ -60,12 +64,14 @@ def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=No
             for r in range(world):
                 ctxs[r].forward(cur[r], emb[r], Wr, br, mine[r], residual=None, top_k=top_k, gate_mode=gate_mode,
                                 ff_scale=1.0, out=moes[r], Wr_packed=packed, return_routing=True, stages=stage,
-                                routing_bufs=rbufs[r], keep_expert_output=keep_expert_output)
+                                routing_bufs=rbufs[r], keep_expert_output=keep_expert_output, x_len=xl_dev[r],
+                                seq_len=Ts[r])
         for stage in stage_seq:
             for r in range(world):
                 ctxs[r].forward(cur[r], emb[r], Wr, br, mine[r], residual=cur[r], top_k=top_k, gate_mode=gate_mode,
                                 ff_scale=0.5, out=outs[r], Wr_packed=packed, return_routing=True, stages=stage,
-                                routing_bufs=rbufs[r], keep_expert_output=keep_expert_output)
+                                routing_bufs=rbufs[r], keep_expert_output=keep_expert_output, x_len=xl_dev[r],
+                                seq_len=Ts[r])
         torch.cuda.synchronize()
         for r in range(world):
             assert ctxs[r].status() == 0, f"rank {r}: a wait on a peer flag timed out (status {ctxs[r].status()})"
@@ -76,7 +82,8 @@ def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=No
             ref = oracle.moe_forward(xin, None if emb[r] is None else emb[r].float().cpu(), w.Wr, w.br, w.W1, w.b1,
                                      w.W2, w.b2, top_k=top_k,
                                      gate_mode=(oracle.GATE_3M if gate_mode == ops.GATE_3M else oracle.GATE_NAIVE),
-                                     residual=xin, ff_scale=0.5, keep_expert_output=keep_expert_output)
+                                     residual=xin, ff_scale=0.5, keep_expert_output=keep_expert_output,
+                                     x_len=xl[r], T=Ts[r])
             idx, score, counts, mapping = rbufs[r]
             if sizes[r] > 0:
                 if top_k == 1:
@@ -117,6 +124,17 @@ def test_ep_cfg3_shape_two_layers(ops, ep_mod, synth, oracle):
     run_world(ops, ep_mod, synth, oracle, 2, [3200, 3200], layers=2, random_bias=False)
 
 
+def test_ep_cfg4_shape_ragged_batches(ops, ep_mod, synth, oracle):
+    """BASELINE.json configs[3]: 256 utterances of 100-1000 frames over 8 ranks (32 each, padded per rank, x_len-masked),
+    4 experts per rank."""
+    g = torch.Generator().manual_seed(20260004)
+    frames = torch.randint(100, 1001, (256,), generator=g)
+    lens = (((frames - 1) // 2 - 1) // 2).to(torch.int32)
+    x_lens = [lens[32 * r:32 * (r + 1)].contiguous() for r in range(8)]
+    sizes = [32 * int(t.max()) for t in x_lens]
+    run_world(ops, ep_mod, synth, oracle, 8, sizes, x_lens=x_lens, random_bias=False)
+
+
 def test_ep_naive_top2(ops, ep_mod, synth, oracle):
     run_world(ops, ep_mod, synth, oracle, 4, [64, 100, 3, 129], top_k=2, gate_mode=ops.GATE_NAIVE)
 
@@ -130,3 +148,27 @@ def test_ep_whole_layer_in_one_call(ops, ep_mod, synth, oracle, S):
     """stages = 7, the call a multi-process rank makes: the dispatch kernel's last CTA itself waits for the arrival
     flags and builds the group table (no separate wait kernel).  With one rank every flag it waits for is its own."""
     run_world(ops, ep_mod, synth, oracle, 1, [S], layers=2, stage_seq=(7,))
+
+
+def test_ep_stalled_peer_poisons_the_output(ops, ep_mod, synth):
+    """A peer that never shows up must not pass for a result: the waits time out (bounded spin), the status word says
+    which one, and the layer's output is NaN instead of stale rows."""
+    dev = torch.device("cuda")
+    world, S = 2, 40
+    ctxs = ep_mod.EpContext.simulate(world, E // world, D, S, dev, timeout_ms=100)
+    w = synth.make_weights(991, E, D, H, DEMB)
+    x, embed = synth.make_activations(992, S, D, DEMB, w)
+    xd, ed, Wr = x.cuda().bfloat16(), embed.cuda().bfloat16(), w.Wr.cuda()
+    full = ops.pack_experts(w.W1.cuda(), w.b1.cuda(), w.W2.cuda(), w.b2.cuda())
+    El = E // world
+    mine = ops.PackedExperts(full.W1[:El].contiguous(), full.b1[:El].contiguous(), full.W2[:El].contiguous(),
+                             full.b2[:El].contiguous())
+    out = torch.zeros_like(xd)
+    for stage in (1, 2, 4):   # rank 0 alone: rank 1 neither sends its rows nor returns rank 0's
+        ctxs[0].forward(xd, ed, Wr, None, mine, residual=xd, ff_scale=0.5, out=out, Wr_packed=ops.pack_router(Wr),
+                        stages=stage)
+    torch.cuda.synchronize()
+    assert ctxs[0].status() != 0
+    assert torch.isnan(out.float()).all()
+    for c in ctxs:
+        c.close()

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from conftest import load_golden, pkg, rel_l2
+from conftest import load_golden, load_golden_repo_dims, pkg, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -65,6 +65,42 @@ def test_golden_3m_top1(ops, oracle):
     # un-weighted, no residual == FMoEExpertPlugin's output
     res2 = run_layer(ops, w, g["x"], g["embed"], dtype=torch.float32, residual=False, keep_expert_output=True)
     assert rel_l2(res2.out.cpu(), g["expert_outputs"]) <= BF16_REL_L2
+
+
+def test_golden_3m_repo_dims(ops, oracle, synth):
+    """Reference-generated vectors at the repo's own dimensions (E=32, D=512, H=1024) through the CUDA path, bf16."""
+    g, w = load_golden_repo_dims(synth)
+    res = run_layer(ops, w, g["x"], g["embed"], ff_scale=float(g["ff_scale"]))
+    assert torch.equal(res.idx.cpu().view(-1).long(), g["gate_idx"])
+    assert torch.equal(res.counts.cpu().long(), g["expert_count"])
+    torch.testing.assert_close(res.score.cpu().view(-1), g["gate_value"], rtol=2e-5, atol=1e-7)
+    assert rel_l2(res.out.float().cpu(), g["final"]) <= BF16_REL_L2
+    res2 = run_layer(ops, w, g["x"], g["embed"], residual=False, keep_expert_output=True)
+    assert rel_l2(res2.out.float().cpu(), g["expert_outputs"]) <= BF16_REL_L2
+
+
+def test_cfg4_shape_ragged_batch(ops, oracle, synth):
+    """BASELINE.json configs[3], one GPU's share: 32 utterances of 100-1000 frames (24-249 tokens after subsampling),
+    padded to the longest, padding masked by x_len (rows >= x_len[b] are not routed, output = residual:
+    softmax_topk_kernel.cu:40, fmoe_expert_plugin.cpp:244-245)."""
+    E, D, H, Demb, B = 32, 512, 1024, 512, 32
+    g = torch.Generator().manual_seed(20260004)
+    frames = torch.randint(100, 1001, (B,), generator=g)
+    x_len = (((frames - 1) // 2 - 1) // 2).to(torch.int32)
+    T = int(x_len.max())
+    S = B * T
+    w = synth.make_weights(20260401, E, D, H, Demb, random_bias=True)
+    x, embed = synth.make_activations(20260402, S, D, Demb, w)
+    ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5, x_len=x_len, T=T)
+    res = run_layer(ops, w, x, embed, ff_scale=0.5, x_len=x_len, T=T)
+    check_against_oracle(oracle, res, ref)
+    pad = (torch.arange(S) % T) >= x_len.long().repeat_interleave(T)
+    assert int(pad.sum()) > 0
+    assert torch.equal(res.idx.cpu().view(-1)[pad], torch.full((int(pad.sum()),), -1, dtype=torch.int32))
+    assert torch.equal(res.out.float().cpu()[pad], x[pad])            # padded rows: the residual, bit for bit
+    res2 = run_layer(ops, w, x, embed, residual=False, ff_scale=1.0, x_len=x_len, T=T)
+    assert rel_l2(res2.out.float().cpu(), ref["moe"]) <= 2 * BF16_REL_L2
+    assert float(res2.out.float().cpu()[pad].abs().max()) == 0.0
 
 
 def test_golden_naive_top2(ops, oracle):
@@ -243,6 +279,42 @@ def test_plugin_enqueue_matches_reference_contract(ops, oracle, synth):
     q = creator.deserialize_plugin("plugin", p.serialize())
     out3 = q.enqueue([x.cuda(), gate_idx.cuda(), w.W1.cuda(), w.b1.cuda(), w.W2.cuda(), w.b2.cuda()])
     assert rel_l2(out2.cpu(), out.cpu()) < 1e-6 and torch.equal(out3, out2)
+
+
+def test_plugin_shared_scratch_and_changing_shapes(ops, oracle, synth):
+    """TensorRT hands ONE scratch workspace to every layer of an engine, does not preserve it between enqueues and
+    passes a different S per utterance: the plugin may keep nothing in it (its weight copies are plugin-owned)."""
+    plugin = pkg("plugin")
+    E, D, H = 8, 256, 512
+    wa = synth.make_weights(171, E, D, H, 0, random_bias=True)
+    wb = synth.make_weights(172, E, D, H, 0, random_bias=True)
+    creator = plugin.PluginRegistry().get_plugin_creator("FMoEExpertPluginDynamic", "1", "")
+    fields = {"data_type": 0, "num_expert": E, "idim": D, "hidden_units": H}
+    pa, pb = creator.create_plugin("a", fields), creator.create_plugin("b", fields)
+    ws = torch.empty(max(pa.get_workspace_size(200), pb.get_workspace_size(200)), dtype=torch.uint8, device="cuda")
+    dev_a = [t.cuda() for t in (wa.W1, wa.b1, wa.W2, wa.b2)]
+    dev_b = [t.cuda() for t in (wb.W1, wb.b1, wb.W2, wb.b2)]
+
+    def check(p, w, dev_w, S, seed):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(1, S, D, generator=g).bfloat16().float()
+        gate_idx = torch.randint(0, E, (1, S, 1), generator=g, dtype=torch.int32)
+        out = p.enqueue([x.cuda(), gate_idx.cuda(), *dev_w], workspace=ws)
+        prep = oracle.prepare(gate_idx.view(-1), E)
+        ybuf = oracle.expert_ffn(x.view(S, D)[prep["pos"]], prep["counts"], w.W1, w.b1, w.W2, w.b2, 0)
+        assert rel_l2(out.cpu().view(S, D), ybuf[prep["mapping"]]) <= BF16_REL_L2
+
+    check(pa, wa, dev_a, 200, 1)
+    check(pa, wa, dev_a, 50, 2)      # another S on the same workspace: the layout of the scratch moves
+    check(pb, wb, dev_b, 200, 3)     # another layer's plugin scribbles over the shared scratch
+    ws.fill_(0xA5)                   # ... and so may anything else between two enqueues
+    check(pa, wa, dev_a, 200, 4)
+    check(pb, wb, dev_b, 37, 5)
+    check(pa, wa, dev_a, 50, 6)
+    # weights updated in place behind the same pointers need an explicit invalidate
+    dev_a[0].copy_(wb.W1.cuda()); dev_a[1].copy_(wb.b1.cuda()); dev_a[2].copy_(wb.W2.cuda()); dev_a[3].copy_(wb.b2.cuda())
+    pa.invalidate()
+    check(pa, wb, dev_a, 64, 7)
 
 
 def test_module_mirrors(ops, oracle, synth):

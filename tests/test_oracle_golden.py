@@ -3,7 +3,7 @@ NaiveGate, moe_prepare_forward, MOEScatter, MOEbiasLinear, MOEGather, _fmoe_gene
 router gate, run on CPU with only the absent fmoe_cuda primitives stubbed."""
 import torch
 
-from conftest import load_golden, rel_l2
+from conftest import load_golden, load_golden_repo_dims, rel_l2
 
 
 def test_3m_top1_matches_reference(oracle):
@@ -19,6 +19,18 @@ def test_3m_top1_matches_reference(oracle):
     y_tok = r["ybuf"][r["mapping"].view(-1)]
     assert rel_l2(y_tok, g["expert_outputs"]) < 1e-6
     assert rel_l2(r["moe"], g["weighted"]) < 1e-6
+    assert rel_l2(r["out"], g["final"]) < 1e-6
+
+
+def test_3m_repo_dims_matches_reference(oracle, synth):
+    """The same reference code at the repo's own dimensions (32 experts, 512 -> 1024 -> 512, cat-embed router)."""
+    g, w = load_golden_repo_dims(synth)
+    r = oracle.moe_forward(g["x"], g["embed"], w.Wr, None, w.W1, w.b1, w.W2, w.b2, top_k=1, gate_mode=oracle.GATE_3M,
+                           act_type=oracle.ACT_SILU, residual=g["x"], ff_scale=float(g["ff_scale"]))
+    assert torch.equal(r["idx"].view(-1), g["gate_idx"])
+    assert torch.equal(r["counts"], g["expert_count"]) and int(r["counts"].sum()) == int(g["fwd_batch_size"])
+    torch.testing.assert_close(r["score"].view(-1), g["gate_value"], rtol=1e-5, atol=1e-7)
+    assert rel_l2(r["ybuf"][r["mapping"].view(-1)], g["expert_outputs"]) < 1e-6
     assert rel_l2(r["out"], g["final"]) < 1e-6
 
 
