@@ -305,9 +305,25 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
         for (int r = 0; r < kRowsPerBatch; ++r) {
           const int j = j0 + r * kWarps;
           if (j < n && d[r] < 0) {
+            // 16-byte accesses, four loads in flight before their stores (the two buffers may alias as far as the
+            // compiler knows: element-wise this was one dependent L2 round trip per element)
             const size_t row = static_cast<size_t>(seg + j) / top_k * D;
-            for (int c = lane; c < D; c += 32)
-              drop_out[row + c] = drop_residual ? drop_residual[row + c] : from_float<InT>(0.0f);
+            uint4* orow = reinterpret_cast<uint4*>(drop_out + row);
+            const uint4* rrow = reinterpret_cast<const uint4*>(drop_residual + row);
+            const int nv = D * static_cast<int>(sizeof(InT)) / 16;  // D % 8 == 0
+            for (int c0 = 0; c0 < nv; c0 += 128) {
+              uint4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * 32 + lane;
+                v[u] = (drop_residual != nullptr && c < nv) ? __ldg(rrow + c) : make_uint4(0u, 0u, 0u, 0u);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * 32 + lane;
+                if (c < nv) orow[c] = v[u];
+              }
+            }
           }
         }
       }

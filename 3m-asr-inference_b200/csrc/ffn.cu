@@ -67,6 +67,7 @@ struct FfnParams {
   int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
   int kps;  // k-blocks (of 64) per pipeline stage: one TMA instruction per operand brings all of them
   int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
+  int warm_mma;     // issue one throw-away MMA before the first tile (B200MOE_WARM, default 1)
   // expert parallelism: results go to the source rank's return buffer over peer-mapped memory (NVLink)
   int ep;                           // 0 = off
   int ep_world, ep_rank;
@@ -75,7 +76,8 @@ struct FfnParams {
   int* ep_ctrl;                     // local control block
   int* clear_ptr;   // zeroed at kernel start, spread over the CTAs (tagged histogram words of the route kernel)
   int clear_ints;
-  int dbg;          // timing experiments only (B200MOE_DBG): 1 = no phase-2 stores, 2 = no phase-1 stores, 4 = no residual
+  int dbg;          // timing experiments only (B200MOE_DBG): 1 = no phase-2 stores, 2 = no phase-1 stores, 4 = no residual,
+                    // 8 / 16 = no B-operand loads in GEMM 1 / 2, 32 = no wait for h
   uint64_t w_policy;  // L2 eviction policy of the weight tiles: evict-first when every tile is read once
   // debug timeline (ffn_kernel<.., true> only): per CTA `trace_cap` records of {tile, event, globaltimer lo, hi}
   uint4* trace;
@@ -87,7 +89,13 @@ enum TraceEvent : int {
   kEvMmaFirstData = 5, kEvMmaIssued = 6, kEvEpiAccReady = 7, kEvEpiAccReleased = 8, kEvEpiStored = 9,
   kEvEpiPublished = 10, kEvKernelEnd = 11, kEvEpiChunkLd = 12, kEvEpiChunkStaged = 13, kEvEpiChunkDone = 14,
   kEvClock = 15,        // time fields = %globaltimer (ns) ...
-  kEvClockCycles = 16   // ... and clock64 read right after it
+  kEvClockCycles = 16,  // ... and clock64 read right after it
+  kEvProdSlotFree = 17, // first two tiles of a CTA only: the producer's wait for ring slot of stage `kb` is over (tile field = kb)
+  kEvMmaStageData = 18, // ... the MMA thread's wait for the data of stage `kb` is over
+  kEvMmaStageIssued = 19,
+  kEvMmaInstr = 20,     // first stage of a CTA's first tile only: after every single tcgen05.mma (tile field = j * 4 + k)
+  kEvWarmIssued = 21,   // trace only: a batch of 8 throw-away MMAs issued at kernel start (tile field = batch) ...
+  kEvWarmDone = 22      // ... and completed (commit -> mbarrier -> wait)
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -368,6 +376,39 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  if (warp == 1 && lane == 0 && (kCtas == 1 || leader) && p.warm_mma) {
+    // The first tcgen05.mma an SM executes in a kernel takes ~2 us to issue (measured: 2.2 us for the first stage's
+    // eight instructions against 0.3 us for every later stage).  One throw-away instruction over whatever the ring
+    // holds, into the first accumulator (the first real MMA of a tile overwrites it), pays that here -- on-chip state
+    // only, so under programmatic dependent launch it overlaps the previous kernel's tail.
+    const uint32_t idesc = ptx::make_idesc(kTf32 ? 2u /*tf32*/ : 1u /*bf16*/, kBlockM * kCtas,
+                                           static_cast<uint32_t>(p.bn));
+    const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a);
+    const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b);
+    for (int i = 0; i < p.warm_mma; ++i) {
+      if constexpr (kTf32) ptx::umma_tf32_ss(tmem_base, a_desc, b_desc, idesc, 0u);
+      else if constexpr (kCtas == 2) ptx::umma_f16_ss_pair(tmem_base, a_desc, b_desc, idesc, 0u);
+      else ptx::umma_f16_ss(tmem_base, a_desc, b_desc, idesc, 0u);
+    }
+    if constexpr (kTrace && kCtas == 1 && !kTf32) {
+      // experiment: how long do 8 MMAs take on an otherwise idle SM, first batch vs later batches?
+      if (p.dbg & 64) {
+        Tracer<kTrace> tr(p, 1, 16);
+        const uint32_t wbar = tmem_slot + 8;
+        ptx::mbar_init(wbar, 1);
+        ptx::fence_mbar_init();
+        for (int b = 0; b < 4; ++b) {
+          tr.rec(b, kEvWarmIssued);
+          for (int i = 0; i < 8; ++i) ptx::umma_f16_ss(tmem_base, a_desc, b_desc, idesc, 0u);
+          ptx::umma_commit(wbar);
+          tr.rec(b, kEvWarmIssued);
+          ptx::mbar_wait(wbar, b & 1);
+          tr.rec(b, kEvWarmDone);
+        }
+      }
+    }
+  }
+
   // Everything above touched only kernel parameters and on-chip state, so under programmatic dependent launch it
   // overlaps the tail of the dispatch kernel.  The routing tables, xbuf and every output come after this wait.
   ptx::pdl_wait();
@@ -396,8 +437,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       uint32_t phase = 0;
       const uint32_t tx_bytes = (a_stage_bytes + b_stage_bytes) * kCtas;  // both CTAs' tiles land on the leader's barrier
       // arm a stage: the leader expects the bytes of both CTAs, the other CTA only announces that its loads are issued
-      auto arm = [&](int st) {
-        if (kCtas == 1 || leader) ptx::mbar_arrive_expect_tx(full_bar(st), tx_bytes);
+      auto arm = [&](int st, uint32_t bytes) {
+        if (kCtas == 1 || leader) ptx::mbar_arrive_expect_tx(full_bar(st), bytes);
         else ptx::mbar_arrive_cluster(full_bar(st) & ptx::kPeerBitMask);
       };
       // rows [row, ..) x k-blocks [kb * kps, (kb + 1) * kps) of a [K/64][rows][64] view
@@ -420,7 +461,12 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         const int b_row = gr.row0 + static_cast<int>(cta_rank) * b_rows;
         const int nkb = tl.phase == 1 ? kb1 : kb2;
         int pre = 0;
-        const bool dep_pending = tl.phase == 2 && ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags;
+        // timing experiments (B200MOE_DBG): 8 / 16 = no token-operand loads in the first / second GEMM (garbage results:
+        // how much of the time is the B operand's L2 -> SM traffic?), 32 = no wait for h (what does the hand-off cost?)
+        const bool skip_b = (tl.phase == 1 && (p.dbg & 8)) || (tl.phase == 2 && (p.dbg & 16));
+        const uint32_t st_bytes = skip_b ? a_stage_bytes * kCtas : tx_bytes;
+        const bool dep_pending =
+            tl.phase == 2 && !(p.dbg & 32) && ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags;
         if (tl.phase == 2 && !dep_pending) ptx::fence_proxy_async_all();  // h was written through the generic proxy
         if (dep_pending) {
           // The W2 tiles do not depend on h: fill the ring with them first, then wait until every phase-1 tile of this
@@ -431,7 +477,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           const int stage0 = stage;
           for (int kb = 0; kb < pre; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            arm(stage);
+            arm(stage, st_bytes);
             load(smem_a + stage * a_stage_bytes, tm_a, stage, kb, a_row, p.w_policy);
             if (++stage == stages) {
               stage = 0;
@@ -442,16 +488,17 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           ptx::fence_proxy_async_all();  // generic-proxy writes of h -> async-proxy (TMA) reads
           int s2 = stage0;
           for (int kb = 0; kb < pre; ++kb) {
-            load(smem_b + s2 * b_stage_bytes, tm_b, s2, kb, b_row, ptx::kEvictLast);
+            if (!skip_b) load(smem_b + s2 * b_stage_bytes, tm_b, s2, kb, b_row, ptx::kEvictLast);
             if (++s2 == stages) s2 = 0;
           }
         }
         tr.rec(t, kEvProdDepOk);
         for (int kb = pre; kb < nkb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          arm(stage);
+          if (t < tile0 + 2 * tile_step) tr.rec(kb, kEvProdSlotFree);
+          arm(stage, st_bytes);
           load(smem_a + stage * a_stage_bytes, tm_a, stage, kb, a_row, p.w_policy);
-          load(smem_b + stage * b_stage_bytes, tm_b, stage, kb, b_row, ptx::kEvictLast);
+          if (!skip_b) load(smem_b + stage * b_stage_bytes, tm_b, stage, kb, b_row, ptx::kEvictLast);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -484,6 +531,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           if (kb == 0) tr.rec(t, kEvMmaFirstData);
+          if (t < tile0 + 2 * tile_step) tr.rec(kb, kEvMmaStageData);
           for (int j = 0; j < kps; ++j) {
             const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a + stage * a_stage_bytes + j * a_blk_bytes);
             const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b + stage * b_stage_bytes + j * b_blk_bytes);
@@ -496,8 +544,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
                 ptx::umma_f16_ss_pair(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
               else
                 ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
+              if (kTrace && t == tile0 && kb == 0) tr.rec(j * 4 + k, kEvMmaInstr);
             }
           }
+          if (t < tile0 + 2 * tile_step) tr.rec(kb, kEvMmaStageIssued);
           if constexpr (kCtas == 2) {
             // the slot is free in BOTH CTAs once these MMAs have read it; both epilogues get the accumulator signal
             ptx::umma_commit_pair(empty_bar(stage), 0x3);
@@ -1050,6 +1100,11 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
     }();
     p.dbg = dbg;
     p.pdl_trigger = (pdl_trigger() & kPdlFfn) ? 1 : 0;
+    static const int warm = [] {
+      const char* v = std::getenv("B200MOE_WARM");
+      return (v && *v) ? std::atoi(v) : 1;
+    }();
+    p.warm_mma = warm;
   }
   // about one token tile per expert: every weight tile is read exactly once, so it can leave L2 right after
   p.w_policy = (static_cast<long long>(a.n_rows) <= static_cast<long long>(a.E) * a.bn) ? ptx::kEvictFirst

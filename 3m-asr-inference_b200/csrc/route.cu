@@ -25,6 +25,7 @@
 //     into the router algebraically, see ln_stats_in_ring below.
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <random>
 
 #include <math_constants.h>
@@ -181,6 +182,7 @@ struct RouteParams {
   const float* ln_beta;
   const float* ln_c;   // c1[32], c0[32] behind the pre-scaled packed router (b200moe_pack_router_ln)
   float ln_eps;
+  int warm_mma;
   uint4* trace;  // debug timeline: 16 records per CTA {event, clock64 lo, hi, -}; slots 14 / 15 hold %globaltimer
 };
 
@@ -250,7 +252,9 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   int* s_dst = s_scratch + 33;                                 // [32]  destination row of each token of the chunk
   int* s_exp = s_dst + 32;                                     // [32]
   int* s_part = s_exp + 32;                                    // [8][2][32]
-  int* s_lastp = s_part + 512;                                 // [1]
+  int* s_part2 = s_part + 512;                                 // [8][32]  prefix of this CTA's second tile
+  int* s_before2 = s_part2 + 256;                              // [32]
+  int* s_lastp = s_before2 + 32;                               // [1]
   // kLn only (the host sizes the allocation accordingly)
   float* s_hx = reinterpret_cast<float*>(s_lastp + 6);         // [32][33]  x-part accumulator, hi rows (16 B aligned)
   float* s_lx = s_hx + 32 * 33;                                // [32][33]  ... lo rows
@@ -300,6 +304,13 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) rtrace(p, 1);
+  if (warp == 1 && lane == 0 && p.warm_mma) {
+    // the first tcgen05.mma of a kernel is ~2 us slower to issue than any later one (see ffn.cu): one throw-away
+    // instruction over whatever the ring holds, into the first accumulator stage (overwritten by the first real MMA),
+    // pays that while the tile is still on its way
+    ptx::umma_f16_ss(tmem_base, ptx::make_kmajor_sw128_desc(smem_base), ptx::make_kmajor_sw128_desc(smem_base + kRSlotA),
+                     ptx::make_idesc(1u, 128, kTok), 0u);
+  }
 
   // ================================================ phase 1: gate ================================================
   if (warp == 0) {
@@ -534,7 +545,10 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const unsigned long long tag = p.tag;
     const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * kRouteTimeoutMs;
     bool gave_up = false;
-    int total = 0, before = 0;
+    // `before2`: the same for this CTA's second tile (a CTA has at most two: route_supported), so that the second chunk
+    // needs no further pass over the histograms (148 dependent-latency loads per expert when it had one)
+    const int c_second = c_first + static_cast<int>(gridDim.x);
+    int total = 0, before = 0, before2 = 0;
     if (e < E)
       for (int r0 = part; r0 < n_tiles; r0 += 8 * 8) {
         // eight rows per batch: the loads are independent and all in flight together (one L2 round trip per batch
@@ -560,23 +574,27 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const int v = static_cast<int>(w[i] & 0xffull);
           total += v;
           if (r < c_first) before += v;
+          if (r < c_second) before2 += v;
         }
       }
     if (gave_up) atomicExch(&g_route_status, kStatusRouteTimeout);
     s_part[part * 32 + e] = total;
     s_part[256 + part * 32 + e] = before;
+    s_part2[part * 32 + e] = before2;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    int tot = 0, bef = 0;
+    int tot = 0, bef = 0, bef2 = 0;
 #pragma unroll
     for (int pt = 0; pt < 8; ++pt) {
       tot += s_part[pt * 32 + threadIdx.x];
       bef += s_part[256 + pt * 32 + threadIdx.x];
+      bef2 += s_part2[pt * 32 + threadIdx.x];
     }
     tot = static_cast<int>(threadIdx.x) < E ? tot : 0;
     s_total[threadIdx.x] = tot;
     s_before[threadIdx.x] = bef;
+    s_before2[threadIdx.x] = bef2;
     // exclusive scan over the experts within the warp
     int incl = tot;
 #pragma unroll
@@ -596,18 +614,8 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 
   for (int c = blockIdx.x; c < n_tiles; c += gridDim.x) {
     if (c != static_cast<int>(blockIdx.x)) {
-      // later chunks of this CTA (more tiles than SMs): add the rows in between
-      if (threadIdx.x < 32) {
-        int add = 0;
-        if (static_cast<int>(threadIdx.x) < E)
-          for (int r = c - gridDim.x; r < c; ++r) {
-            const unsigned long long w = p.hist64[static_cast<size_t>(r) * E + threadIdx.x];
-            // (a word that never arrived counted as 0 in the prefix sums above: keep the two consistent)
-            if ((w & ~0xffull) == p.tag && (w & 0xffull) <= static_cast<unsigned long long>(kTok))
-              add += static_cast<int>(w & 0xffull);
-          }
-        s_before[threadIdx.x] += add;
-      }
+      // second chunk of this CTA (more tiles than SMs): its prefix was accumulated in the same pass
+      if (threadIdx.x < 32) s_before[threadIdx.x] = s_before2[threadIdx.x];
       __syncthreads();
     }
     if (warp == 0) {
@@ -657,11 +665,18 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           reinterpret_cast<uint4*>(drow)[j * 8 + ch] = *reinterpret_cast<const uint4*>(sx + j * kRBBlk);
       } else if (tok < p.S && p.drop_out != nullptr) {
         // dropped token (padding): output row = residual row (or zero); the fused FFN epilogue never touches it
+        // (16-byte accesses, every load of the row issued before its stores: the compiler cannot prove that the two
+        // buffers do not alias, and one dependent L2 round trip per element made a padded batch 4x slower)
         const size_t row = static_cast<size_t>(tok) * p.D;
-        for (int k = ch * 8; k < p.D; k += 64)
+        uint4* orow = reinterpret_cast<uint4*>(p.drop_out + row);
+        const uint4* rrow = reinterpret_cast<const uint4*>(p.drop_residual + row);
+        uint4 v[kHalfKb];
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            p.drop_out[row + k + u] = p.drop_residual ? p.drop_residual[row + k + u] : __float2bfloat16_rn(0.0f);
+        for (int j = 0; j < kHalfKb; ++j)
+          v[j] = (p.drop_residual != nullptr && j < kb_x) ? __ldg(rrow + j * 8 + ch) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < kHalfKb; ++j)
+          if (j < kb_x) orow[j * 8 + ch] = v[j];
       }
     } else
     // row copies: warp w moves rows w, w + 8, w + 16, w + 24 of the chunk, all four in flight (2 x 16 B per lane each)
@@ -732,8 +747,16 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const int tok = c * kTok + warp + r * 8;
           if (tok < p.S && d[r] < 0) {
             const size_t row = static_cast<size_t>(tok) * p.D;
-            for (int k = lane; k < p.D; k += 32)
-              p.drop_out[row + k] = p.drop_residual ? p.drop_residual[row + k] : __float2bfloat16_rn(0.0f);
+            uint4* orow = reinterpret_cast<uint4*>(p.drop_out + row);
+            const uint4* rrow = reinterpret_cast<const uint4*>(p.drop_residual + row);
+            uint4 v[kRouteLnVec];   // D <= 512: at most two 16-byte vectors per lane
+#pragma unroll
+            for (int k = 0; k < kRouteLnVec; ++k)
+              v[k] = (p.drop_residual != nullptr && k * 32 + lane < p.D / 8) ? __ldg(rrow + k * 32 + lane)
+                                                                            : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int k = 0; k < kRouteLnVec; ++k)
+              if (k * 32 + lane < p.D / 8) orow[k * 32 + lane] = v[k];
           }
         }
       }
@@ -933,10 +956,16 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   p.ln_beta = ln_beta;
   p.ln_c = ln_c;
   p.ln_eps = ln_eps;
+  static const int warm = [] {
+    const char* v = std::getenv("B200MOE_WARM");
+    return (v && *v) ? std::atoi(v) : 1;
+  }();
+  p.warm_mma = warm;
   p.trace = static_cast<uint4*>(g_route_trace);
   EpPeers epv{};
   if (ep) epv = *ep;
-  const size_t smem_plain = kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 32 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 64);
+  const size_t smem_plain =
+      kRSlots * kRSlot + 8 * (2 * kRSlots + 4) + 32 + 4 * (32 + 2 * 32 * 33 + 7 * 33 + 512 + 256 + 32 + 64);
   // kLn: x-part accumulator copies, statistics, c1 / c0, gamma / beta
   const size_t smem_ln = smem_plain + 4 * (2 * 32 * 33 + 4 * 32 + 2 * 32 + 2 * kHalfKb * kRK);
   const size_t smem = p.ln_gamma != nullptr ? smem_ln : smem_plain;

@@ -71,6 +71,7 @@ def parse():
     ap.add_argument("--sustain", type=float, default=0.0,
                     help="additionally replay the step back to back for this many seconds (own clock record)")
     ap.add_argument("--sweep-max", type=int, default=SWEEP_TOKENS[-1], help="largest sweep point (global tokens)")
+    ap.add_argument("--sweep-points", default="", help="run only these sweep points: 'tokens:k[:zipf],...'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -578,6 +579,11 @@ def run_sweep(b: Bench):
     wl = WORKLOADS["sweep"]
     points = [(s, k, False) for s in SWEEP_TOKENS if s <= args.sweep_max for k in (1, 2)]
     points.append((min(65536, args.sweep_max), 1, True))
+    if args.sweep_points:
+        points = []
+        for item in args.sweep_points.split(","):
+            f = item.split(":")
+            points.append((int(f[0]), int(f[1]) if len(f) > 1 else 1, len(f) > 2 and f[2] == "zipf"))
     for s_glob, k, zipf in points:
         s_loc = s_glob // b.world
         br = None

@@ -103,6 +103,25 @@ def test_cfg4_shape_ragged_batch(ops, oracle, synth):
     assert float(res2.out.float().cpu()[pad].abs().max()) == 0.0
 
 
+def test_layer_next_to_a_foreign_kernel(ops, oracle, synth):
+    """The fused gate + dispatch kernel waits for the other CTAs of its own grid; with foreign kernels holding SMs on
+    another stream its CTAs become resident late.  The layer must still be right (no trap, status word clear)."""
+    E, D, H, Demb, S = 32, 512, 1024, 512, 3200
+    w = synth.make_weights(20260501, E, D, H, Demb)
+    x, embed = synth.make_activations(20260502, S, D, Demb, w)
+    ref = oracle.moe_forward(x, embed, w.Wr, None, w.W1, w.b1, w.W2, w.b2, residual=x, ff_scale=0.5)
+    side = torch.cuda.Stream()
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    with torch.cuda.stream(side):
+        for _ in range(40):          # ~1.3 ms each: every SM busy with foreign CTAs for the whole test
+            a @ a
+    outs = [run_layer(ops, w, x, embed, ff_scale=0.5) for _ in range(8)]
+    torch.cuda.synchronize()
+    assert ops.status(clear=True) == 0
+    for res in outs:
+        check_against_oracle(oracle, res, ref)
+
+
 def test_golden_naive_top2(ops, oracle):
     g = load_golden("case_naive_top2.npz")
 

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 PKG = "3m-asr-inference_b200"
 EV = ["kernel_start", "prod_tile_start", "prod_dep_ok", "prod_issued", "mma_acc_free", "mma_first_data", "mma_issued",
       "epi_acc_ready", "epi_acc_released", "epi_stored", "epi_published", "kernel_end", "epi_chunk_ld", "epi_chunk_staged",
-      "epi_chunk_done", "clock"]
+      "epi_chunk_done", "clock", "cycles", "prod_slot_free(kb)", "mma_stage_data(kb)", "mma_stage_issued(kb)", "mma_instr(i)", "warm_issued(b)", "warm_done(b)"]
 
 
 def analyze(rec, cap, n_cta, S, n_print):
@@ -34,7 +34,7 @@ def analyze(rec, cap, n_cta, S, n_print):
             continue
         rate = (k[-1] - k[0]) / (g[-1] - g[0])                 # cycles per ns
         rates.append(rate * 1e3)
-        m = (raw[c] > 0) & (evc[c] < 15)
+        m = (raw[c] > 0) & ((evc[c] < 15) | (evc[c] > 16))
         t[c][m] = 1.0 + float(g[0] - gbase) + (raw[c][m] - k[0]).astype(np.float64) / rate
     valid = t > 0
     t0 = t[valid].min()
@@ -42,7 +42,7 @@ def analyze(rec, cap, n_cta, S, n_print):
     if rates:
         print(f"  SM clock during the kernel: median {np.median(rates):.0f} MHz (min {min(rates):.0f}, max {max(rates):.0f})")
     # per-event statistics relative to kernel start
-    for ev in range(15):
+    for ev in list(range(15)) + [17, 18, 19, 20, 21, 22]:
         m = valid & (rec[..., 1] == ev)
         if m.any():
             tt = (t[m] - t0) / 1e3
