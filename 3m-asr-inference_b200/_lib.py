@@ -73,6 +73,9 @@ SIGNATURES = {
     "b200moe_ep_workspace_bytes": (_sz, [_vp, _i]),
     "b200moe_ep_forward": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _vp]),
     "b200moe_ep_forward_stages": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _i, _vp]),
+    "b200moe_ep_forward_deferred": (_i, [_vp, C.POINTER(LayerArgs), _vp, _sz, _vp]),
+    "b200moe_ep_wait": (_i, [_vp, _vp]),
+    "b200moe_ep_out_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz)]),
     "b200moe_ep_status": (_i, [_vp, C.POINTER(_i)]),
     "b200moe_router_ln_pack_bytes": (_sz, [_i]),
     "b200moe_pack_router_ln": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

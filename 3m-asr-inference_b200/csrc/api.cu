@@ -522,6 +522,11 @@ static int forward_impl(const b200moe_layer_args* a, void* ws, size_t ws_bytes, 
 
 struct b200moe_ep_ctx {
   EpPeers peers;
+  // folded path: the owners are still writing this rank's `out` rows of the last layer call; whatever touches `out`
+  // next has to be ordered behind launch_ep_wait_done (the next b200moe_ep_forward* does it itself)
+  bool pending = false;
+  void* pending_out = nullptr;
+  int pending_S = 0;
 };
 
 size_t b200moe_ep_buffer_bytes(int world, int E_local, int D, int cap) {
@@ -615,23 +620,59 @@ int b200moe_ep_status(const b200moe_ep_ctx* c, int* host_status) {
   return B200MOE_OK;
 }
 
-int b200moe_ep_forward(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes,
-                       cudaStream_t stream) {
-  return b200moe_ep_forward_stages(c, a, ws, ws_bytes, 7, stream);
+namespace {
+constexpr int kEpAllStages = 15;
+constexpr int kEpFlagDeferWait = 1;
+
+int ep_flush_pending(b200moe_ep_ctx* c, cudaStream_t stream) {
+  if (!c->pending) return B200MOE_OK;
+  cudaError_t e = launch_ep_wait_done(c->peers, c->pending_out, c->pending_S, c->peers.D, stream);
+  c->pending = false;
+  c->pending_out = nullptr;
+  if (e != cudaSuccess) return cuda_fail(e, "ep_wait");
+  return B200MOE_OK;
 }
+}  // namespace
 
 static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes, int stages,
-                           cudaStream_t stream, const LnFuse* ln_in, const LnFuse* ln_out);
+                           int flags, cudaStream_t stream, const LnFuse* ln_in, const LnFuse* ln_out);
+
+int b200moe_ep_forward(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes,
+                       cudaStream_t stream) {
+  return ep_forward_impl(c, a, ws, ws_bytes, kEpAllStages, 0, stream, nullptr, nullptr);
+}
+
+int b200moe_ep_forward_deferred(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes,
+                                cudaStream_t stream) {
+  return ep_forward_impl(c, a, ws, ws_bytes, kEpAllStages, kEpFlagDeferWait, stream, nullptr, nullptr);
+}
+
+int b200moe_ep_wait(b200moe_ep_ctx* c, cudaStream_t stream) {
+  if (!c) return fail(B200MOE_ERR_ARG, "ep_wait: null context");
+  return ep_flush_pending(c, stream);
+}
+
+int b200moe_ep_out_buffer(const b200moe_ep_ctx* c, int slot, void** dev_ptr, size_t* bytes) {
+  if (!c || !dev_ptr || slot < 0 || slot > 1) return fail(B200MOE_ERR_ARG, "ep_out_buffer: bad argument");
+  const EpPeers& p = c->peers;
+  const size_t one = sizeof(bf16) * static_cast<size_t>(p.cap) * p.D;
+  *dev_ptr = p.base[p.rank] + p.lay.out_heap + slot * one;
+  if (bytes) *bytes = one;
+  return B200MOE_OK;
+}
 
 int b200moe_ep_forward_stages(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes, int stages,
                               cudaStream_t stream) {
-  return ep_forward_impl(c, a, ws, ws_bytes, stages, stream, nullptr, nullptr);
+  return ep_forward_impl(c, a, ws, ws_bytes, stages, 0, stream, nullptr, nullptr);
 }
 
+// stages (bit mask): 1 gate + counts to every rank, 8 scatter (wait for the counts, push rows), 2 wait for the rows +
+// expert FFN + push back, 4 wait for the results (+ combine); 15 = the whole layer, with the fused gate + dispatch
+// kernel where it applies.
 // ln_in: norm_ff fused into the route kernel (the caller has checked that the route kernel is taken);
 // ln_out: norm_final fused into the combine kernel
 static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void* ws, size_t ws_bytes, int stages,
-                           cudaStream_t stream, const LnFuse* ln_in, const LnFuse* ln_out) {
+                           int flags, cudaStream_t stream, const LnFuse* ln_in, const LnFuse* ln_out) {
   if (!c || !a) return fail(B200MOE_ERR_ARG, "ep_forward: null argument");
   const EpPeers& ep = c->peers;
   const int S = a->B * a->T;
@@ -646,6 +687,7 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
   if (a->top_k < 1 || a->top_k > 8 || a->top_k > a->E) return fail(B200MOE_ERR_ARG, "ep_forward: bad top_k %d", a->top_k);
   if (a->gate_mode == B200MOE_GATE_3M && a->top_k != 1) return fail(B200MOE_ERR_ARG, "ep_forward: the 3M router is top-1");
   if (a->act_type < 0 || a->act_type > 2) return fail(B200MOE_ERR_ARG, "ep_forward: bad act_type %d", a->act_type);
+  if (stages < 1 || stages > kEpAllStages) return fail(B200MOE_ERR_ARG, "ep_forward: bad stage mask %d", stages);
   const int Sk = S * a->top_k;
   if (Sk > ep.cap) return fail(B200MOE_ERR_ARG, "ep_forward: %d entries exceed the context capacity %d", Sk, ep.cap);
   if ((S > 0 && (!a->x || !a->out)) || (!a->Wr && !a->Wr_packed) || !a->W1 || !a->W2 || !ws)
@@ -660,84 +702,127 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
   int* idx = a->idx_out ? a->idx_out : w.idx;
   float* score = a->score_out ? a->score_out : w.score;
 
+  // Folded combine: the owners' second-GEMM epilogue writes  residual + ff_scale * score * y  straight into this rank's
+  // `out` rows.  Needs: top-1; the residual (if any) to be the very rows that were dispatched (the owner holds them); no
+  // norm_final (the owner produces a row in D / 128 pieces); and `out` inside the symmetric buffer, at the same offset
+  // on every rank, where the peers can reach it (b200moe_ep_out_buffer).  Every rank must decide the same way: the
+  // decision travels with the counts and a mismatch raises the status word.
+  const uint8_t* heap0 = ep.base[ep.rank] + ep.lay.out_heap;
+  const size_t out_bytes = sizeof(bf16) * static_cast<size_t>(S) * a->D;
+  const uint8_t* outp = static_cast<const uint8_t*>(a->out);
+  // (decided from the pointers alone, also for a rank without tokens: it still serves the others as an owner)
+  const bool out_in_heap =
+      outp != nullptr && outp >= heap0 && outp + out_bytes <= heap0 + 2 * sizeof(bf16) * static_cast<size_t>(ep.cap) * a->D;
+  static const int fold_env = env_int("B200MOE_EP_FOLD", 1);
+  const bool fold = fold_env != 0 && a->top_k == 1 && ln_in == nullptr && ln_out == nullptr && out_in_heap &&
+                    (a->residual == nullptr || a->residual == a->x);
+  const int mode = (fold ? kEpModeFold : 0) | ((fold && a->residual) ? kEpModeResidual : 0);
+
   cudaError_t e = cudaSuccess;
+  // the previous call's results may still be on their way into the buffer this call reads (or overwrites)
+  if (stages & 1) {
+    int rc = ep_flush_pending(c, stream);
+    if (rc != B200MOE_OK) return rc;
+  }
   const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
-  const int bn = choose_bn(Sk, E_total);
-  const int gmax = max_groups(rows_cap, E_total, bn);
-  // all stages in one call: the dispatch kernel's last CTA also waits for the peers and builds the group table
-  const bool fold_wait = (stages & 3) == 3;
-  const bool route = tc_gate && route_supported(S, a->D, Demb, a->E, a->top_k, a->dtype);
-  if (route && (stages & 1)) {
+  // merged layout: every local expert's rows are contiguous whatever rank they came from, about Sk / E_local each
+  const int bn = choose_bn(Sk, ep.E_local);
+  const int gmax = max_groups(rows_cap, ep.E_local, bn);
+  const bool one_call = (stages & 11) == 11;   // gate, scatter and the expert kernel in this call
+  const bool route = one_call && tc_gate && route_supported(S, a->D, Demb, a->E, a->top_k, a->dtype);
+  void* drop_out = fold ? a->out : nullptr;     // padded / dropped tokens: output row = residual row, written locally
+  if (route) {
     StageScope t(0, stream);
     e = launch_route(a->x, a->embed, ln_in ? ln_in->packed : a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb,
-                     a->E, a->gate_mode, 0, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out, w.xbuf, nullptr,
-                     nullptr, stream, &ep, fold_wait, ln_in ? ln_in->gamma : nullptr, ln_in ? ln_in->beta : nullptr,
-                     ln_in ? ln_in->eps : 0.0f, ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr);
+                     a->E, a->gate_mode, a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out,
+                     w.xbuf, drop_out, a->residual, stream, &ep, true, ln_in ? ln_in->gamma : nullptr,
+                     ln_in ? ln_in->beta : nullptr, ln_in ? ln_in->eps : 0.0f,
+                     ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr, mode);
     if (e != cudaSuccess) return cuda_fail(e, "ep_forward/route");
+  } else {
+    if (S > 0 && (stages & 1)) {
+      StageScope t(0, stream);
+      if (tc_gate)
+        e = launch_gate_tc(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
+                           a->gate_mode, idx, score, w.hist32, nullptr, 0, nullptr, 0, stream);
+      else
+        e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k, a->gate_mode,
+                        a->dtype, idx, score, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "ep_forward/gate");
+    }
+    const float* dscore = a->keep_expert_output ? nullptr : score;
+    const int* hist = tc_gate && S > 0 ? w.hist32 : nullptr;
+    if ((stages & 9) == 9) {          // counts + scatter in one kernel
+      StageScope t(1, stream);
+      e = launch_dispatch(a->x, idx, dscore, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
+                          a->mapping_out, w.xbuf, drop_out, a->residual, hist, stream, &ep, one_call, false, mode, 0);
+    } else if (stages & 1) {          // staged: the counts alone ...
+      e = launch_dispatch(a->x, idx, dscore, S, a->D, E_total, a->top_k, a->dtype, bn, w, nullptr, nullptr, nullptr,
+                          w.xbuf, nullptr, nullptr, hist, stream, &ep, false, false, mode, 1);
+    } else if (stages & 8) {          // ... then the scatter, once every rank's counts are on their way
+      e = launch_dispatch(a->x, idx, dscore, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
+                          a->mapping_out, w.xbuf, drop_out, a->residual, hist, stream, &ep, false, false, mode, 2);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "ep_forward/dispatch");
   }
-  if (S > 0 && (stages & 1) && !route) {
-    StageScope t(0, stream);
-    if (tc_gate)
-      e = launch_gate_tc(a->x, a->embed, a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k,
-                         a->gate_mode, idx, score, w.hist32, nullptr, 0, nullptr, 0, stream);
-    else
-      e = launch_gate(a->x, a->embed, a->Wr, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E, a->top_k, a->gate_mode,
-                      a->dtype, idx, score, stream);
-  }
-  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/gate");
-
-  if ((stages & 1) && !route) {
+  if ((stages & 2) && !one_call) {
     StageScope t(1, stream);
-    e = launch_dispatch(a->x, idx, nullptr, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
-                        a->mapping_out, w.xbuf, nullptr, nullptr, tc_gate && S > 0 ? w.hist32 : nullptr, stream, &ep,
-                        fold_wait);
+    e = launch_ep_wait_rows(ep, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ep_forward/wait_rows");
   }
-  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/dispatch");
-  if ((stages & 2) && !fold_wait) {
-    StageScope t(1, stream);
-    e = launch_ep_wait_build(ep, bn, w.groups, w.n_groups, w.h_ready, gmax, stream);
-  }
-  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/wait_build");
 
-  FfnLaunch f{};
-  f.xbuf = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.recv_x);
-  f.hbuf = static_cast<bf16*>(w.hbuf);
-  f.W1 = static_cast<const bf16*>(a->W1);
-  f.W2 = static_cast<const bf16*>(a->W2);
-  f.b1 = a->b1;
-  f.b2 = a->b2;
-  f.groups = w.groups;
-  f.n_groups = w.n_groups;
-  f.h_ready = w.h_ready;
-  f.n_rows = rows_cap;
-  f.E = ep.E_local;
-  f.D = a->D;
-  f.H = a->H;
-  f.bn = bn;
-  f.act = a->act_type;
-  f.gmax = gmax;
-  f.fused = 0;
-  f.out_dtype = B200MOE_BF16;
-  f.out = ep.base[ep.rank] + ep.lay.ret_y;
-  f.top_k = 1;
-  f.ff_scale = 1.0f;
-  f.ep = &ep;
-  if (route) {
-    f.clear_ptr = w.hist32;
-    f.clear_ints = 2 * ((S + 31) / 32) * a->E;  // 64-bit words
-  }
   if (stages & 2) {
+    FfnLaunch f{};
+    f.xbuf = reinterpret_cast<const bf16*>(ep.base[ep.rank] + ep.lay.recv_x);
+    f.hbuf = static_cast<bf16*>(w.hbuf);
+    f.W1 = static_cast<const bf16*>(a->W1);
+    f.W2 = static_cast<const bf16*>(a->W2);
+    f.b1 = a->b1;
+    f.b2 = a->b2;
+    f.groups = w.groups;
+    f.n_groups = w.n_groups;
+    f.h_ready = w.h_ready;
+    f.n_rows = rows_cap;
+    f.E = ep.E_local;
+    f.D = a->D;
+    f.H = a->H;
+    f.bn = bn;
+    f.act = a->act_type;
+    f.gmax = gmax;
+    f.fused = 0;
+    f.out_dtype = B200MOE_BF16;
+    f.out = ep.base[ep.rank] + ep.lay.ret_y;
+    f.top_k = 1;
+    f.ff_scale = a->ff_scale;
+    f.ep = &ep;
+    f.ep_fold = fold ? 1 : 0;
+    f.ep_out_off = fold ? static_cast<size_t>(outp - ep.base[ep.rank]) : 0;
+    f.residual = fold ? ep.base[ep.rank] + ep.lay.recv_x : nullptr;   // (per row: only where the source had one)
+    if (route) {
+      f.clear_ptr = w.hist32;
+      f.clear_ints = 2 * ((S + 31) / 32) * a->E;
+    }
     StageScope t(2, stream);
     e = launch_ffn(f, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ep_forward/expert_ffn");
   }
-  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/expert_ffn");
   if (stages & 4) {
     StageScope t(3, stream);
-    e = launch_ep_combine(ep, w.mapping, a->keep_expert_output ? nullptr : score, a->residual, a->ff_scale, S, a->D,
-                          a->top_k, a->out, stream, ln_out ? ln_out->gamma : nullptr, ln_out ? ln_out->beta : nullptr,
-                          ln_out ? ln_out->eps : 0.0f);
+    if (fold) {
+      c->pending = true;
+      c->pending_out = a->out;
+      c->pending_S = S;
+      if (!(flags & kEpFlagDeferWait)) {
+        int rc = ep_flush_pending(c, stream);
+        if (rc != B200MOE_OK) return rc;
+      }
+    } else {
+      e = launch_ep_combine(ep, w.mapping, a->keep_expert_output ? nullptr : score, a->residual, a->ff_scale, S, a->D,
+                            a->top_k, a->out, stream, ln_out ? ln_out->gamma : nullptr, ln_out ? ln_out->beta : nullptr,
+                            ln_out ? ln_out->eps : 0.0f);
+      if (e != cudaSuccess) return cuda_fail(e, "ep_forward/combine");
+    }
   }
-  if (e != cudaSuccess) return cuda_fail(e, "ep_forward/combine");
   return B200MOE_OK;
 }
 
@@ -1039,7 +1124,7 @@ int b200moe_ep_block_forward(b200moe_ep_ctx* c, const b200moe_block_args* b, voi
     if (e != cudaSuccess) return cuda_fail(e, "ep_block_forward/norm_ff");
   }
   // norm_final rides in the combine kernel (it runs even for a rank without tokens: the flags must be consumed)
-  return ep_forward_impl(c, &plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, 7, stream,
+  return ep_forward_impl(c, &plan.layer, ws, ws_bytes < layer_ws ? ws_bytes : layer_ws, kEpAllStages, 0, stream,
                          fuse_in ? &lin : nullptr, b->norm_final_gamma ? &lout : nullptr);
 }
 

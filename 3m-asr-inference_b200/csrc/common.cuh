@@ -26,8 +26,8 @@ struct GroupRec {
   int expert;  // (local) expert whose weights the group uses
   int row0;    // first row of the group in xbuf / hbuf
   int nrows;   // 1 .. BN
-  int src;     // expert parallelism: rank the rows came from (selects the output buffer); else 0
-  int orow0;   // expert parallelism: first output row in the source rank's return buffer; else == row0
+  int src;     // unused (0)
+  int orow0;   // first output row of the group in ybuf (== row0)
   int pad[3];
 };
 
@@ -35,16 +35,47 @@ struct GroupRec {
 constexpr int kMaxEpWorld = 8;
 
 // Byte offsets inside the symmetric buffer every rank allocates (identical on all ranks).
+//
+// Protocol of one layer call `seq` on rank r (W ranks, E_local experts per rank, E = W * E_local):
+//   1. gate -> r's per-expert counts for ALL E experts.  One CTA stores them into cnt_all[seq & 1][r][:] of EVERY rank and
+//      raises cnt_flag[r] = seq there (st.release.sys).
+//   2. every CTA of the dispatch / route kernel waits for all W count flags (local memory) and derives, for each expert,
+//      the row of the OWNER's receive buffer where r's first row for that expert belongs: the owner's rows are laid out
+//      expert-major, source-rank-major inside an expert, stable inside a source -- i.e. every local expert's rows are
+//      CONTIGUOUS whatever rank they came from, so the expert kernel runs full token tiles per expert instead of one
+//      tile per (expert, source) (functions.py:37-50's count exchange, without the host).
+//   3. rows -> recv_x[row] and 8 bytes of routing data -> meta[row] on the owner; every CTA fence.acq_rel.sys; the last
+//      CTA raises disp_flag[r] = seq on every rank ("r's rows have landed").
+//   4. owner: expert FFN over recv_x.  The second GEMM's epilogue sends each row where meta says: either (fold) the
+//      finished layer output  residual + ff_scale * score * y  straight into the source rank's `out` row, or the bare y
+//      row into the source's ret_y for ep_combine.  Last CTA raises ret_flag[owner] = seq on every rank.
+//   5. source: waits for all W ret_flags (ep_wait_done_kernel in front of whatever consumes `out`, or ep_combine).
+// Flags carry the layer sequence number and are never reset.  One receive buffer suffices: r pushes layer L+1 only after
+// it has seen every owner's ret_flag of layer L, which an owner raises after its last read of recv_x / meta / cnt_all.
 struct EpLayout {
-  size_t ctrl;       // int32[16]: [0] seq (layer calls so far), [1] dispatch CTAs done, [2] FFN CTAs done, [3] error
+  size_t ctrl;       // int32[16]: [0] seq (layer calls so far), [1] dispatch CTAs done, [2] FFN CTAs done, [3] error,
+                     //            [4] mode bits of the current call (bit 0 fold, bit 1 residual)
+  size_t cnt_flag;   // int32[kMaxEpWorld]: cnt_flag[s] = seq of the last call whose counts from rank s have landed
   size_t disp_flag;  // int32[kMaxEpWorld]: disp_flag[s] = seq of the last dispatch whose rows from rank s have landed
-  size_t ret_flag;   // int32[kMaxEpWorld]: ret_flag[r] = seq of the last layer whose results from expert rank r landed
-  size_t recv_cnt;   // int32[kMaxEpWorld][E_local + 1]: rows per local expert from rank s; [E_local] = first row of
-                     //   this rank's segment in rank s's expert-ordered entries
-  size_t recv_x;     // bf16 [world][cap][D]: rows from rank s, ordered by local expert (stable inside an expert)
-  size_t ret_y;      // bf16 [cap][D]: expert outputs for this rank's own entries, in its expert order
+  size_t ret_flag;   // int32[kMaxEpWorld]: ret_flag[o] = seq of the last layer whose results from owner rank o landed
+  size_t cnt_all;    // int32[2][kMaxEpWorld][E + 1]: [seq & 1][s][e] rows rank s routes to global expert e; [E] = mode bits
+  size_t meta;       // int2 [world * cap]: per received row {residual? << 31 | source rank << 27 | index at the source,
+                     //   gate score bits}; index = the token (fold) or the source's expert-order row (ret_y + ep_combine)
+  size_t recv_x;     // bf16 [world * cap][D]: received rows, expert-major / source-major / stable
+  size_t ret_y;      // bf16 [cap][D]: expert outputs for this rank's own entries, in its expert order (un-folded path)
+  size_t out_heap;   // bf16 [2][cap][D]: two layer-output buffers inside the symmetric heap (the folded path writes the
+                     //   source rank's output rows remotely, so `out` has to live where the peers can reach it)
   size_t bytes;
 };
+
+constexpr int kEpModeFold = 1, kEpModeResidual = 2;
+constexpr int kEpMetaRankShift = 27;
+constexpr int kEpMetaIndexMask = (1 << kEpMetaRankShift) - 1;
+constexpr int kEpMetaRankMask = 0xF;
+__host__ __device__ inline int ep_meta_word(int rank, int index, bool residual) {
+  return static_cast<int>((residual ? 0x80000000u : 0u) | (static_cast<unsigned>(rank) << kEpMetaRankShift) |
+                          static_cast<unsigned>(index));
+}
 
 inline EpLayout ep_layout(int world, int E_local, int D, int cap) {
   EpLayout l;
@@ -54,12 +85,16 @@ inline EpLayout ep_layout(int world, int E_local, int D, int cap) {
     off = align_up(off + b, 1024);
     return o;
   };
+  const size_t E = static_cast<size_t>(world) * E_local;
   l.ctrl = take(sizeof(int) * 16);
+  l.cnt_flag = take(sizeof(int) * kMaxEpWorld);
   l.disp_flag = take(sizeof(int) * kMaxEpWorld);
   l.ret_flag = take(sizeof(int) * kMaxEpWorld);
-  l.recv_cnt = take(sizeof(int) * kMaxEpWorld * (E_local + 1));
+  l.cnt_all = take(sizeof(int) * 2 * kMaxEpWorld * (E + 1));
+  l.meta = take(sizeof(int) * 2 * static_cast<size_t>(world) * cap);
   l.recv_x = take(sizeof(bf16) * static_cast<size_t>(world) * cap * D);
   l.ret_y = take(sizeof(bf16) * static_cast<size_t>(cap) * D);
+  l.out_heap = take(sizeof(bf16) * 2 * static_cast<size_t>(cap) * D);
   l.bytes = off;
   return l;
 }
@@ -153,7 +188,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
                             const int* hist32, cudaStream_t stream, const EpPeers* ep = nullptr,
-                            bool ep_fold_wait = false, bool xbuf_f32 = false);
+                            bool ep_fold_wait = false, bool xbuf_f32 = false, int ep_mode = 0, int ep_phase = 0);
 constexpr int kMaxHistRows = 512;  // above this many 32-token rows the scatter CTAs would re-read too much
 // Builds only the group table (+ zeroes the flags) from an existing offsets array.
 cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
@@ -170,7 +205,8 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream,
                          const EpPeers* ep = nullptr, bool ep_fold_wait = false, const float* ln_gamma = nullptr,
-                         const float* ln_beta = nullptr, float ln_eps = 0.0f, const float* ln_c = nullptr);
+                         const float* ln_beta = nullptr, float ln_eps = 0.0f, const float* ln_c = nullptr,
+                         int ep_mode = 0);
 // Router packed for the route kernel's fused norm_ff: like launch_pack_router, with the x rows (k >= R - D) scaled by
 // gamma, followed by c1[32] = gamma^T Wr_x and c0[32] = beta^T Wr_x (fp32).  router_ln_pack_bytes(R) bytes.
 size_t router_ln_pack_bytes(int R);
@@ -199,7 +235,9 @@ struct FfnLaunch {
   const float* row_score;  // null => 1
   float ff_scale;
   int top_k;
-  const EpPeers* ep;  // expert parallelism (un-fused only): rows of group g go to rank g.src's return buffer
+  const EpPeers* ep;  // expert parallelism: every row goes to the rank its routing data (EpLayout::meta) names
+  int ep_fold;        // 1: finished output rows (residual = the received row, x ff_scale x score) into the source's `out`
+  size_t ep_out_off;  //    at this byte offset of every rank's symmetric buffer; 0: bare y rows into the source's ret_y
   int* clear_ptr;     // optional: `clear_ints` ints zeroed at kernel start (the route kernel's tagged histogram)
   int clear_ints;
   int tf32;           // 1: xbuf, W1, W2 and hbuf hold fp32 (the pointers above are reinterpreted), TF32 tensor-core math
@@ -209,10 +247,12 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
 void set_ffn_trace(void* dev_buf, int records_per_cta);
 
 // ep.cu
-// Waits until every rank's rows of the current layer call have landed, then builds the FFN group table over the receive
-// buffer (expert-major, source rank inside an expert) and clears the h flags.
-cudaError_t launch_ep_wait_build(const EpPeers& ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax,
-                                 cudaStream_t stream);
+// Waits until every rank's rows of the current layer call have landed (staged drivers; the one-call path folds the wait
+// into the dispatch / route kernel).
+cudaError_t launch_ep_wait_rows(const EpPeers& ep, cudaStream_t stream);
+// Folded path: returns (on the stream) once every owner has written this rank's output rows of the current layer call;
+// poisons out [S, D] bf16 with NaNs when a peer failed to deliver.
+cudaError_t launch_ep_wait_done(const EpPeers& ep, void* out, int S, int D, cudaStream_t stream);
 // Waits until every expert rank has returned this rank's rows, then out = residual + ff_scale * sum_k score * ret_y[mapping].
 // ln_gamma / ln_beta non-null: LayerNorm over the D features of every output row on top (norm_final).
 cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float* score, const void* residual,

@@ -93,44 +93,11 @@ __device__ __forceinline__ uint4 load8_as_bf16<__half>(const __half* __restrict_
   return o;
 }
 
-// Group table: expert e contributes ceil(count[e] / bn) groups, in expert order. Runs in one CTA.
-__device__ void build_groups_block(const int* offsets_sm /*[E+1] in smem or global*/, int E, int bn,
-                                   GroupRec* groups, int* n_groups, int* h_ready, int gmax, int* scratch /*[E+1]*/) {
-  // scratch[e] = exclusive prefix of tiles per expert
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int e = 0; e < E; ++e) {
-      scratch[e] = acc;
-      const int c = offsets_sm[e + 1] - offsets_sm[e];
-      acc += (c + bn - 1) / bn;
-    }
-    scratch[E] = acc;
-    n_groups[0] = acc;
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const int c = offsets_sm[e + 1] - offsets_sm[e];
-    const int nt = (c + bn - 1) / bn;
-    const int g0 = scratch[e];
-    for (int j = 0; j < nt; ++j) {
-      GroupRec r;
-      r.expert = e;
-      r.row0 = offsets_sm[e] + j * bn;
-      r.nrows = min(bn, c - j * bn);
-      r.src = 0;
-      r.orow0 = r.row0;
-      r.pad[0] = r.pad[1] = r.pad[2] = 0;
-      groups[g0 + j] = r;
-    }
-  }
-  for (int g = threadIdx.x; g < gmax; g += blockDim.x) h_ready[g] = 0;
-}
-
-// kEp: expert parallelism.  Rows are pushed straight into the destination rank's receive buffer over peer-mapped
-// memory (NVLink): expert e lives on rank e / E_local, and this rank's rows for that rank land, ordered by local expert,
-// at recv_x[my rank][mapping - offsets[first expert of that rank]].  The last CTA to finish then writes the per-expert
-// counts into every peer and raises its arrival flag with a system-scope release (the reference does this with two
-// NCCL all-to-alls and a host round trip: trainer_3m_fix/fmoe/functions.py:37-50,74-80).
+// kEp: expert parallelism (protocol: common.cuh, EpLayout).  Expert e lives on rank e / E_local.  CTA 0 sends this rank's
+// per-expert counts to every rank, every CTA waits for all ranks' counts and pushes its rows over peer-mapped memory
+// (NVLink) to where they belong in the owner's receive buffer -- expert-major, source-major inside an expert -- together
+// with 8 bytes of routing data per row; the last CTA to finish raises the arrival flag with a system-scope release (the
+// reference does this with two NCCL all-to-alls and a host round trip: trainer_3m_fix/fmoe/functions.py:37-50,74-80).
 // kXf32: the expert-order buffer keeps fp32 rows (TF32 compute; fp32 activations only) instead of bf16.
 template <typename InT, bool kEp, bool kXf32>
 __global__ void __launch_bounds__(kDispatchThreads)
@@ -141,7 +108,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
                         float* __restrict__ row_score, bf16* __restrict__ xbuf, GroupRec* groups, int* n_groups,
                         int* h_ready, int* counts_out, int* offsets_out, int* mapping_out, InT* __restrict__ drop_out,
                         const InT* __restrict__ drop_residual, int early_trigger, const EpPeers ep,
-                        int ep_fold_wait) {
+                        int ep_fold_wait, int ep_mode, int ep_send) {
   constexpr int kWarps = kDispatchThreads / 32;
   constexpr int kRowsPerBatch = 4;            // rows a warp keeps in flight during the copy
   constexpr int kMaxParts = 8;
@@ -156,6 +123,8 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   int* s_wcnt = s_dst + kDispatchThreads;     // [kWarps][E] per-warp counts of the current segment
   int* s_part = s_wcnt + kWarps * E;          // [nparts][2][E] partial column sums (before / total)
   int* s_exp = s_part + kMaxParts * 2 * E;    // [kDispatchThreads] expert of each entry of the segment (kEp)
+  int* s_cnt = s_exp + kDispatchThreads;      // [world][E + 1] every rank's counts (kEp)
+  int* s_base = s_cnt + kMaxEpWorld * (E + 1);  // [E] owner row of this rank's first row per expert (kEp)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,6 +176,13 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   __syncthreads();
   for (int e = threadIdx.x; e < E; e += blockDim.x) s_cursor[e] += s_off[e];
   __syncthreads();
+  int ep_seq = 0;
+  bool ep_ok = true;
+  if (kEp) {
+    ep_seq = ep_ctrl(ep)[0] + 1;   // (only this kernel's last CTA advances the word, after every CTA has read it)
+    if (blockIdx.x == 0 && ep_send) ep_send_counts(ep, ep_seq, s_total, E, ep_mode);
+    ep_ok = ep_wait_counts(ep, ep_seq, E, ep_mode, s_cnt, s_base);
+  }
 
   const int begin = blockIdx.x * chunk;
   const int end = min(begin + chunk, Sk);
@@ -235,7 +211,15 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
       if (mapping_out) mapping_out[i] = dst;
       if (dst >= 0) {
         pos[dst] = i;
-        row_score[dst] = score ? score[i] : 1.0f;
+        const float sc = score ? score[i] : 1.0f;
+        row_score[dst] = sc;
+        if (kEp && ep_ok) {
+          const int owner = e / ep.E_local;
+          int2* meta = reinterpret_cast<int2*>(ep.base[owner] + ep.lay.meta);
+          meta[s_base[e] + dst - s_off[e]] =
+              make_int2(ep_meta_word(ep.rank, (ep_mode & kEpModeFold) ? i / top_k : dst, (ep_mode & kEpModeResidual) != 0),
+                        __float_as_int(sc));
+        }
       }
     }
     __syncthreads();
@@ -258,15 +242,16 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
         src[r] = x + static_cast<size_t>((seg + (j < n ? j : 0)) / top_k) * D;
       }
       bf16* drow[kRowsPerBatch];
+      bool drop[kRowsPerBatch];
 #pragma unroll
       for (int r = 0; r < kRowsPerBatch; ++r) {
         drow[r] = xbuf + static_cast<size_t>(d[r] < 0 ? 0 : d[r]) * D;
+        drop[r] = d[r] < 0;
         if (kEp && d[r] >= 0) {
-          const int j = j0 + r * kWarps;
-          const int dest = s_exp[j] / ep.E_local;
-          const int slot = d[r] - s_off[dest * ep.E_local];
-          drow[r] = reinterpret_cast<bf16*>(ep.base[dest] + ep.lay.recv_x) +
-                    (static_cast<size_t>(ep.rank) * ep.cap + slot) * D;
+          const int ex = s_exp[j0 + r * kWarps];
+          drow[r] = reinterpret_cast<bf16*>(ep.base[ex / ep.E_local] + ep.lay.recv_x) +
+                    static_cast<size_t>(s_base[ex] + d[r] - s_off[ex]) * D;
+          if (!ep_ok) d[r] = -1;  // a peer's counts are missing: push nothing
         }
       }
       if constexpr (kXf32) {
@@ -304,7 +289,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
 #pragma unroll
         for (int r = 0; r < kRowsPerBatch; ++r) {
           const int j = j0 + r * kWarps;
-          if (j < n && d[r] < 0) {
+          if (j < n && drop[r]) {
             // 16-byte accesses, four loads in flight before their stores (the two buffers may alias as far as the
             // compiler knows: element-wise this was one dependent L2 round trip per element)
             const size_t row = static_cast<size_t>(seg + j) / top_k * D;
@@ -342,6 +327,8 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
       if (offsets_out) offsets_out[e] = s_off[e];
     }
     if (!kEp) build_groups_block(s_off, E, bn, groups, n_groups, h_ready, gmax, s_scratch);
+    // this rank as an OWNER: group table over the merged rows of its local experts (s_part is free by now)
+    else ep_build_groups_merged(ep, E, s_cnt, ep_ok, bn, groups, n_groups, h_ready, gmax, s_part, s_part + E + 1);
   }
 
   if (kEp) {
@@ -360,34 +347,33 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
     }
     __syncthreads();
     if (s_last) {
-      const int seq = ctrl[0] + 1;
-      const int El = ep.E_local;
-      // counts (and the base row of the destination's segment) into every peer's recv_cnt[my rank][...]
-      for (int i = threadIdx.x; i < ep.world * (El + 1); i += blockDim.x) {
-        const int dest = i / (El + 1);
-        const int k = i - dest * (El + 1);
-        int* rc = reinterpret_cast<int*>(ep.base[dest] + ep.lay.recv_cnt) + ep.rank * (El + 1);
-        rc[k] = k < El ? s_total[dest * El + k] : s_off[dest * El];
-      }
+      // step 3: this rank's rows (and routing data) have landed everywhere -- one thread per peer raises the flag
       if (threadIdx.x == 0) {
         ctrl[1] = 0;
-        ctrl[0] = seq;
+        ctrl[0] = ep_seq;
+        ctrl[4] = ep_mode;
       }
-      __syncthreads();
-      // one release per peer (second round trip): covers the counts above through the barrier
       if (threadIdx.x < ep.world)
-        ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, seq);
-      if (ep_fold_wait) {
-        // Same CTA goes on to wait for the peers' rows and to build the FFN group table, which saves a kernel launch
-        // per layer (the standalone ep_wait_build_kernel exists for drivers that run the stages separately).
-        // s_part (8 * 2 * E ints) is free by now and large enough for both scratch arrays.
-        __syncthreads();
-        int* s_cnt2 = s_part;
-        int* s_g02 = s_part + ep.world * (El + 1);
-        ep_wait_and_build_groups(ep, seq, bn, groups, n_groups, h_ready, gmax, s_cnt2, s_g02);
-      }
+        ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, ep_seq);
+      // the same CTA waits for the peers' rows, so that the expert kernel behind this one can start on them at once
+      if (ep_fold_wait) ep_wait_rows(ep, ep_seq);
     }
   }
+}
+
+// Expert parallelism driven stage by stage (tests that emulate several ranks on one GPU: a kernel must never wait for a
+// kernel that is queued behind it): the counts alone, from the chunk histograms, without the scatter.
+__global__ void __launch_bounds__(kDispatchThreads)
+dispatch_ep_counts_kernel(const int* __restrict__ chunk_hist, int hist_rows, int E, const EpPeers ep, int ep_mode) {
+  extern __shared__ int s_dyn[];
+  int* s_total = s_dyn;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    int t = 0;
+    for (int c = 0; c < hist_rows; ++c) t += chunk_hist[c * E + e];
+    s_total[e] = t;
+  }
+  __syncthreads();
+  ep_send_counts(ep, ep_ctrl(ep)[0] + 1, s_total, E, ep_mode);
 }
 
 __global__ void __launch_bounds__(256)
@@ -416,13 +402,13 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
                             const int* hist32, cudaStream_t stream, const EpPeers* ep, bool ep_fold_wait,
-                            bool xbuf_f32) {
+                            bool xbuf_f32, int ep_mode, int ep_phase) {
   if (xbuf_f32 && (dtype != B200MOE_F32 || ep != nullptr || D % 4 != 0)) return cudaErrorInvalidValue;
   const int Sk = S * top_k;
-  if (top_k != 1 || ep != nullptr) drop_out = nullptr;
+  if (top_k != 1) drop_out = nullptr;  // (expert parallelism: only the folded path passes one)
   if (ep != nullptr && (ep->world * ep->E_local != E || Sk > ep->cap || ep->D != D)) return cudaErrorInvalidValue;
   if (E > kMaxExperts || E < 1 || D % 8 != 0) return cudaErrorInvalidValue;
-  const int gmax = max_groups(Sk, E, bn);
+  const int gmax = ep ? max_groups(ep->world * ep->cap, ep->E_local, bn) : max_groups(Sk, E, bn);
   if (Sk == 0 && ep == nullptr) {
     // nothing to route: still publish zero counts / offsets and an empty group table
     cudaError_t e = cudaMemsetAsync(ws.counts, 0, sizeof(int) * E, stream);
@@ -442,7 +428,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
     hist = hist32;  // counts came with the gate: no count kernel
     hist_rows = rows32;
     rows_per_chunk = ck.chunk_tok / 32;
-  } else {
+  } else if (ep_phase != 2) {   // (phase 2 = scatter only: the histograms are there from phase 1)
     dispatch_count_kernel<<<ck.nchunks, kDispatchThreads, 0, stream>>>(idx, Sk, E, ck.chunk, ws.chunk_hist);
     count_launch();
     cudaError_t err = cudaGetLastError();
@@ -450,10 +436,17 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
   }
   const int nparts_max = 8;
   const size_t dyn = sizeof(int) * (2 * E + 2 * (E + 1) + kDispatchThreads + (kDispatchThreads / 32) * E +
-                                    nparts_max * 2 * E + kDispatchThreads);
+                                    nparts_max * 2 * E + kDispatchThreads + kMaxEpWorld * (E + 1) + E);
   cudaError_t lerr = cudaSuccess;
   EpPeers epv{};
   if (ep) epv = *ep;
+  if (ep != nullptr && ep_phase == 1) {
+    // counts only (ranks emulated on one GPU are driven phase by phase: nobody may wait for a kernel queued behind it)
+    dispatch_ep_counts_kernel<<<1, kDispatchThreads, sizeof(int) * E, stream>>>(hist, hist_rows, E, epv, ep_mode);
+    count_launch();
+    return cudaGetLastError();
+  }
+  const int ep_send = ep_phase == 2 ? 0 : 1;
 #define B200MOE_SCATTER_K(T, EP)                                                                                  \
   lerr = launch_kernel(dispatch_scatter_kernel<T, EP, false>, dim3(ck.nchunks), dim3(kDispatchThreads), dyn, stream, \
       kPdlDispatch,                                                                                               \
@@ -461,7 +454,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
       rows_per_chunk, bn, gmax,                                                                                   \
       ws.counts, ws.offsets, ws.mapping, ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready,          \
       counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual),      \
-      (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, ep_fold_wait ? 1 : 0)
+      (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, ep_fold_wait ? 1 : 0, ep_mode, ep_send)
 #define B200MOE_SCATTER(T)          \
   if (ep)                           \
     B200MOE_SCATTER_K(T, true);     \
@@ -475,7 +468,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
                              ck.nchunks, hist, hist_rows, rows_per_chunk, bn, gmax, ws.counts, ws.offsets, ws.mapping,
                              ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready, counts_out, offsets_out,
                              mapping_out, static_cast<float*>(drop_out), static_cast<const float*>(drop_residual),
-                             (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, 0);
+                             (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, 0, 0, 0);
         break;
       }
       B200MOE_SCATTER(float);

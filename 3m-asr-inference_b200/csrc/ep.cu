@@ -3,18 +3,15 @@
 // data-parallel, and rows travel by plain stores into the destination GPU's memory.
 //
 // Reference behaviour replaced (trainer_3m_fix/fmoe/functions.py):
-//   :37-44   fmoe_cuda.expert_exchange   all-to-all of per-expert counts      -> counts stored into the peers by the
-//                                                                               dispatch kernel's last CTA
+//   :37-44   fmoe_cuda.expert_exchange   all-to-all of per-expert counts      -> count vectors stored into every rank by one
+//                                                                               CTA of the dispatch / route kernel
 //   :48-50   .cpu() of the counts        host synchronisation                 -> none: counts are only read on the device
-//   :74-80   fmoe_cuda.global_scatter    all-to-all-v of token rows           -> dispatch_scatter_kernel<.., kEp = true>
-//                                                                               pushes rows into recv_x of the owner rank
+//   :74-80   fmoe_cuda.global_scatter    all-to-all-v of token rows           -> the dispatch / route kernel pushes rows
+//                                                                               to their final place in the owner's buffer
 //   :185-191 fmoe_cuda.global_gather     all-to-all-v of expert outputs       -> the FFN kernel's second-GEMM epilogue
-//                                                                               stores rows into ret_y of the source rank
-// Per layer and rank: gate -> dispatch (push) -> ep_wait_build -> expert FFN (push back) -> ep_combine.  Every wait is a
-// spin on a flag in LOCAL memory that a peer raises with st.release.sys after its data; flags carry the layer sequence
-// number, so nothing is ever reset across ranks.  One receive buffer suffices: a rank can only start pushing layer L+1
-// after its combine of layer L, which needed every peer's "rows are back" flag, which a peer raises at the very end of
-// its FFN kernel, i.e. after its last read of the receive buffer.
+//                                                                               stores each row on its source rank
+// The protocol is described next to EpLayout (common.cuh).  Every wait is a bounded spin on a flag in LOCAL memory that
+// a peer raises with st.release.sys after its data.
 #include <cstring>
 
 #include "common.cuh"
@@ -26,13 +23,31 @@ namespace b200moe {
 
 namespace {
 
+// Staged drivers only (the one-call path folds this wait into the dispatch / route kernel's last CTA).
+__global__ void __launch_bounds__(32) ep_wait_rows_kernel(const EpPeers ep) {
+  const int seq = ep_ctrl(ep)[0];  // set by this rank's own dispatch kernel, which precedes this kernel in the stream
+  ep_wait_rows(ep, seq);
+}
+
+// Folded path (the owners write finished output rows into this rank's `out`): whatever consumes `out` next -- the next
+// layer's gate, a copy to the host -- is ordered behind this one-CTA kernel, which returns once every owner has raised
+// its "rows are back" flag for the current layer call.  A missing peer poisons `out` (NaN) and leaves the status word.
 __global__ void __launch_bounds__(256)
-ep_wait_build_kernel(const EpPeers ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax) {
-  __shared__ int s_cnt[kMaxEpWorld * (kMaxExperts + 1)];
-  __shared__ int s_g0[kMaxExperts + 1];  // E_local * world <= kMaxExperts
-  const int* ctrl = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ctrl);
-  const int seq = ctrl[0];  // set by this rank's own dispatch kernel, which precedes this kernel in the stream
-  ep_wait_and_build_groups(ep, seq, bn, groups, n_groups, h_ready, gmax, s_cnt, s_g0);
+ep_wait_done_kernel(const EpPeers ep, bf16* __restrict__ out, size_t n8) {
+  ptx::pdl_launch_dependents();  // the next layer's route kernel may set itself up (it touches constants only until its wait)
+  ptx::pdl_wait();               // this rank's own expert kernel (and through it the dispatch that set seq) has completed
+  int* ctrl = ep_ctrl(ep);
+  if (threadIdx.x < ep.world) {
+    const int seq = ctrl[0];
+    const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ret_flag);
+    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
+    if (!ep_wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kEpErrReturnTimeout);
+  }
+  __syncthreads();
+  if (*reinterpret_cast<volatile int*>(&ctrl[3]) != 0 && out != nullptr) {
+    const uint4 nan8 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
+    for (size_t i = threadIdx.x; i < n8; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = nan8;
+  }
 }
 
 __device__ __forceinline__ void bf16x8_to_f(const uint4& v, float (&o)[8]) {
@@ -171,12 +186,17 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
 
 }  // namespace
 
-cudaError_t launch_ep_wait_build(const EpPeers& ep, int bn, GroupRec* groups, int* n_groups, int* h_ready, int gmax,
-                                 cudaStream_t stream) {
-  if (ep.E_local > kMaxExperts || ep.world > kMaxEpWorld) return cudaErrorInvalidValue;
-  ep_wait_build_kernel<<<1, 256, 0, stream>>>(ep, bn, groups, n_groups, h_ready, gmax);
+cudaError_t launch_ep_wait_rows(const EpPeers& ep, cudaStream_t stream) {
+  ep_wait_rows_kernel<<<1, 32, 0, stream>>>(ep);
   count_launch();
   return cudaGetLastError();
+}
+
+cudaError_t launch_ep_wait_done(const EpPeers& ep, void* out, int S, int D, cudaStream_t stream) {
+  cudaError_t e = launch_kernel(ep_wait_done_kernel, dim3(1), dim3(256), 0, stream, kPdlFfn, ep, static_cast<bf16*>(out),
+                                static_cast<size_t>(S) * D / 8);
+  count_launch();
+  return e;
 }
 
 cudaError_t launch_ep_combine(const EpPeers& ep, const int* mapping, const float* score, const void* residual,

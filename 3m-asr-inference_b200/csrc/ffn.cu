@@ -71,7 +71,10 @@ struct FfnParams {
   // expert parallelism: results go to the source rank's return buffer over peer-mapped memory (NVLink)
   int ep;                           // 0 = off
   int ep_world, ep_rank;
-  uint8_t* ep_out[kMaxEpWorld];     // ret_y of every rank
+  int ep_fold;                      // 1: the epilogue writes the finished layer output (residual + ff_scale * score * y)
+                                    //    into the source rank's `out`; 0: the bare y row into the source's ret_y
+  const int2* ep_meta;              // per received row: {source rank << 27 | row index at the source, gate score bits}
+  uint8_t* ep_out[kMaxEpWorld];     // where rank r's rows go: its `out` buffer (fold) or its ret_y
   int* ep_ret_flag[kMaxEpWorld];    // &ret_flag[my rank] in every rank's buffer
   int* ep_ctrl;                     // local control block
   int* clear_ptr;   // zeroed at kernel start, spread over the CTAs (tagged histogram words of the route kernel)
@@ -338,6 +341,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   const uint32_t stage_off = ((tmem_slot + 16u + 15u) & ~15u) - ptx::smem_u32(smem_raw);
   int* s_tok = reinterpret_cast<int*>(smem_raw + stage_off + 2 * kStagingBytes);
   float* s_sc = reinterpret_cast<float*>(smem_raw + stage_off + 2 * kStagingBytes + 256 * 4);
+  // (expert parallelism packs more into s_tok: residual? << 31 | destination rank << 27 | row index, like EpLayout::meta)
   // generic pointer to the tmem slot for reading it back
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -716,19 +720,27 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         ptx::named_bar_sync(set_bar, kSetThreads);  // staging buffers free before the next tile reuses them
       } else {
         const float bias = p.b2 ? p.b2[static_cast<size_t>(gr.expert) * p.D + feat0 + feat_l] : 0.0f;
-        OutT* out = p.ep ? reinterpret_cast<OutT*>(p.ep_out[gr.src]) : static_cast<OutT*>(p.out);
+        OutT* out = static_cast<OutT*>(p.out);
         const OutT* res = static_cast<const OutT*>(p.residual);
-        const bool with_res = p.fused && res != nullptr && !(p.dbg & 4);
+        const bool with_res = (p.fused || p.ep_fold) && res != nullptr && !(p.dbg & 4);
         const bool st2 = !(p.dbg & 1);
         // routing table of the tile's columns: output row and scale (filled while the MMAs are still running)
         ptx::named_bar_sync(3, kEpiThreads);  // every warp is done with the previous table
         for (int i = et; i < nrows; i += kEpiThreads) {
           const int row = gr.row0 + i;
-          int tok = gr.orow0 + i;  // un-fused: same row of the output buffer (the source rank's under EP)
+          int tok = gr.orow0 + i;  // un-fused: same row of the output buffer
           float sc = 1.0f;
           if (p.fused) {
             tok = p.pos[row] / p.top_k;
             sc = p.ff_scale * (p.row_score ? p.row_score[row] : 1.0f);
+          }
+          if (p.ep) {
+            // expert parallelism: the row's routing data came with it (written by the source GPU: L2-coherent load)
+            const int2 m = __ldcg(p.ep_meta + row);
+            tok = m.x;
+            if (((m.x >> kEpMetaRankShift) & kEpMetaRankMask) >= p.ep_world)  // (never for a row that was really sent)
+              tok = ep_meta_word(p.ep_rank, m.x & kEpMetaIndexMask, false);
+            if (p.ep_fold) sc = p.ff_scale * __int_as_float(m.y);
           }
           s_tok[i] = tok;
           s_sc[i] = sc;
@@ -755,8 +767,11 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
               for (int i = 0; i < 4; ++i) {
                 const int col = (2 * cc + set) * 32 + q * 8 + 2 * i + half;
                 const bool v = col < nrows;
-                const int tok = v ? s_tok[col] : 0;
-                rres[cc][i] = ld_pred_v4(res + static_cast<size_t>(tok) * p.D + fo16, v && with_res);
+                // residual row: the token's (fused), or -- expert parallelism -- the received row itself when the source had one
+                const int w = v ? s_tok[col] : 0;
+                const bool hr = v && (!p.ep || w < 0);
+                const int rr = p.ep ? gr.row0 + col : w;
+                rres[cc][i] = ld_pred_v4(res + static_cast<size_t>(hr ? rr : 0) * p.D + fo16, hr && with_res);
               }
             } else {
 #pragma unroll
@@ -799,14 +814,16 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
                   const int j = q * 8 + 2 * i + half;
                   const int col = c0 + j;
                   const bool v = col < nrows;
-                  const int tok = v ? s_tok[col] : 0;
+                  const int w = v ? s_tok[col] : 0;
+                  const int tok = p.ep ? (w & kEpMetaIndexMask) : w;
+                  OutT* ob = p.ep ? reinterpret_cast<OutT*>(p.ep_out[(w >> kEpMetaRankShift) & kEpMetaRankMask]) : out;
                   const uint4 a = *reinterpret_cast<const uint4*>(sb + j * kBlockM + l16 * 8);
                   uint4 o;
                   o.x = add_packed<OutT>(rres[cs][i].x, a.x);
                   o.y = add_packed<OutT>(rres[cs][i].y, a.y);
                   o.z = add_packed<OutT>(rres[cs][i].z, a.z);
                   o.w = add_packed<OutT>(rres[cs][i].w, a.w);
-                  st_pred_v4(out + static_cast<size_t>(tok) * p.D + fo16, o, v && st2);
+                  st_pred_v4(ob + static_cast<size_t>(tok) * p.D + fo16, o, v && st2);
                 }
                 if (tracer_thread) tr.rec(t, kEvEpiChunkDone);
               }
@@ -1060,14 +1077,19 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
     p.ep_out[r] = nullptr;
     p.ep_ret_flag[r] = nullptr;
   }
+  p.ep_fold = 0;
+  p.ep_meta = nullptr;
   if (a.ep != nullptr) {
     if (a.fused || a.out_dtype != B200MOE_BF16) return cudaErrorInvalidValue;
     p.ep = 1;
     p.ep_world = a.ep->world;
     p.ep_rank = a.ep->rank;
+    p.ep_fold = a.ep_fold ? 1 : 0;
+    p.ep_meta = reinterpret_cast<const int2*>(a.ep->base[a.ep->rank] + a.ep->lay.meta);
     p.ep_ctrl = reinterpret_cast<int*>(a.ep->base[a.ep->rank] + a.ep->lay.ctrl);
     for (int r = 0; r < a.ep->world; ++r) {
-      p.ep_out[r] = a.ep->base[r] + a.ep->lay.ret_y;
+      // fold: the same offset inside every rank's symmetric buffer as this rank's own `out` (symmetric allocation)
+      p.ep_out[r] = a.ep->base[r] + (a.ep_fold ? a.ep_out_off : a.ep->lay.ret_y);
       p.ep_ret_flag[r] = reinterpret_cast<int*>(a.ep->base[r] + a.ep->lay.ret_flag) + a.ep->rank;
     }
   }

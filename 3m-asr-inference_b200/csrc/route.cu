@@ -177,6 +177,7 @@ struct RouteParams {
   unsigned nonce;
   unsigned long long tag;  // 56 random bits (<< 8) drawn per launch: what makes a histogram word this launch's
   int ep_fold_wait;
+  int ep_mode;   // kEpModeFold / kEpModeResidual bits of this call (checked against the peers')
   // norm_ff fused into the router (block call, route_kernel<.., kLn = true>); null = off
   const float* ln_gamma;
   const float* ln_beta;
@@ -607,10 +608,20 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     if (static_cast<int>(threadIdx.x) == E - 1) s_off[E] = incl;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    rtrace(p, 6);
-    rtrace(p, 7);
+  if (threadIdx.x == 0) rtrace(p, 6);
+  // Expert parallelism, steps 1 and 2 of the protocol (common.cuh): CTA 0 tells every rank how many rows this rank has for
+  // each expert, every CTA waits for all ranks' counts and learns where its rows belong in the owners' receive buffers.
+  // s_part is free again: [0, W * (E + 1)) count matrix, then s_base[E], then scratch for the group table.
+  int* s_cnt = s_part;
+  int* s_base = s_part + kMaxEpWorld * 33;
+  int ep_seq = 0;
+  bool ep_ok = true;
+  if (kEp) {
+    ep_seq = ep_ctrl(ep)[0] + 1;   // (only this kernel's last CTA advances the word, after every CTA has read it)
+    if (blockIdx.x == 0) ep_send_counts(ep, ep_seq, s_total, E, p.ep_mode);
+    ep_ok = ep_wait_counts(ep, ep_seq, E, p.ep_mode, s_cnt, s_base);
   }
+  if (threadIdx.x == 0) rtrace(p, 7);
 
   for (int c = blockIdx.x; c < n_tiles; c += gridDim.x) {
     if (c != static_cast<int>(blockIdx.x)) {
@@ -635,7 +646,17 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         if (p.mapping_out) p.mapping_out[tok] = dst;
         if (dst >= 0) {
           p.pos[dst] = tok;
-          p.row_score[dst] = p.keep_expert_output ? 1.0f : p.score[tok];
+          const float sc = p.keep_expert_output ? 1.0f : p.score[tok];
+          p.row_score[dst] = sc;
+          if (kEp && ep_ok) {
+            // routing data travels with the row: where the owner sends the result (the token's output row when the
+            // combine is folded into the owner's epilogue, else this rank's expert-order row) and the gate score
+            const int owner = e / ep.E_local;
+            const int slot = s_base[e] + dst - s_off[e];
+            int2* meta = reinterpret_cast<int2*>(ep.base[owner] + ep.lay.meta);
+            meta[slot] = make_int2(ep_meta_word(ep.rank, (p.ep_mode & kEpModeFold) ? tok : dst,
+                                                (p.ep_mode & kEpModeResidual) != 0), __float_as_int(sc));
+          }
         }
       }
     }
@@ -650,20 +671,19 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const int ch = lane & 7;
       const int tok = c * kTok + r;
       const int d = tok < p.S ? s_dst[r] : -1;
-      if (d >= 0) {
+      if (d >= 0 && (!kEp || ep_ok)) {
         bf16* drow = p.xbuf + static_cast<size_t>(d) * p.D;
         if (kEp) {
-          const int dest = s_exp[r] / ep.E_local;
-          const int slot = d - s_off[dest * ep.E_local];
-          drow = reinterpret_cast<bf16*>(ep.base[dest] + ep.lay.recv_x) +
-                 (static_cast<size_t>(ep.rank) * ep.cap + slot) * p.D;
+          const int ex = s_exp[r];
+          drow = reinterpret_cast<bf16*>(ep.base[ex / ep.E_local] + ep.lay.recv_x) +
+                 static_cast<size_t>(s_base[ex] + d - s_off[ex]) * p.D;
         }
         const uint8_t* sx = smem_raw + (n_parts - 1) * kRSlot + kRSlotA + r * 128 + ((ch ^ (r & 7)) << 4);
         // (kLn: the statistics warps have normalised the rows in place by now)
 #pragma unroll 4
         for (int j = 0; j < kb_x; ++j)
           reinterpret_cast<uint4*>(drow)[j * 8 + ch] = *reinterpret_cast<const uint4*>(sx + j * kRBBlk);
-      } else if (tok < p.S && p.drop_out != nullptr) {
+      } else if (d < 0 && tok < p.S && p.drop_out != nullptr) {
         // dropped token (padding): output row = residual row (or zero); the fused FFN epilogue never touches it
         // (16-byte accesses, every load of the row issued before its stores: the compiler cannot prove that the two
         // buffers do not alias, and one dependent L2 round trip per element made a padded batch 4x slower)
@@ -684,6 +704,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       const bf16* src[4];
       bf16* drow[4];
       int d[4];
+      bool drop[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int j = warp + r * 8;
@@ -691,11 +712,12 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         d[r] = tok < p.S ? s_dst[j] : -1;
         src[r] = p.x + static_cast<size_t>(tok < p.S ? tok : 0) * p.D;
         drow[r] = p.xbuf + static_cast<size_t>(d[r] < 0 ? 0 : d[r]) * p.D;
+        drop[r] = tok < p.S && d[r] < 0;
         if (kEp && d[r] >= 0) {
-          const int dest = s_exp[j] / ep.E_local;
-          const int slot = d[r] - s_off[dest * ep.E_local];
-          drow[r] = reinterpret_cast<bf16*>(ep.base[dest] + ep.lay.recv_x) +
-                    (static_cast<size_t>(ep.rank) * ep.cap + slot) * p.D;
+          const int ex = s_exp[j];
+          drow[r] = reinterpret_cast<bf16*>(ep.base[ex / ep.E_local] + ep.lay.recv_x) +
+                    static_cast<size_t>(s_base[ex] + d[r] - s_off[ex]) * p.D;
+          if (!ep_ok) d[r] = -1;  // a peer's counts are missing: push nothing
         }
       }
       if constexpr (kLn) {
@@ -745,7 +767,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int tok = c * kTok + warp + r * 8;
-          if (tok < p.S && d[r] < 0) {
+          if (drop[r]) {
             const size_t row = static_cast<size_t>(tok) * p.D;
             uint4* orow = reinterpret_cast<uint4*>(p.drop_out + row);
             const uint4* rrow = reinterpret_cast<const uint4*>(p.drop_residual + row);
@@ -799,6 +821,10 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         }
       }
       for (int g = threadIdx.x; g < p.gmax; g += blockDim.x) p.h_ready[g] = 0;
+    } else {
+      // this rank as an OWNER: the expert kernel's group table over the merged rows of its local experts
+      ep_build_groups_merged(ep, E, s_cnt, ep_ok, p.bn, p.groups, p.n_groups, p.h_ready, p.gmax,
+                             s_base + 40, s_base + 40 + kMaxExperts / 4 + 8);
     }
   }
 
@@ -821,25 +847,16 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     __syncthreads();
   }
   if (kEp && *s_lastp) {
-    int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
-    const int seq = ctrl[0] + 1;
-    const int El = ep.E_local;
-    for (int i = threadIdx.x; i < ep.world * (El + 1); i += blockDim.x) {
-      const int dest = i / (El + 1);
-      const int k = i - dest * (El + 1);
-      int* rc = reinterpret_cast<int*>(ep.base[dest] + ep.lay.recv_cnt) + ep.rank * (El + 1);
-      rc[k] = k < El ? s_total[dest * El + k] : s_off[dest * El];
+    // step 3: this rank's rows (and routing data) have landed everywhere -- one thread per peer raises the flag
+    int* ctrl = ep_ctrl(ep);
+    if (threadIdx.x == 0) {
+      ctrl[0] = ep_seq;
+      ctrl[4] = p.ep_mode;
     }
-    if (threadIdx.x == 0) ctrl[0] = seq;
-    __syncthreads();
     if (threadIdx.x < ep.world)
-      ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, seq);
-    if (p.ep_fold_wait) {
-      __syncthreads();
-      // E_local * world == E <= 32 here: s_part (512 ints) holds both scratch arrays
-      ep_wait_and_build_groups(ep, seq, p.bn, p.groups, p.n_groups, p.h_ready, p.gmax, s_part,
-                               s_part + ep.world * (El + 1));
-    }
+      ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, ep_seq);
+    // the same CTA waits for the peers' rows, so that the expert kernel behind this one can start on them at once
+    if (p.ep_fold_wait) ep_wait_rows(ep, ep_seq);
   }
 
   ptx::tc_fence_before();
@@ -896,7 +913,8 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          int B, int T, int D, int Demb, int E, int gate_mode, int keep_expert_output, int* idx,
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream, const EpPeers* ep,
-                         bool ep_fold_wait, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* ln_c) {
+                         bool ep_fold_wait, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* ln_c,
+                         int ep_mode) {
   const int S = B * T;
   if (embed == nullptr) Demb = 0;
   if (!route_supported(S, D, Demb, E, 1, B200MOE_BF16)) return cudaErrorInvalidValue;
@@ -937,11 +955,11 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   p.n_groups = ws.n_groups;
   p.h_ready = ws.h_ready;
   p.bn = bn;
-  p.gmax = ep ? max_groups(ep->world * ep->cap, E, bn) : max_groups(S, E, bn);
+  p.gmax = ep ? max_groups(ep->world * ep->cap, ep->E_local, bn) : max_groups(S, E, bn);
   p.counts_out = counts_out;
   p.offsets_out = offsets_out;
   p.mapping_out = mapping_out;
-  p.drop_out = ep ? nullptr : static_cast<bf16*>(drop_out);
+  p.drop_out = static_cast<bf16*>(drop_out);  // (expert parallelism: only the folded path passes one)
   p.drop_residual = static_cast<const bf16*>(drop_residual);
   p.keep_expert_output = keep_expert_output;
   p.bar = reinterpret_cast<unsigned long long*>(ws.n_groups + 2);  // completion counter {nonce, CTAs done}
@@ -951,6 +969,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   p.nonce = nonce;
   p.tag = next_route_tag();
   p.ep_fold_wait = ep_fold_wait ? 1 : 0;
+  p.ep_mode = ep_mode;
   // kLn: `wr_packed` is the pre-scaled router of b200moe_pack_router_ln and ln_c its c1 / c0 tail
   p.ln_gamma = (ln_gamma != nullptr && ln_beta != nullptr && ln_c != nullptr) ? ln_gamma : nullptr;
   p.ln_beta = ln_beta;

@@ -3,10 +3,14 @@
 Reference behaviour being reproduced: experts partitioned contiguously over the GPUs of one node, `num_expert` per
 worker (trainer_3m_fix/model/..._hier.py:259-273), tokens exchanged around the expert computation
 (trainer_3m_fix/fmoe/functions.py:37-50 counts, :74-80 rows out, :185-191 rows back).  Here the exchange is done by the
-kernels themselves: the dispatch kernel stores rows into the owner GPU's receive buffer, the expert-FFN kernel stores
-results into the source GPU's return buffer, flags with system-scope release/acquire signal arrival.  torch.distributed
-is used ONCE, at set-up, to pass the 64-byte CUDA IPC handles around; there is no collective and no host
-synchronisation per layer (see include/b200moe.h, "expert parallelism over peer-mapped memory").
+kernels themselves: the dispatch kernel tells every rank its counts and stores rows to their final place in the owner
+GPU's receive buffer, the expert-FFN kernel stores results on the source GPU, flags with system-scope release/acquire
+signal arrival.  torch.distributed is used ONCE, at set-up, to pass the 64-byte CUDA IPC handles around; there is no
+collective and no host synchronisation per layer (see include/b200moe.h, "expert parallelism over peer-mapped memory").
+
+Folded combine: pass `out=ctx.out_buffer(slot, S)` (slots 0 / 1 alternately, the same slot on every rank) with
+`residual=x` (or None) and top-1 routing, and the owners write the finished output rows straight into that buffer; with
+`wait=False` the wait for them is left to the next `forward` on the context (or `ctx.wait()`).
 """
 from __future__ import annotations
 
@@ -16,6 +20,21 @@ from typing import List, Optional
 import torch
 
 from . import _lib, ops
+
+
+class _RawDeviceMemory:
+    """__cuda_array_interface__ over memory this package allocated with cudaMalloc (the symmetric buffer)."""
+
+    def __init__(self, ptr: int, rows: int, cols: int, owner):
+        self._owner = owner   # keeps the context (and with it the allocation) alive
+        self.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<i2", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def _device_view(ptr: int, rows: int, cols: int, device, owner) -> torch.Tensor:
+    with torch.cuda.device(device):
+        t = torch.as_tensor(_RawDeviceMemory(ptr, rows, cols, owner), device=device)
+    return t.view(torch.bfloat16)
 
 
 class EpContext:
@@ -33,6 +52,7 @@ class EpContext:
         self._owned_local = owned_local      # buffer this object cudaMalloc'ed (freed on close)
         self._opened = opened or []          # IPC mappings this object opened
         self._ws = {}
+        self._out = {}
 
     # ---- construction -------------------------------------------------------------------------------------------------
     @staticmethod
@@ -110,6 +130,23 @@ class EpContext:
             self._ws[key] = ws
         return ws
 
+    def out_buffer(self, slot: int, rows: int) -> torch.Tensor:
+        """[rows, D] bf16 view of output slot 0 / 1 inside this rank's symmetric buffer (reachable by the peers)."""
+        if rows > self.cap:
+            raise ValueError(f"{rows} rows exceed the context capacity {self.cap}")
+        base = self._out.get(slot)
+        if base is None:
+            ptr, nbytes = C.c_void_p(), C.c_size_t()
+            _lib.check(_lib.load().b200moe_ep_out_buffer(self._ctx, slot, C.byref(ptr), C.byref(nbytes)),
+                       "b200moe_ep_out_buffer")
+            base = _device_view(ptr.value, self.cap, self.D, self.device, self)
+            self._out[slot] = base
+        return base[:rows]
+
+    def wait(self) -> None:
+        """Orders the current stream behind the owners' writes of the last folded `forward(..., wait=False)`."""
+        _lib.check(_lib.load().b200moe_ep_wait(self._ctx, ops._stream()), "b200moe_ep_wait")
+
     def status(self) -> int:
         st = C.c_int(0)
         _lib.check(_lib.load().b200moe_ep_status(self._ctx, C.byref(st)), "b200moe_ep_status")
@@ -120,14 +157,17 @@ class EpContext:
                 x_len: Optional[torch.Tensor] = None, seq_len: Optional[int] = None, top_k: int = 1,
                 gate_mode: int = ops.GATE_3M, act_type: int = ops.ACT_SILU, ff_scale: float = 1.0,
                 keep_expert_output: bool = False, out: Optional[torch.Tensor] = None,
-                Wr_packed: Optional[torch.Tensor] = None, return_routing: bool = False, stages: int = 7,
-                routing_bufs=None, norm_ff=None, norm_final=None, eps: float = 1e-12, Wr_packed_ln=None):
+                Wr_packed: Optional[torch.Tensor] = None, return_routing: bool = False, stages: int = 15,
+                routing_bufs=None, norm_ff=None, norm_final=None, eps: float = 1e-12, Wr_packed_ln=None,
+                wait: bool = True, out_slot: Optional[int] = None):
         """x [S, D] bf16: this rank's tokens.  experts: this rank's `num_local_expert` experts.  Wr [R, E_total].
         norm_ff / norm_final = (gamma, beta) fp32 [D]: the block's LayerNorms either side of the layer (ops.moe_layer)."""
         block = norm_ff is not None or norm_final is not None
         norms = [t for pair in (norm_ff, norm_final) if pair is not None for t in pair]
-        if block and stages != 7:
+        if block and stages != 15:
             raise ValueError("the block call runs all stages at once")
+        if not wait and stages != 15:
+            raise ValueError("wait=False goes with the one-call form")
         dev = ops._need_cuda(x, embed, Wr, br, residual, x_len, experts.W1, experts.b1, experts.W2, experts.b2, out,
                              Wr_packed, Wr_packed_ln, *norms)
         if x.dtype != torch.bfloat16:
@@ -140,7 +180,13 @@ class EpContext:
             raise ValueError(f"got {E_local} local experts, the context was built for {self.E_local}")
         E_total = E_local * self.world
         Demb = 0 if embed is None else embed.shape[-1]
-        if out is None:
+        out_ptr = None
+        if out_slot is not None:
+            # output slot of the symmetric buffer (folded combine).  The pointer is passed even for a rank without tokens
+            # (an empty view has no data pointer): every rank has to decide for or against folding the same way.
+            out = self.out_buffer(out_slot, S)
+            out_ptr = self._out[out_slot].data_ptr()
+        elif out is None:
             out = torch.empty_like(x)
         idx = score = counts = mapping = None
         if return_routing:
@@ -154,7 +200,8 @@ class EpContext:
         ws = self.workspace(H, block)
         p = ops._ptr
         a = _lib.LayerArgs(
-            x=p(x), embed=p(embed), residual=p(residual), out=p(out), x_len=p(x_len), Wr=p(Wr), Wr_packed=p(Wr_packed),
+            x=p(x), embed=p(embed), residual=p(residual), out=out_ptr if out_ptr is not None else p(out), x_len=p(x_len),
+            Wr=p(Wr), Wr_packed=p(Wr_packed),
             br=p(br), W1=p(experts.W1), b1=p(experts.b1), W2=p(experts.W2), b2=p(experts.b2), B=B, T=T, D=D, Demb=Demb,
             E=E_total, H=H, top_k=top_k, gate_mode=gate_mode, act_type=act_type, dtype=ops.dtype_code(x),
             keep_expert_output=int(keep_expert_output), ff_scale=float(ff_scale), idx_out=p(idx), score_out=p(score),
@@ -167,6 +214,9 @@ class EpContext:
                                Wr_packed_ln=p(Wr_packed_ln) if norm_ff else None)
             _lib.check(_lib.load().b200moe_ep_block_forward(self._ctx, C.byref(b), p(ws), ws.numel(), ops._stream()),
                        "b200moe_ep_block_forward")
+        elif not wait:
+            _lib.check(_lib.load().b200moe_ep_forward_deferred(self._ctx, C.byref(a), p(ws), ws.numel(), ops._stream()),
+                       "b200moe_ep_forward_deferred")
         else:
             _lib.check(_lib.load().b200moe_ep_forward_stages(self._ctx, C.byref(a), p(ws), ws.numel(), stages,
                                                              ops._stream()), "b200moe_ep_forward")

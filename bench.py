@@ -360,6 +360,9 @@ class Case:
         if b.world > 1 and b.args.ep == "p2p":
             self.ep_ctx = b.ep_mod.EpContext.from_process_group(b.E_local, D, cap=cap or max(S * top_k, 1),
                                                                 timeout_ms=20000)
+        if self.ep_ctx is not None:
+            # outputs inside the symmetric buffer: the owners' epilogue writes the finished rows there (folded combine)
+            self.bufs = [self.ep_ctx.out_buffer(0, S), self.ep_ctx.out_buffer(1, S)]
         self.graph = None
         self.final = None
 
@@ -382,7 +385,10 @@ class Case:
         e_in = self.e_dev if e_in is None else e_in
         for li in range(self.L):
             out = self.bufs[li & 1]
-            self.layer_call(li, cur, e_in, out)
+            if self.ep_ctx is not None:   # the wait for the owners' rows is left to the next layer's call; the last waits
+                self.layer_call(li, cur, e_in, out, wait=li == self.L - 1, out_slot=li & 1)
+            else:
+                self.layer_call(li, cur, e_in, out)
             cur = out
         return cur
 
@@ -472,10 +478,10 @@ def ep_parity(b: Bench, case: Case):
         return torch.cat(parts, 0)
 
     full = ops.PackedExperts(gather(ex.W1), gather(ex.b1), gather(ex.W2), gather(ex.b2))
-    out_ep = torch.empty_like(case.x_dev)
+    out_ep = case.bufs[0]   # (the timed configuration: output in the symmetric buffer, combine folded into the owners)
     common = dict(residual=case.x_dev, top_k=case.top_k, gate_mode=case.gate_mode, act_type=ops.ACT_SILU, ff_scale=0.5,
                   x_len=case.x_len, seq_len=case.T, return_routing=True)
-    r_ep = case.ep_ctx.forward(case.x_dev, case.e_dev, ly["Wr"], ly["br"], ex, Wr_packed=ly["Wrp"], out=out_ep,
+    r_ep = case.ep_ctx.forward(case.x_dev, case.e_dev, ly["Wr"], ly["br"], ex, Wr_packed=ly["Wrp"], out_slot=0,
                                **common)
     torch.cuda.synchronize()
     dist.barrier()

@@ -186,10 +186,13 @@ int b200moe_forward(const b200moe_layer_args* args, void* ws, size_t ws_bytes, c
  * (expert e on rank e / E_local; `num_expert` is per worker: trainer_3m_fix/model/..._hier.py:259-273), tokens stay
  * data-parallel, and fmoe_cuda exchanges counts and rows with all-to-alls around the expert computation
  * (trainer_3m_fix/fmoe/functions.py:37-50 expert_exchange + .cpu(), :74-80 global_scatter, :185-191 global_gather).
- * Here the exchange is fused into the kernels on either side of it: the dispatch kernel stores token rows straight
- * into the owner GPU's receive buffer, the expert-FFN kernel's second GEMM stores its result rows straight into the
- * source GPU's return buffer, and arrival is signalled with system-scope release/acquire flags -- no collective call,
- * no host synchronisation, CUDA-graph capturable.  One process per GPU; the buffers are exchanged once at set-up:
+ * Here the exchange is fused into the kernels on either side of it, over peer-mapped memory: one CTA of the dispatch
+ * kernel stores this rank's per-expert counts into every rank; every CTA waits for all ranks' counts and stores its
+ * token rows straight to their final place in the owner GPU's receive buffer (expert-major, so that each local expert's
+ * rows are contiguous whatever rank they came from and the expert kernel runs full token tiles); the expert-FFN kernel's
+ * second GEMM stores every result row straight to its source GPU; arrival is signalled with system-scope
+ * release/acquire flags -- no collective call, no host synchronisation, CUDA-graph capturable.  One process per GPU;
+ * the buffers are exchanged once at set-up:
  *
  *   every rank:  b200moe_ep_alloc(b200moe_ep_buffer_bytes(world, E_local, D, cap), &buf);   (cudaMalloc, zeroed)
  *                b200moe_ep_ipc_export(buf, handle);   all-gather the 64-byte handles by any means (host side)
@@ -199,8 +202,17 @@ int b200moe_forward(const b200moe_layer_args* args, void* ws, size_t ws_bytes, c
  *
  * cap = the largest B*T*top_k any rank will ever pass.  args->E is the TOTAL number of experts (router width),
  * args->W1/b1/W2/b2 hold this rank's E_local experts.  Activations must be bf16.  Every rank must call
- * b200moe_ep_forward the same number of times (ranks without tokens pass B*T = 0).  A peer that does not show up
- * within timeout_ms makes the waiting kernels give up and sets the status word (b200moe_ep_status != 0). */
+ * b200moe_ep_forward the same number of times with the same kind of arguments (ranks without tokens pass B*T = 0).  A
+ * peer that does not show up within timeout_ms makes the waiting kernels give up, sets the status word
+ * (b200moe_ep_status != 0) and poisons the layer's output with NaNs.
+ *
+ * Folded combine.  When the call is top-1, args->residual is NULL or args->x itself, there is no norm_final, and
+ * args->out lies inside this rank's symmetric buffer (b200moe_ep_out_buffer: two slots, to be used alternately, the same
+ * slot on every rank), the owner's epilogue writes the finished rows  residual + ff_scale * score * y  directly into the
+ * source rank's `out` and no combine kernel runs at all (the reference's MOEGather + weighting + residual add,
+ * functions.py:185-194, positionwise_feed_forward.py:257-258).  b200moe_ep_forward then ends with a one-CTA kernel that
+ * waits for the owners' flags; b200moe_ep_forward_deferred leaves that wait to the next b200moe_ep_forward* call on the
+ * context (which does it first thing) or to an explicit b200moe_ep_wait -- nothing else may touch `out` before. */
 typedef struct b200moe_ep_ctx b200moe_ep_ctx;
 size_t b200moe_ep_buffer_bytes(int world, int E_local, int D, int cap);
 int b200moe_ep_alloc(size_t bytes, void** dev_ptr);
@@ -214,13 +226,19 @@ void b200moe_ep_destroy(b200moe_ep_ctx* ctx);
 size_t b200moe_ep_workspace_bytes(const b200moe_ep_ctx* ctx, int H);
 int b200moe_ep_forward(b200moe_ep_ctx* ctx, const b200moe_layer_args* args, void* ws, size_t ws_bytes,
                        cudaStream_t stream);
-/* Same, restricted to some of its stages (bit 0: gate + dispatch/push, bit 1: wait for the peers' rows + expert FFN
- * + push back, bit 2: wait for the returned rows + combine).  Lets one process drive several ranks on ONE GPU stage
- * by stage (tests): kernels that wait on one another must never be queued on the same GPU in the wrong order. */
+int b200moe_ep_forward_deferred(b200moe_ep_ctx* ctx, const b200moe_layer_args* args, void* ws, size_t ws_bytes,
+                                cudaStream_t stream);
+int b200moe_ep_wait(b200moe_ep_ctx* ctx, cudaStream_t stream);
+/* Output slot 0 / 1 inside this rank's symmetric buffer: [cap, D] bf16 each. */
+int b200moe_ep_out_buffer(const b200moe_ep_ctx* ctx, int slot, void** dev_ptr, size_t* bytes);
+/* The same layer, driven in stages (bit mask: 1 gate + this rank's counts to every rank, 8 wait for the counts + push
+ * the rows, 2 wait for the rows + expert FFN + push back, 4 wait for the results (+ combine); 15 = b200moe_ep_forward).
+ * Lets one process drive several ranks on ONE GPU stage by stage (tests): kernels that wait on one another must never
+ * be queued on the same GPU in the wrong order. */
 int b200moe_ep_forward_stages(b200moe_ep_ctx* ctx, const b200moe_layer_args* args, void* ws, size_t ws_bytes,
                               int stages, cudaStream_t stream);
 /* Reads the context's device status word (synchronous copy): 0 ok, 1 a peer's rows did not arrive, 2 returned rows did
- * not arrive. */
+ * not arrive, 3 a peer's counts did not arrive, 4 the ranks disagree on folding the combine. */
 int b200moe_ep_status(const b200moe_ep_ctx* ctx, int* host_status);
 
 /* ---- plugin object: mirror of FMoEExpertPlugin / FMoEExpertPluginCreator --------------------------------------

@@ -26,8 +26,10 @@ E, D, H, DEMB = 32, 512, 1024, 512
 
 
 def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=None, random_bias=True, seed=4242,
-              layers=1, keep_expert_output=False, stage_seq=(1, 2, 4), x_lens=None):
-    """x_lens: per rank an int32 tensor of valid lengths (sizes[r] = len(x_lens[r]) * T_r padded rows) or None."""
+              layers=1, keep_expert_output=False, stage_seq=(1, 8, 2, 4), x_lens=None, fold=False):
+    """x_lens: per rank an int32 tensor of valid lengths (sizes[r] = len(x_lens[r]) * T_r padded rows) or None.
+    stage_seq: 1 gate + counts, 8 scatter, 2 expert FFN, 4 results (15 = everything in one call: one rank only).
+    fold: outputs live in the symmetric buffers, so that top-1 calls with residual = x (or none) take the folded combine."""
     gate_mode = ops.GATE_3M if gate_mode is None else gate_mode
     dev = torch.device("cuda")
     E_local = E // world
@@ -53,23 +55,30 @@ def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=No
                                   full.b1[r * E_local:(r + 1) * E_local].contiguous(),
                                   full.W2[r * E_local:(r + 1) * E_local].contiguous(),
                                   full.b2[r * E_local:(r + 1) * E_local].contiguous()) for r in range(world)]
-        outs = [torch.empty_like(c) for c in cur]
+        outs = ([ctxs[r].out_buffer(li & 1, sizes[r]) for r in range(world)] if fold
+                else [torch.empty_like(c) for c in cur])
         rbufs = [(torch.empty(sizes[r], top_k, dtype=torch.int32, device=dev),
                   torch.empty(sizes[r], top_k, dtype=torch.float32, device=dev),
                   torch.empty(E, dtype=torch.int32, device=dev),
                   torch.empty(sizes[r] * top_k, dtype=torch.int32, device=dev)) for r in range(world)]
         # the MoE term alone first (no residual, ff_scale 1): the O(1) residual must not be able to mask an error in it
-        moes = [torch.empty_like(c) for c in cur]
+        moes = ([ctxs[r].out_buffer((li + 1) & 1, sizes[r]) for r in range(world)] if fold
+                else [torch.empty_like(c) for c in cur])
+        moe_keep = [None] * world
         for stage in stage_seq:
             for r in range(world):
                 ctxs[r].forward(cur[r], emb[r], Wr, br, mine[r], residual=None, top_k=top_k, gate_mode=gate_mode,
-                                ff_scale=1.0, out=moes[r], Wr_packed=packed, return_routing=True, stages=stage,
+                                ff_scale=1.0, out=moes[r], out_slot=((li + 1) & 1) if fold else None, Wr_packed=packed,
+                                return_routing=True, stages=stage,
                                 routing_bufs=rbufs[r], keep_expert_output=keep_expert_output, x_len=xl_dev[r],
                                 seq_len=Ts[r])
+        torch.cuda.synchronize()
+        moe_keep = [m.clone() for m in moes]   # (fold: the slot is reused two layers on)
         for stage in stage_seq:
             for r in range(world):
                 ctxs[r].forward(cur[r], emb[r], Wr, br, mine[r], residual=cur[r], top_k=top_k, gate_mode=gate_mode,
-                                ff_scale=0.5, out=outs[r], Wr_packed=packed, return_routing=True, stages=stage,
+                                ff_scale=0.5, out=outs[r], out_slot=(li & 1) if fold else None, Wr_packed=packed,
+                                return_routing=True, stages=stage,
                                 routing_bufs=rbufs[r], keep_expert_output=keep_expert_output, x_len=xl_dev[r],
                                 seq_len=Ts[r])
         torch.cuda.synchronize()
@@ -94,10 +103,10 @@ def run_world(ops, ep_mod, synth, oracle, world, sizes, *, top_k=1, gate_mode=No
                 if top_k == 1:
                     assert torch.equal(mapping.cpu().long(), ref["mapping"].view(-1)), f"rank {r}: scatter indices"
                 err = rel_l2(outs[r].float().cpu(), ref["out"])
-                moe_err = rel_l2(moes[r].float().cpu(), ref["moe"])
+                moe_err = rel_l2(moe_keep[r].float().cpu(), ref["moe"])
                 assert err <= BF16_REL_L2 and moe_err <= 2 * BF16_REL_L2, f"rank {r}: rel-L2 {err:.2e} / {moe_err:.2e}"
                 last.append((err, moe_err))
-        cur = outs
+        cur = [o.clone() for o in outs] if fold else outs
     for c in ctxs:
         c.close()
     return last
@@ -147,7 +156,27 @@ def test_ep_keep_expert_output(ops, ep_mod, synth, oracle):
 def test_ep_whole_layer_in_one_call(ops, ep_mod, synth, oracle, S):
     """stages = 7, the call a multi-process rank makes: the dispatch kernel's last CTA itself waits for the arrival
     flags and builds the group table (no separate wait kernel).  With one rank every flag it waits for is its own."""
-    run_world(ops, ep_mod, synth, oracle, 1, [S], layers=2, stage_seq=(7,))
+    run_world(ops, ep_mod, synth, oracle, 1, [S], layers=2, stage_seq=(15,))
+
+
+@pytest.mark.parametrize("world,sizes", [(1, [3200]), (2, [50, 63]), (8, [400 + 7 * r for r in range(8)]),
+                                         (4, [0, 1, 700, 37])])
+def test_ep_folded_combine(ops, ep_mod, synth, oracle, world, sizes):
+    """Outputs inside the symmetric buffers + residual = x: the owners' second-GEMM epilogue writes the finished rows
+    residual + ff_scale * score * y into the source rank's `out`; no combine kernel runs."""
+    n0 = ops.launch_count()
+    run_world(ops, ep_mod, synth, oracle, world, sizes, layers=2, fold=True,
+              stage_seq=(15,) if world == 1 else (1, 8, 2, 4))
+    assert ops.launch_count() > n0
+
+
+def test_ep_folded_cfg4_shape(ops, ep_mod, synth, oracle):
+    g = torch.Generator().manual_seed(20260004)
+    frames = torch.randint(100, 1001, (256,), generator=g)
+    lens = (((frames - 1) // 2 - 1) // 2).to(torch.int32)
+    x_lens = [lens[32 * r:32 * (r + 1)].contiguous() for r in range(8)]
+    sizes = [32 * int(t.max()) for t in x_lens]
+    run_world(ops, ep_mod, synth, oracle, 8, sizes, x_lens=x_lens, random_bias=False, fold=True)
 
 
 def test_ep_stalled_peer_poisons_the_output(ops, ep_mod, synth):
@@ -164,7 +193,7 @@ def test_ep_stalled_peer_poisons_the_output(ops, ep_mod, synth):
     mine = ops.PackedExperts(full.W1[:El].contiguous(), full.b1[:El].contiguous(), full.W2[:El].contiguous(),
                              full.b2[:El].contiguous())
     out = torch.zeros_like(xd)
-    for stage in (1, 2, 4):   # rank 0 alone: rank 1 neither sends its rows nor returns rank 0's
+    for stage in (1, 8, 2, 4):   # rank 0 alone: rank 1 sends neither counts nor rows and returns nothing
         ctxs[0].forward(xd, ed, Wr, None, mine, residual=xd, ff_scale=0.5, out=out, Wr_packed=ops.pack_router(Wr),
                         stages=stage)
     torch.cuda.synchronize()
