@@ -731,13 +731,14 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
   const bool one_call = (stages & 11) == 11;   // gate, scatter and the expert kernel in this call
   const bool route = one_call && tc_gate && route_supported(S, a->D, Demb, a->E, a->top_k, a->dtype);
   void* drop_out = fold ? a->out : nullptr;     // padded / dropped tokens: output row = residual row, written locally
+  const int ffn_ctas = ffn_grid_ctas(bn, gmax, a->D, a->H, false);  // announced with the counts (see EpLayout)
   if (route) {
     StageScope t(0, stream);
     e = launch_route(a->x, a->embed, ln_in ? ln_in->packed : a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb,
                      a->E, a->gate_mode, a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out,
                      w.xbuf, drop_out, a->residual, stream, &ep, true, ln_in ? ln_in->gamma : nullptr,
                      ln_in ? ln_in->beta : nullptr, ln_in ? ln_in->eps : 0.0f,
-                     ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr, mode);
+                     ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr, mode, ffn_ctas);
     if (e != cudaSuccess) return cuda_fail(e, "ep_forward/route");
   } else {
     if (S > 0 && (stages & 1)) {
@@ -755,13 +756,15 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
     if ((stages & 9) == 9) {          // counts + scatter in one kernel
       StageScope t(1, stream);
       e = launch_dispatch(a->x, idx, dscore, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
-                          a->mapping_out, w.xbuf, drop_out, a->residual, hist, stream, &ep, one_call, false, mode, 0);
+                          a->mapping_out, w.xbuf, drop_out, a->residual, hist, stream, &ep, one_call, false, mode, 0,
+                          ffn_ctas);
     } else if (stages & 1) {          // staged: the counts alone ...
       e = launch_dispatch(a->x, idx, dscore, S, a->D, E_total, a->top_k, a->dtype, bn, w, nullptr, nullptr, nullptr,
-                          w.xbuf, nullptr, nullptr, hist, stream, &ep, false, false, mode, 1);
+                          w.xbuf, nullptr, nullptr, hist, stream, &ep, false, false, mode, 1, ffn_ctas);
     } else if (stages & 8) {          // ... then the scatter, once every rank's counts are on their way
       e = launch_dispatch(a->x, idx, dscore, S, a->D, E_total, a->top_k, a->dtype, bn, w, a->counts_out, nullptr,
-                          a->mapping_out, w.xbuf, drop_out, a->residual, hist, stream, &ep, false, false, mode, 2);
+                          a->mapping_out, w.xbuf, drop_out, a->residual, hist, stream, &ep, false, false, mode, 2,
+                          ffn_ctas);
     }
     if (e != cudaSuccess) return cuda_fail(e, "ep_forward/dispatch");
   }

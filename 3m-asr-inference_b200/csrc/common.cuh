@@ -37,28 +37,34 @@ constexpr int kMaxEpWorld = 8;
 // Byte offsets inside the symmetric buffer every rank allocates (identical on all ranks).
 //
 // Protocol of one layer call `seq` on rank r (W ranks, E_local experts per rank, E = W * E_local):
-//   1. gate -> r's per-expert counts for ALL E experts.  One CTA stores them into cnt_all[seq & 1][r][:] of EVERY rank and
-//      raises cnt_flag[r] = seq there (st.release.sys).
-//   2. every CTA of the dispatch / route kernel waits for all W count flags (local memory) and derives, for each expert,
+//   1. gate -> r's per-expert counts for ALL E experts.  One CTA stores them into cnt_all[r][:] of EVERY rank, each as a
+//      self-validating word (seq << 32 | count).
+//   2. every CTA of the dispatch / route kernel waits until all W x E words carry `seq` (local memory) and derives, for each expert,
 //      the row of the OWNER's receive buffer where r's first row for that expert belongs: the owner's rows are laid out
 //      expert-major, source-rank-major inside an expert, stable inside a source -- i.e. every local expert's rows are
 //      CONTIGUOUS whatever rank they came from, so the expert kernel runs full token tiles per expert instead of one
 //      tile per (expert, source) (functions.py:37-50's count exchange, without the host).
-//   3. rows -> recv_x[row] and 8 bytes of routing data -> meta[row] on the owner; every CTA fence.acq_rel.sys; the last
-//      CTA raises disp_flag[r] = seq on every rank ("r's rows have landed").
-//   4. owner: expert FFN over recv_x.  The second GEMM's epilogue sends each row where meta says: either (fold) the
-//      finished layer output  residual + ff_scale * score * y  straight into the source rank's `out` row, or the bare y
-//      row into the source's ret_y for ep_combine.  Last CTA raises ret_flag[owner] = seq on every rank.
-//   5. source: waits for all W ret_flags (ep_wait_done_kernel in front of whatever consumes `out`, or ep_combine).
-// Flags carry the layer sequence number and are never reset.  One receive buffer suffices: r pushes layer L+1 only after
-// it has seen every owner's ret_flag of layer L, which an owner raises after its last read of recv_x / meta / cnt_all.
+//   3. rows -> recv_x[row] and 8 bytes of routing data -> meta[row] on the owner; every CTA: fence.acq_rel.sys, then one
+//      remote increment of arrive[r] on every rank ("one more CTA of r has delivered").  How many CTAs there will have been
+//      after this call travels with the counts (cumulative, never reset), so nobody has to be the last.
+//   4. owner: expert FFN over recv_x.  Its producer streams the first weight tiles at once and waits for the arrival
+//      counters only before it touches the rows.  The second GEMM's epilogue sends each row where meta says: either
+//      (fold) the finished layer output  residual + ff_scale * score * y  straight into the source rank's `out` row, or
+//      the bare y row into the source's ret_y for ep_combine.  Every CTA: fence.acq_rel.sys, then one remote increment of
+//      done[owner] on every rank.
+//   5. source: waits until every owner's done counter has reached what that owner announced (ep_wait_done_kernel in front
+//      of whatever consumes `out`, or ep_combine).
+// Counters and sequence numbers only ever grow.  One receive buffer suffices: r pushes layer L+1 only after it has seen
+// every owner finish layer L, i.e. after the owner's last read of recv_x / meta / cnt_all.
 struct EpLayout {
-  size_t ctrl;       // int32[16]: [0] seq (layer calls so far), [1] dispatch CTAs done, [2] FFN CTAs done, [3] error,
-                     //            [4] mode bits of the current call (bit 0 fold, bit 1 residual)
-  size_t cnt_flag;   // int32[kMaxEpWorld]: cnt_flag[s] = seq of the last call whose counts from rank s have landed
-  size_t disp_flag;  // int32[kMaxEpWorld]: disp_flag[s] = seq of the last dispatch whose rows from rank s have landed
-  size_t ret_flag;   // int32[kMaxEpWorld]: ret_flag[o] = seq of the last layer whose results from owner rank o landed
-  size_t cnt_all;    // int32[2][kMaxEpWorld][E + 1]: [seq & 1][s][e] rows rank s routes to global expert e; [E] = mode bits
+  size_t ctrl;       // int32[64], local bookkeeping: [0] seq (layer calls so far), [1] dispatch CTAs done (this call),
+                     //   [3] error, [5] / [6] cumulative dispatch / FFN CTAs this rank has announced,
+                     //   [16 + s] arrive[s] to wait for in this call, [32 + o] done[o] to wait for in this call
+  size_t arrive;     // int32[kMaxEpWorld]: arrive[s] = CTAs of rank s's dispatch kernels that have delivered (cumulative)
+  size_t done;       // int32[kMaxEpWorld]: done[o] = CTAs of owner o's expert kernels that have delivered (cumulative)
+  size_t cnt_all;    // uint64[kMaxEpWorld][E + 3]: [s][e] = (seq << 32) | rows rank s routes to global expert e in call seq;
+                     //   [s][E] mode bits, [s][E + 1] / [s][E + 2] the arrive / done counts rank s will have reached after
+                     //   this call.  Self-validating words: no flag, no fence behind them
   size_t meta;       // int2 [world * cap]: per received row {residual? << 31 | source rank << 27 | index at the source,
                      //   gate score bits}; index = the token (fold) or the source's expert-order row (ret_y + ep_combine)
   size_t recv_x;     // bf16 [world * cap][D]: received rows, expert-major / source-major / stable
@@ -69,6 +75,8 @@ struct EpLayout {
 };
 
 constexpr int kEpModeFold = 1, kEpModeResidual = 2;
+constexpr int kEpCntExtra = 3;                       // words behind the E counts of a count message
+constexpr int kEpCtrlArrive = 16, kEpCtrlDone = 32;  // ctrl[] slots of the counter values to wait for
 constexpr int kEpMetaRankShift = 27;
 constexpr int kEpMetaIndexMask = (1 << kEpMetaRankShift) - 1;
 constexpr int kEpMetaRankMask = 0xF;
@@ -86,11 +94,10 @@ inline EpLayout ep_layout(int world, int E_local, int D, int cap) {
     return o;
   };
   const size_t E = static_cast<size_t>(world) * E_local;
-  l.ctrl = take(sizeof(int) * 16);
-  l.cnt_flag = take(sizeof(int) * kMaxEpWorld);
-  l.disp_flag = take(sizeof(int) * kMaxEpWorld);
-  l.ret_flag = take(sizeof(int) * kMaxEpWorld);
-  l.cnt_all = take(sizeof(int) * 2 * kMaxEpWorld * (E + 1));
+  l.ctrl = take(sizeof(int) * 64);
+  l.arrive = take(sizeof(int) * kMaxEpWorld);
+  l.done = take(sizeof(int) * kMaxEpWorld);
+  l.cnt_all = take(sizeof(unsigned long long) * kMaxEpWorld * (E + kEpCntExtra));
   l.meta = take(sizeof(int) * 2 * static_cast<size_t>(world) * cap);
   l.recv_x = take(sizeof(bf16) * static_cast<size_t>(world) * cap * D);
   l.ret_y = take(sizeof(bf16) * static_cast<size_t>(cap) * D);
@@ -188,7 +195,8 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
                             const int* hist32, cudaStream_t stream, const EpPeers* ep = nullptr,
-                            bool ep_fold_wait = false, bool xbuf_f32 = false, int ep_mode = 0, int ep_phase = 0);
+                            bool ep_fold_wait = false, bool xbuf_f32 = false, int ep_mode = 0, int ep_phase = 0,
+                            int ep_ffn_ctas = 0);
 constexpr int kMaxHistRows = 512;  // above this many 32-token rows the scatter CTAs would re-read too much
 // Builds only the group table (+ zeroes the flags) from an existing offsets array.
 cudaError_t launch_build_groups(const int* offsets, int E, int bn, GroupRec* groups, int* n_groups, int* h_ready,
@@ -206,7 +214,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream,
                          const EpPeers* ep = nullptr, bool ep_fold_wait = false, const float* ln_gamma = nullptr,
                          const float* ln_beta = nullptr, float ln_eps = 0.0f, const float* ln_c = nullptr,
-                         int ep_mode = 0);
+                         int ep_mode = 0, int ep_ffn_ctas = 0);
 // Router packed for the route kernel's fused norm_ff: like launch_pack_router, with the x rows (k >= R - D) scaled by
 // gamma, followed by c1[32] = gamma^T Wr_x and c0[32] = beta^T Wr_x (fp32).  router_ln_pack_bytes(R) bytes.
 size_t router_ln_pack_bytes(int R);
@@ -243,6 +251,8 @@ struct FfnLaunch {
   int tf32;           // 1: xbuf, W1, W2 and hbuf hold fp32 (the pointers above are reinterpreted), TF32 tensor-core math
 };
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
+// Grid the expert kernel will be launched with (expert parallelism announces it ahead of the launch).
+int ffn_grid_ctas(int bn, int gmax, int D, int H, bool tf32);
 // Debug timeline: every following ffn launch records per-CTA events into dev_buf (16 B records); null disables.
 void set_ffn_trace(void* dev_buf, int records_per_cta);
 

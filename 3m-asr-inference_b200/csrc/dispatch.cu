@@ -108,7 +108,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
                         float* __restrict__ row_score, bf16* __restrict__ xbuf, GroupRec* groups, int* n_groups,
                         int* h_ready, int* counts_out, int* offsets_out, int* mapping_out, InT* __restrict__ drop_out,
                         const InT* __restrict__ drop_residual, int early_trigger, const EpPeers ep,
-                        int ep_fold_wait, int ep_mode, int ep_send) {
+                        int ep_fold_wait, int ep_mode, int ep_send, int ep_ffn_ctas) {
   constexpr int kWarps = kDispatchThreads / 32;
   constexpr int kRowsPerBatch = 4;            // rows a warp keeps in flight during the copy
   constexpr int kMaxParts = 8;
@@ -123,8 +123,8 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   int* s_wcnt = s_dst + kDispatchThreads;     // [kWarps][E] per-warp counts of the current segment
   int* s_part = s_wcnt + kWarps * E;          // [nparts][2][E] partial column sums (before / total)
   int* s_exp = s_part + kMaxParts * 2 * E;    // [kDispatchThreads] expert of each entry of the segment (kEp)
-  int* s_cnt = s_exp + kDispatchThreads;      // [world][E + 1] every rank's counts (kEp)
-  int* s_base = s_cnt + kMaxEpWorld * (E + 1);  // [E] owner row of this rank's first row per expert (kEp)
+  int* s_cnt = s_exp + kDispatchThreads;      // [world][E + kEpCntExtra] every rank's count message (kEp)
+  int* s_base = s_cnt + kMaxEpWorld * (E + kEpCntExtra);  // [E] owner row of this rank's first row per expert (kEp)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -180,7 +180,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   bool ep_ok = true;
   if (kEp) {
     ep_seq = ep_ctrl(ep)[0] + 1;   // (only this kernel's last CTA advances the word, after every CTA has read it)
-    if (blockIdx.x == 0 && ep_send) ep_send_counts(ep, ep_seq, s_total, E, ep_mode);
+    if (blockIdx.x == 0 && ep_send) ep_send_counts(ep, ep_seq, s_total, E, ep_mode, gridDim.x, ep_ffn_ctas, s_dst);
     ep_ok = ep_wait_counts(ep, ep_seq, E, ep_mode, s_cnt, s_base);
   }
 
@@ -332,31 +332,18 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   }
 
   if (kEp) {
-    // Completion: every CTA makes its pushed rows visible system-wide, the last one tells the peers.
+    // step 3: this CTA's rows (and routing data) have landed -- fence, then one increment on every rank.  The expert
+    // kernels wait for the counters themselves, so nobody has to be the last CTA and nobody waits here.
     __syncthreads();
-    __shared__ int s_last;
-    int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
+    ep_signal(ep, ep.lay.arrive);
     if (threadIdx.x == 0) {
-      // (one NVLink round trip: the fence returns once this CTA's pushes have been performed at the peers)
-      ptx::fence_acq_rel_sys();
-      const int prev = atomicAdd(&ctrl[1], 1);
-      s_last = prev == static_cast<int>(gridDim.x) - 1;
-      // acquire side: every other CTA fenced its pushes system-wide before its increment, so observing the increments
-      // at gpu scope is enough to order them before the flags below
-      if (s_last) ptx::fence_acq_rel_gpu();
-    }
-    __syncthreads();
-    if (s_last) {
-      // step 3: this rank's rows (and routing data) have landed everywhere -- one thread per peer raises the flag
-      if (threadIdx.x == 0) {
+      // the sequence number advances once every CTA of this launch has read it (a later wave's CTA may start long
+      // after the first ones have finished)
+      int* ctrl = ep_ctrl(ep);
+      if (atomicAdd(&ctrl[1], 1) == static_cast<int>(gridDim.x) - 1) {
         ctrl[1] = 0;
         ctrl[0] = ep_seq;
-        ctrl[4] = ep_mode;
       }
-      if (threadIdx.x < ep.world)
-        ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, ep_seq);
-      // the same CTA waits for the peers' rows, so that the expert kernel behind this one can start on them at once
-      if (ep_fold_wait) ep_wait_rows(ep, ep_seq);
     }
   }
 }
@@ -364,7 +351,8 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
 // Expert parallelism driven stage by stage (tests that emulate several ranks on one GPU: a kernel must never wait for a
 // kernel that is queued behind it): the counts alone, from the chunk histograms, without the scatter.
 __global__ void __launch_bounds__(kDispatchThreads)
-dispatch_ep_counts_kernel(const int* __restrict__ chunk_hist, int hist_rows, int E, const EpPeers ep, int ep_mode) {
+dispatch_ep_counts_kernel(const int* __restrict__ chunk_hist, int hist_rows, int E, const EpPeers ep, int ep_mode,
+                          int push_ctas, int ffn_ctas) {
   extern __shared__ int s_dyn[];
   int* s_total = s_dyn;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
@@ -373,7 +361,7 @@ dispatch_ep_counts_kernel(const int* __restrict__ chunk_hist, int hist_rows, int
     s_total[e] = t;
   }
   __syncthreads();
-  ep_send_counts(ep, ep_ctrl(ep)[0] + 1, s_total, E, ep_mode);
+  ep_send_counts(ep, ep_ctrl(ep)[0] + 1, s_total, E, ep_mode, push_ctas, ffn_ctas, s_total + E);
 }
 
 __global__ void __launch_bounds__(256)
@@ -388,13 +376,16 @@ build_groups_kernel(const int* __restrict__ offsets, int E, int bn, GroupRec* gr
 
 }  // namespace
 
-// Token-tile width of the FFN kernel: the smallest of 32/64/128/256 that holds ~1.25x the mean tokens per expert,
-// so a balanced router gives one tile per expert and weights are streamed once.
+// Token-tile width of the FFN kernel: the smallest of 32/64/128/256 that holds ~1.25x the mean tokens per expert, so a
+// balanced router gives one tile per expert and weights are streamed once -- but 256 (CTA pairs) only when there are
+// rows enough for several waves of such tiles.  Below that the kernel is a latency chain (first GEMM -> h -> second GEMM
+// per group), a 256-token tile's K loops are twice as long and 74 pairs take half as many tiles at a time: at 3 200 rows
+// over 16 experts, 128-token tiles finish in about half the time of 256-token pair tiles.
 int choose_bn(int Sk, int E) {
   const long long need = (static_cast<long long>(Sk) * 5 + 4LL * E - 1) / (4LL * E);
   if (need <= 32) return 32;
   if (need <= 64) return 64;
-  if (need <= 128) return 128;
+  if (need <= 128 || Sk < 12288) return 128;
   return 256;
 }
 
@@ -402,7 +393,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
                             int dtype, int bn, const RouteWs& ws, int* counts_out, int* offsets_out,
                             int* mapping_out, bf16* xbuf, void* drop_out, const void* drop_residual,
                             const int* hist32, cudaStream_t stream, const EpPeers* ep, bool ep_fold_wait,
-                            bool xbuf_f32, int ep_mode, int ep_phase) {
+                            bool xbuf_f32, int ep_mode, int ep_phase, int ep_ffn_ctas) {
   if (xbuf_f32 && (dtype != B200MOE_F32 || ep != nullptr || D % 4 != 0)) return cudaErrorInvalidValue;
   const int Sk = S * top_k;
   if (top_k != 1) drop_out = nullptr;  // (expert parallelism: only the folded path passes one)
@@ -436,13 +427,14 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
   }
   const int nparts_max = 8;
   const size_t dyn = sizeof(int) * (2 * E + 2 * (E + 1) + kDispatchThreads + (kDispatchThreads / 32) * E +
-                                    nparts_max * 2 * E + kDispatchThreads + kMaxEpWorld * (E + 1) + E);
+                                    nparts_max * 2 * E + kDispatchThreads + kMaxEpWorld * (E + kEpCntExtra) + E);
   cudaError_t lerr = cudaSuccess;
   EpPeers epv{};
   if (ep) epv = *ep;
   if (ep != nullptr && ep_phase == 1) {
     // counts only (ranks emulated on one GPU are driven phase by phase: nobody may wait for a kernel queued behind it)
-    dispatch_ep_counts_kernel<<<1, kDispatchThreads, sizeof(int) * E, stream>>>(hist, hist_rows, E, epv, ep_mode);
+    dispatch_ep_counts_kernel<<<1, kDispatchThreads, sizeof(int) * (E + 2), stream>>>(hist, hist_rows, E, epv, ep_mode,
+                                                                                     ck.nchunks, ep_ffn_ctas);
     count_launch();
     return cudaGetLastError();
   }
@@ -454,7 +446,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
       rows_per_chunk, bn, gmax,                                                                                   \
       ws.counts, ws.offsets, ws.mapping, ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready,          \
       counts_out, offsets_out, mapping_out, static_cast<T*>(drop_out), static_cast<const T*>(drop_residual),      \
-      (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, ep_fold_wait ? 1 : 0, ep_mode, ep_send)
+      (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, ep_fold_wait ? 1 : 0, ep_mode, ep_send, ep_ffn_ctas)
 #define B200MOE_SCATTER(T)          \
   if (ep)                           \
     B200MOE_SCATTER_K(T, true);     \
@@ -468,7 +460,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
                              ck.nchunks, hist, hist_rows, rows_per_chunk, bn, gmax, ws.counts, ws.offsets, ws.mapping,
                              ws.pos, ws.row_score, xbuf, ws.groups, ws.n_groups, ws.h_ready, counts_out, offsets_out,
                              mapping_out, static_cast<float*>(drop_out), static_cast<const float*>(drop_residual),
-                             (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, 0, 0, 0);
+                             (pdl_trigger() & kPdlDispatch) ? 1 : 0, epv, 0, 0, 0, 0);
         break;
       }
       B200MOE_SCATTER(float);

@@ -23,28 +23,22 @@ namespace b200moe {
 
 namespace {
 
-// Staged drivers only (the one-call path folds this wait into the dispatch / route kernel's last CTA).
+// Staged drivers only (in the one-call path the expert kernel's producer does this wait itself).
 __global__ void __launch_bounds__(32) ep_wait_rows_kernel(const EpPeers ep) {
-  const int seq = ep_ctrl(ep)[0];  // set by this rank's own dispatch kernel, which precedes this kernel in the stream
-  ep_wait_rows(ep, seq);
+  ep_wait_counters(ep, ep.lay.arrive, kEpCtrlArrive, kEpErrDispatchTimeout);
 }
 
 // Folded path (the owners write finished output rows into this rank's `out`): whatever consumes `out` next -- the next
-// layer's gate, a copy to the host -- is ordered behind this one-CTA kernel, which returns once every owner has raised
-// its "rows are back" flag for the current layer call.  A missing peer poisons `out` (NaN) and leaves the status word.
+// layer's gate, a copy to the host -- is ordered behind this one-CTA kernel, which returns once every owner's done
+// counter has reached what it announced for the current layer call.  A missing peer poisons `out` (NaN) and leaves the
+// status word.
 __global__ void __launch_bounds__(256)
 ep_wait_done_kernel(const EpPeers ep, bf16* __restrict__ out, size_t n8) {
   ptx::pdl_launch_dependents();  // the next layer's route kernel may set itself up (it touches constants only until its wait)
-  ptx::pdl_wait();               // this rank's own expert kernel (and through it the dispatch that set seq) has completed
-  int* ctrl = ep_ctrl(ep);
-  if (threadIdx.x < ep.world) {
-    const int seq = ctrl[0];
-    const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ret_flag);
-    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
-    if (!ep_wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kEpErrReturnTimeout);
-  }
+  ptx::pdl_wait();               // this rank's own expert kernel (and through it the dispatch that set the targets) has completed
+  if (threadIdx.x < 32) ep_wait_counters(ep, ep.lay.done, kEpCtrlDone, kEpErrReturnTimeout);
   __syncthreads();
-  if (*reinterpret_cast<volatile int*>(&ctrl[3]) != 0 && out != nullptr) {
+  if (*reinterpret_cast<volatile int*>(&ep_ctrl(ep)[3]) != 0 && out != nullptr) {
     const uint4 nan8 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
     for (size_t i = threadIdx.x; i < n8; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = nan8;
   }
@@ -70,22 +64,17 @@ ep_combine_kernel(const EpPeers ep, const int* __restrict__ mapping, const float
   // Programmatic dependent launch, both ways.  (1) The next layer's route kernel may start now: it only touches
   // constants (embed, router) until its own griddepcontrol.wait, which returns when this grid has completed.  (2) This
   // kernel is itself launched early (the FFN kernel releases its dependents at its start) and does its own
-  // griddepcontrol.wait before it reads anything an earlier kernel wrote: seq, mapping and score come from this layer's
-  // route / dispatch kernel, whose stores are only guaranteed visible through the chain of completed grids (a stale seq
-  // would let the flag wait pass on the previous layer's flags).  This rank's own return flag is raised by the last CTA
-  // of the FFN grid, so the wait costs nothing the flags would not have cost.
+  // griddepcontrol.wait before it reads anything an earlier kernel wrote: the counter targets, mapping and score come
+  // from this layer's route / dispatch kernel, whose stores are only guaranteed visible through the chain of completed
+  // grids (a stale target would let the wait pass on the previous layer's counts).  This rank's own expert kernel is one
+  // of the owners waited for anyway, so the wait costs nothing the counters would not have cost.
   ptx::pdl_launch_dependents();
   // (kLn) gamma / beta are constants of the layer: fetched before the waits
   LnAffine<kVec> aff;
   if constexpr (kLn) aff.load(ln_gamma, ln_beta, D, threadIdx.x & 31);
   ptx::pdl_wait();
-  int* ctrl = reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl);
-  const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.ret_flag);
-  if (threadIdx.x < ep.world) {
-    const int seq = ctrl[0];
-    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
-    if (!ep_wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kEpErrReturnTimeout);
-  }
+  int* ctrl = ep_ctrl(ep);
+  if (threadIdx.x < 32) ep_wait_counters(ep, ep.lay.done, kEpCtrlDone, kEpErrReturnTimeout);
   __syncthreads();
   // A peer that never delivered (rows out or rows back): the layer's output is POISONED with NaNs rather than built
   // from stale rows, so that a stalled rank cannot pass for a result; ctrl[3] (b200moe_ep_status) says which wait failed.

@@ -56,36 +56,60 @@ __device__ __forceinline__ void build_groups_block(const int* offsets_sm, int E,
 }
 
 // Step 1 of the protocol.  Called by every thread of ONE CTA once s_total[E] (this rank's rows per global expert) is
-// complete and visible to the CTA: thread t < world stores the counts into rank t and raises the count flag there.
-__device__ __forceinline__ void ep_send_counts(const EpPeers& ep, int seq, const int* s_total, int E, int mode) {
-  const int t = threadIdx.x;
-  if (t < ep.world) {
-    int* dst = reinterpret_cast<int*>(ep.base[t] + ep.lay.cnt_all) + ((seq & 1) * kMaxEpWorld + ep.rank) * (E + 1);
-    for (int e = 0; e < E; ++e) dst[e] = s_total[e];
-    dst[E] = mode;
-    // release at system scope: the counts above (same thread) are performed at rank t before the flag is
-    ptx::st_release_sys(reinterpret_cast<int*>(ep.base[t] + ep.lay.cnt_flag) + ep.rank, seq);
+// complete and visible to the CTA.  push_ctas / ffn_ctas: how many CTAs of this rank will signal "delivered" in this call
+// (dispatch side) and "results delivered" (expert kernel); their running totals go out with the counts.  Every word
+// travels self-validating, (seq << 32) | value, stored straight into every rank: no flag and no release fence behind the
+// data (a system-scope release costs an NVLink round trip of its own), the receiver simply re-reads a word until it
+// carries this call's sequence number.  s_scr: two ints of shared memory.
+__device__ __forceinline__ void ep_send_counts(const EpPeers& ep, int seq, const int* s_total, int E, int mode,
+                                               int push_ctas, int ffn_ctas, int* s_scr) {
+  if (threadIdx.x == 0) {
+    int* ctrl = ep_ctrl(ep);
+    s_scr[0] = ctrl[5] = ctrl[5] + push_ctas;
+    s_scr[1] = ctrl[6] = ctrl[6] + ffn_ctas;
+  }
+  __syncthreads();
+  const int stride = E + kEpCntExtra;
+  const unsigned long long tag = static_cast<unsigned long long>(static_cast<unsigned>(seq)) << 32;
+  for (int i = threadIdx.x; i < ep.world * stride; i += blockDim.x) {
+    const int t = i / stride, e = i - t * stride;
+    unsigned long long* dst =
+        reinterpret_cast<unsigned long long*>(ep.base[t] + ep.lay.cnt_all) + static_cast<size_t>(ep.rank) * stride + e;
+    const int v = e < E ? s_total[e] : (e == E ? mode : s_scr[e - E - 1]);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(tag | static_cast<unsigned>(v)) : "memory");
   }
 }
 
 // Step 2.  Called by every thread of a CTA.  Waits for every rank's counts of call `seq`, copies the matrix into s_cnt
-// (world x (E + 1) ints) and derives s_base[e]: the row of the owner's receive buffer where THIS rank's first row for
-// global expert e belongs (owner rows: expert-major, source-major inside an expert).  Returns false when a peer did not
-// deliver or the ranks disagree on the mode: the caller then pushes nothing (the output is poisoned further down).
+// (world x (E + kEpCntExtra) ints) and derives s_base[e]: the row of the owner's receive buffer where THIS rank's first
+// row for global expert e belongs (owner rows: expert-major, source-major inside an expert).  Returns false when a peer
+// did not deliver or the ranks disagree on the mode: the caller then pushes nothing (the output is poisoned further down).
 __device__ __forceinline__ bool ep_wait_counts(const EpPeers& ep, int seq, int E, int mode, int* s_cnt, int* s_base) {
   int* ctrl = ep_ctrl(ep);
-  const int W = ep.world, El = ep.E_local, stride = E + 1;
-  if (static_cast<int>(threadIdx.x) < W) {
-    const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.cnt_flag);
+  const int W = ep.world, El = ep.E_local, stride = E + kEpCntExtra;
+  {
+    // (written by other GPUs during this kernel's lifetime: system-scope loads that bypass L1)
+    const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(ep.base[ep.rank] + ep.lay.cnt_all);
     const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
-    if (!ep_wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kEpErrCountTimeout);
+    bool gave_up = false;
+    for (int i = threadIdx.x; i < W * stride; i += blockDim.x) {
+      unsigned long long w;
+      while (true) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(cnt + i) : "memory");
+        if (static_cast<int>(w >> 32) == seq) break;
+        if (gave_up || ptx::globaltimer_ns() > deadline) {
+          gave_up = true;
+          w = 0;
+          break;
+        }
+        __nanosleep(40);
+      }
+      s_cnt[i] = static_cast<int>(w & 0xffffffffu);
+    }
+    if (gave_up) atomicExch(&ctrl[3], kEpErrCountTimeout);
   }
   __syncthreads();
   const bool failed = *reinterpret_cast<volatile int*>(&ctrl[3]) != 0;
-  // (written by other GPUs during this kernel's lifetime: L2-coherent loads, never the L1 / read-only path)
-  const int* cnt = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.cnt_all) + (seq & 1) * kMaxEpWorld * stride;
-  for (int i = threadIdx.x; i < W * stride; i += blockDim.x) s_cnt[i] = failed ? 0 : __ldcg(cnt + i);
-  __syncthreads();
   bool ok = !failed;
   if (ok)
     for (int s = 0; s < W; ++s) ok = ok && ((s_cnt[s * stride + E] ^ mode) & kEpModeFold) == 0;
@@ -96,18 +120,24 @@ __device__ __forceinline__ bool ep_wait_counts(const EpPeers& ep, int seq, int E
     for (int e2 = owner * El; e2 < e; ++e2)
       for (int s = 0; s < W; ++s) row += s_cnt[s * stride + e2];
     for (int s = 0; s < ep.rank; ++s) row += s_cnt[s * stride + e];
-    s_base[e] = row;
+    s_base[e] = ok ? row : 0;
   }
   __syncthreads();
   return ok;
 }
 
-// Owner side of step 2, one CTA (every thread calls it, after ep_wait_counts): the expert kernel's group table over the
-// merged rows of this rank's E_local experts.  s_off / s_scr: E_local + 1 ints of shared memory each.
+// Owner side of step 2, one CTA (every thread calls it, after ep_wait_counts): what this rank's expert kernel and its
+// consumers will wait for in this call (local bookkeeping), and the expert kernel's group table over the merged rows of
+// this rank's E_local experts.  s_off / s_scr: E_local + 1 ints of shared memory each.
 __device__ __forceinline__ void ep_build_groups_merged(const EpPeers& ep, int E, const int* s_cnt, bool ok, int bn,
                                                        GroupRec* groups, int* n_groups, int* h_ready, int gmax,
                                                        int* s_off, int* s_scr) {
-  const int W = ep.world, El = ep.E_local, stride = E + 1;
+  const int W = ep.world, El = ep.E_local, stride = E + kEpCntExtra;
+  if (static_cast<int>(threadIdx.x) < W && ok) {
+    int* ctrl = ep_ctrl(ep);
+    ctrl[kEpCtrlArrive + threadIdx.x] = s_cnt[threadIdx.x * stride + E + 1];
+    ctrl[kEpCtrlDone + threadIdx.x] = s_cnt[threadIdx.x * stride + E + 2];
+  }
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int e = 0; e < El; ++e) {
@@ -122,14 +152,75 @@ __device__ __forceinline__ void ep_build_groups_merged(const EpPeers& ep, int E,
   build_groups_block(s_off, El, bn, groups, n_groups, h_ready, gmax, s_scr);
 }
 
-// Step 3, receiving side: wait until every rank's rows of call `seq` have landed.  Threads [0, world) of one CTA.
-__device__ __forceinline__ void ep_wait_rows(const EpPeers& ep, int seq) {
-  if (static_cast<int>(threadIdx.x) < ep.world) {
-    int* ctrl = ep_ctrl(ep);
-    const int* flags = reinterpret_cast<const int*>(ep.base[ep.rank] + ep.lay.disp_flag);
-    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
-    if (!ep_wait_flag_sys(flags + threadIdx.x, seq, deadline)) atomicExch(&ctrl[3], kEpErrDispatchTimeout);
+// Step 3, sending side.  Every CTA of the dispatch / route kernel, after a __syncthreads behind its last row store: the
+// fence returns once this CTA's pushes have been performed at the peers (one NVLink round trip), then every rank's
+// arrive[my rank] goes up by one.  Relaxed increments: the fence in front of them is what orders the rows.
+__device__ __forceinline__ void ep_signal(const EpPeers& ep, size_t counters_off) {
+  if (threadIdx.x == 0) {
+    ptx::fence_acq_rel_sys();
+    for (int t = 0; t < ep.world; ++t) {
+      int* c = reinterpret_cast<int*>(ep.base[t] + counters_off) + ep.rank;
+      asm volatile("red.relaxed.sys.global.add.s32 [%0], 1;" ::"l"(c) : "memory");
+    }
   }
+}
+
+// Waits until every rank's counter has reached the value announced for this call (ctrl[slot + s], written by this rank's
+// own dispatch kernel).  Lanes [0, world) of one warp call it; the loads are relaxed and overlap, one acquire fence
+// behind them orders everything that follows.  Returns false (and raises the status word) on a timeout.
+__device__ __forceinline__ bool ep_wait_counters(const EpPeers& ep, size_t counters_off, int slot, int err) {
+  int* ctrl = ep_ctrl(ep);
+  bool ok = true;
+  const int s = threadIdx.x & 31;
+  if (s < ep.world) {
+    const int want = *reinterpret_cast<volatile int*>(&ctrl[slot + s]);
+    const int* c = reinterpret_cast<const int*>(ep.base[ep.rank] + counters_off) + s;
+    const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
+    while (true) {
+      int v;
+      asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+      if (v - want >= 0) break;
+      if (ptx::globaltimer_ns() > deadline) {
+        atomicExch(&ctrl[3], err);
+        ok = false;
+        break;
+      }
+      __nanosleep(40);
+    }
+    ptx::fence_acq_rel_sys();
+  }
+  return ok;
+}
+
+// The same wait by ONE thread (the expert kernel's TMA producer): all counters are read together each round.
+__device__ __forceinline__ bool ep_wait_counters_1t(const EpPeers& ep, size_t counters_off, int slot, int err) {
+  int* ctrl = ep_ctrl(ep);
+  const int* c = reinterpret_cast<const int*>(ep.base[ep.rank] + counters_off);
+  int want[kMaxEpWorld];
+#pragma unroll
+  for (int s = 0; s < kMaxEpWorld; ++s) want[s] = s < ep.world ? *reinterpret_cast<volatile int*>(&ctrl[slot + s]) : 0;
+  const unsigned long long deadline = ptx::globaltimer_ns() + 1000000ull * static_cast<unsigned>(ep.timeout_ms);
+  bool ok = true;
+  while (true) {
+    int v[kMaxEpWorld];
+#pragma unroll
+    for (int s = 0; s < kMaxEpWorld; ++s) {
+      v[s] = want[s];
+      if (s < ep.world) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v[s]) : "l"(c + s) : "memory");
+    }
+    bool all = true;
+#pragma unroll
+    for (int s = 0; s < kMaxEpWorld; ++s) all = all && (v[s] - want[s] >= 0);
+    if (all) break;
+    if (ptx::globaltimer_ns() > deadline) {
+      atomicExch(&ctrl[3], err);
+      ok = false;
+      break;
+    }
+    __nanosleep(40);
+  }
+  ptx::fence_acq_rel_sys();
+  return ok;
 }
 
 }  // namespace b200moe

@@ -28,6 +28,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "ep_device.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
 
@@ -75,8 +76,7 @@ struct FfnParams {
                                     //    into the source rank's `out`; 0: the bare y row into the source's ret_y
   const int2* ep_meta;              // per received row: {source rank << 27 | row index at the source, gate score bits}
   uint8_t* ep_out[kMaxEpWorld];     // where rank r's rows go: its `out` buffer (fold) or its ret_y
-  int* ep_ret_flag[kMaxEpWorld];    // &ret_flag[my rank] in every rank's buffer
-  int* ep_ctrl;                     // local control block
+  EpPeers ep_peers;                 // (arrival / done counters live in the symmetric buffers)
   int* clear_ptr;   // zeroed at kernel start, spread over the CTAs (tagged histogram words of the route kernel)
   int clear_ints;
   int dbg;          // timing experiments only (B200MOE_DBG): 1 = no phase-2 stores, 2 = no phase-1 stores, 4 = no residual,
@@ -455,6 +455,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       Tracer<kTrace> tr(p, 0);
       tr.sync();
       tr.rec(-1, kEvKernelStart);
+      // expert parallelism: the token rows may still be landing (the peers' dispatch kernels push them); the first
+      // weight tiles are requested at once, the rows only when every rank's arrival counter says they are there
+      bool rows_ready = !p.ep;
       for (int t = tile0; t < n_tiles; t += tile_step) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
         const GroupRec gr = (t == tile0 && tl.g == g_first) ? gr_first : p.groups[tl.g];
@@ -470,7 +473,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         const bool skip_b = (tl.phase == 1 && (p.dbg & 8)) || (tl.phase == 2 && (p.dbg & 16));
         const uint32_t st_bytes = skip_b ? a_stage_bytes * kCtas : tx_bytes;
         const bool dep_pending =
-            tl.phase == 2 && !(p.dbg & 32) && ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags;
+            (tl.phase == 2 && !(p.dbg & 32) && ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) ||
+            (tl.phase == 1 && !rows_ready);
         if (tl.phase == 2 && !dep_pending) ptx::fence_proxy_async_all();  // h was written through the generic proxy
         if (dep_pending) {
           // The W2 tiles do not depend on h: fill the ring with them first, then wait until every phase-1 tile of this
@@ -488,8 +492,13 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
               phase ^= 1u;
             }
           }
-          while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) __nanosleep(32);
-          ptx::fence_proxy_async_all();  // generic-proxy writes of h -> async-proxy (TMA) reads
+          if (tl.phase == 2) {
+            while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) __nanosleep(32);
+          } else {
+            ep_wait_counters_1t(p.ep_peers, p.ep_peers.lay.arrive, kEpCtrlArrive, kEpErrDispatchTimeout);
+            rows_ready = true;
+          }
+          ptx::fence_proxy_async_all();  // generic-proxy writes of h / of the pushed rows -> async-proxy (TMA) reads
           int s2 = stage0;
           for (int kb = 0; kb < pre; ++kb) {
             if (!skip_b) load(smem_b + s2 * b_stage_bytes, tm_b, s2, kb, b_row, ptx::kEvictLast);
@@ -531,6 +540,11 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         ptx::tc_fence_after();
         tr.rec(t, kEvMmaAccFree);
         const uint32_t tmem_d = tmem_base + as * kAccStride;
+        if ((p.dbg & 128) && t == tile0) {
+          // experiment: let every stage of the ring land before the first MMA (does the first stage's slowness come from
+          // the TMA writes that are still streaming into shared memory?)
+          for (int s2 = 1; s2 < stages && s2 < nkb; ++s2) ptx::mbar_wait(full_bar(s2), 0);
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
@@ -934,28 +948,18 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     else ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
   if (p.ep) {
-    // Every store of this CTA into the peers' return buffers precedes the barrier above.  The last CTA of the grid to
-    // get here tells every source rank that its rows are back (functions.py:185-191's all-to-all, without the host).
-    // One thread per peer raises the flag: a single thread would serialise `world` NVLink round trips (each release
-    // waits for the previous flag's acknowledgement), which is what made this tail grow with the number of GPUs.
-    int* s_ep_last = s_tok;  // (the epilogue's routing table is free after the barrier above; no static smem here)
+    // Every store of this CTA into the peers' buffers precedes the barrier above: fence (one NVLink round trip), then one
+    // increment of done[my rank] on every rank (functions.py:185-191's all-to-all, without the host and without a last
+    // CTA: how many CTAs there are went out with the counts).
     if (threadIdx.x == 0) {
       Tracer<kTrace> tr(p, 3, 4);
       tr.rec(-2, kEvEpiChunkLd);
-      ptx::fence_acq_rel_sys();
-      tr.rec(-2, kEvEpiChunkStaged);
-      const int prev = atomicAdd(&p.ep_ctrl[2], 1);
-      tr.rec(-2, kEvEpiChunkDone);
-      const int last = prev == static_cast<int>(gridDim.x) - 1;
-      if (last) {
-        ptx::fence_acq_rel_gpu();  // the other CTAs' system-wide fences precede their increments
-        p.ep_ctrl[2] = 0;
-      }
-      *s_ep_last = last;
     }
-    __syncthreads();
-    if (*s_ep_last && static_cast<int>(threadIdx.x) < p.ep_world)
-      ptx::st_release_sys(p.ep_ret_flag[threadIdx.x], p.ep_ctrl[0]);
+    ep_signal(p.ep_peers, p.ep_peers.lay.done);
+    if (threadIdx.x == 0) {
+      Tracer<kTrace> tr(p, 3, 3);
+      tr.rec(-2, kEvEpiChunkStaged);
+    }
   }
 }
 
@@ -976,6 +980,27 @@ size_t smem_bytes_for(int b_rows, int kps, int stages) {
          2 * kStagingBytes + 2 * 256 * 4;
 }
 
+int grid_for(int gmax, int D, int H, int ctas) {
+  const int m1 = H / (kBlockM * ctas), m2 = D / (kBlockM * ctas);
+  long long tiles_ub = static_cast<long long>(gmax) * (m1 + m2) * ctas;  // in CTAs
+  int grid = num_sms();
+  if (tiles_ub < grid) grid = static_cast<int>(tiles_ub);
+  if (ctas == 2) grid &= ~1;  // whole pairs
+  if (grid < ctas) grid = ctas;
+  return grid;
+}
+
+// CTA pairs for the compute-bound regime: full 256-token tiles and an even number of 128-row blocks per GEMM
+bool use_pairs(int bn, int D, int H, bool tf32) {
+  static const int pair_env = [] {
+    const char* v = std::getenv("B200MOE_PAIR");
+    return (v && *v) ? std::atoi(v) : 1;
+  }();
+  // (B200MOE_PAIR=2, experiments: pairs for 128-token tiles as well)
+  return !tf32 && pair_env != 0 && (bn == 256 || (pair_env == 2 && bn == 128)) && (H / kBlockM) % 2 == 0 &&
+         (D / kBlockM) % 2 == 0;
+}
+
 template <typename OutT, int kCtas, bool kTf32 = false>
 cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
                          const CUtensorMap& th, const FfnParams& p, cudaStream_t stream) {
@@ -990,12 +1015,7 @@ cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUten
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int m1 = a.H / (kBlockM * kCtas), m2 = a.D / (kBlockM * kCtas);
-  long long tiles_ub = static_cast<long long>(a.gmax) * (m1 + m2) * kCtas;  // in CTAs
-  int grid = num_sms();
-  if (tiles_ub < grid) grid = static_cast<int>(tiles_ub);
-  if (kCtas == 2) grid &= ~1;  // whole pairs
-  if (grid < kCtas) grid = kCtas;
+  const int grid = grid_for(a.gmax, a.D, a.H, kCtas);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -1033,19 +1053,18 @@ void set_ffn_trace(void* dev_buf, int records_per_cta) {
   g_trace_cap = records_per_cta;
 }
 
+int ffn_grid_ctas(int bn, int gmax, int D, int H, bool tf32) {
+  return grid_for(gmax > 0 ? gmax : 1, D, H, use_pairs(bn, D, H, tf32) ? 2 : 1);
+}
+
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   if (a.n_rows <= 0) return cudaSuccess;
   if (a.D % kBlockM != 0 || a.H % kBlockM != 0) return cudaErrorInvalidValue;
   if (a.bn % 16 != 0 || a.bn < 16 || a.bn > 256) return cudaErrorInvalidValue;
   if (a.fused && a.top_k != 1) return cudaErrorInvalidValue;
-  // CTA pairs for the compute-bound regime: full 256-token tiles and an even number of 128-row blocks per GEMM
-  static const int pair_env = [] {
-    const char* v = std::getenv("B200MOE_PAIR");
-    return (v && *v) ? std::atoi(v) : 1;
-  }();
   const bool tf32 = a.tf32 != 0;
   if (tf32 && (a.out_dtype != B200MOE_F32 || a.ep != nullptr)) return cudaErrorInvalidValue;
-  const bool pair = !tf32 && pair_env != 0 && a.bn == 256 && (a.H / kBlockM) % 2 == 0 && (a.D / kBlockM) % 2 == 0;
+  const bool pair = use_pairs(a.bn, a.D, a.H, tf32);
   const int ctas = pair ? 2 : 1;
   // two k-blocks per pipeline stage (one TMA instruction per operand and stage) wherever that still leaves >= 3 stages
   static const int kps_env = [] {
@@ -1072,11 +1091,8 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   FfnParams p;
   p.ep = 0;
   p.ep_world = p.ep_rank = 0;
-  p.ep_ctrl = nullptr;
-  for (int r = 0; r < kMaxEpWorld; ++r) {
-    p.ep_out[r] = nullptr;
-    p.ep_ret_flag[r] = nullptr;
-  }
+  p.ep_peers = EpPeers{};
+  for (int r = 0; r < kMaxEpWorld; ++r) p.ep_out[r] = nullptr;
   p.ep_fold = 0;
   p.ep_meta = nullptr;
   if (a.ep != nullptr) {
@@ -1084,14 +1100,11 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
     p.ep = 1;
     p.ep_world = a.ep->world;
     p.ep_rank = a.ep->rank;
+    p.ep_peers = *a.ep;
     p.ep_fold = a.ep_fold ? 1 : 0;
     p.ep_meta = reinterpret_cast<const int2*>(a.ep->base[a.ep->rank] + a.ep->lay.meta);
-    p.ep_ctrl = reinterpret_cast<int*>(a.ep->base[a.ep->rank] + a.ep->lay.ctrl);
-    for (int r = 0; r < a.ep->world; ++r) {
-      // fold: the same offset inside every rank's symmetric buffer as this rank's own `out` (symmetric allocation)
-      p.ep_out[r] = a.ep->base[r] + (a.ep_fold ? a.ep_out_off : a.ep->lay.ret_y);
-      p.ep_ret_flag[r] = reinterpret_cast<int*>(a.ep->base[r] + a.ep->lay.ret_flag) + a.ep->rank;
-    }
+    // fold: the same offset inside every rank's symmetric buffer as this rank's own `out` (symmetric allocation)
+    for (int r = 0; r < a.ep->world; ++r) p.ep_out[r] = a.ep->base[r] + (a.ep_fold ? a.ep_out_off : a.ep->lay.ret_y);
   }
   p.clear_ptr = a.clear_ptr;
   p.clear_ints = a.clear_ptr ? a.clear_ints : 0;

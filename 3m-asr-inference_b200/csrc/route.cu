@@ -178,6 +178,7 @@ struct RouteParams {
   unsigned long long tag;  // 56 random bits (<< 8) drawn per launch: what makes a histogram word this launch's
   int ep_fold_wait;
   int ep_mode;   // kEpModeFold / kEpModeResidual bits of this call (checked against the peers')
+  int ep_ffn_ctas;  // grid of the expert kernel that follows (announced with the counts)
   // norm_ff fused into the router (block call, route_kernel<.., kLn = true>); null = off
   const float* ln_gamma;
   const float* ln_beta;
@@ -613,12 +614,12 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   // each expert, every CTA waits for all ranks' counts and learns where its rows belong in the owners' receive buffers.
   // s_part is free again: [0, W * (E + 1)) count matrix, then s_base[E], then scratch for the group table.
   int* s_cnt = s_part;
-  int* s_base = s_part + kMaxEpWorld * 33;
+  int* s_base = s_part + kMaxEpWorld * (32 + kEpCntExtra);
   int ep_seq = 0;
   bool ep_ok = true;
   if (kEp) {
     ep_seq = ep_ctrl(ep)[0] + 1;   // (only this kernel's last CTA advances the word, after every CTA has read it)
-    if (blockIdx.x == 0) ep_send_counts(ep, ep_seq, s_total, E, p.ep_mode);
+    if (blockIdx.x == 0) ep_send_counts(ep, ep_seq, s_total, E, p.ep_mode, gridDim.x, p.ep_ffn_ctas, s_dst);
     ep_ok = ep_wait_counts(ep, ep_seq, E, p.ep_mode, s_cnt, s_base);
   }
   if (threadIdx.x == 0) rtrace(p, 7);
@@ -830,33 +831,20 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 
   // ================================================ completion ================================================
   // The histogram words must not survive into a replay of the same CUDA graph (same tag): the expert-FFN kernel that
-  // always follows clears them (FfnLaunch::clear_ptr).  Only expert parallelism needs to know the last CTA here.
+  // always follows clears them (FfnLaunch::clear_ptr).
   __syncthreads();
   if (threadIdx.x == 0) rtrace(p, 9);
   if (kEp) {
+    // step 3: this CTA's rows (and routing data) have landed -- fence, then one increment on every rank.  The expert
+    // kernels wait for the counters themselves, so nobody has to be the last CTA and nobody waits here.
+    ep_signal(ep, ep.lay.arrive);
     if (threadIdx.x == 0) {
-      ptx::fence_acq_rel_sys();  // this CTA's pushes are performed at the peers (one NVLink round trip)
-      const int last = grid_arrive(p.bar, p.nonce) == gridDim.x;
-      *s_lastp = last;
-      if (last) {
-        __threadfence();
-        // leave the counter with a foreign nonce: the next launch (or CUDA-graph replay, same nonce) starts from scratch
-        p.bar[0] = static_cast<unsigned long long>(~p.nonce) << 32;
+      // (the sequence number advances once every CTA has read it: they all have by the grid barrier above)
+      if (grid_arrive(p.bar, p.nonce) == gridDim.x) {
+        ep_ctrl(ep)[0] = ep_seq;
+        p.bar[0] = static_cast<unsigned long long>(~p.nonce) << 32;  // a foreign nonce: the next launch starts from scratch
       }
     }
-    __syncthreads();
-  }
-  if (kEp && *s_lastp) {
-    // step 3: this rank's rows (and routing data) have landed everywhere -- one thread per peer raises the flag
-    int* ctrl = ep_ctrl(ep);
-    if (threadIdx.x == 0) {
-      ctrl[0] = ep_seq;
-      ctrl[4] = p.ep_mode;
-    }
-    if (threadIdx.x < ep.world)
-      ptx::st_release_sys(reinterpret_cast<int*>(ep.base[threadIdx.x] + ep.lay.disp_flag) + ep.rank, ep_seq);
-    // the same CTA waits for the peers' rows, so that the expert kernel behind this one can start on them at once
-    if (p.ep_fold_wait) ep_wait_rows(ep, ep_seq);
   }
 
   ptx::tc_fence_before();
@@ -914,7 +902,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream, const EpPeers* ep,
                          bool ep_fold_wait, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* ln_c,
-                         int ep_mode) {
+                         int ep_mode, int ep_ffn_ctas) {
   const int S = B * T;
   if (embed == nullptr) Demb = 0;
   if (!route_supported(S, D, Demb, E, 1, B200MOE_BF16)) return cudaErrorInvalidValue;
@@ -970,6 +958,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   p.tag = next_route_tag();
   p.ep_fold_wait = ep_fold_wait ? 1 : 0;
   p.ep_mode = ep_mode;
+  p.ep_ffn_ctas = ep_ffn_ctas;
   // kLn: `wr_packed` is the pre-scaled router of b200moe_pack_router_ln and ln_c its c1 / c0 tail
   p.ln_gamma = (ln_gamma != nullptr && ln_beta != nullptr && ln_c != nullptr) ? ln_gamma : nullptr;
   p.ln_beta = ln_beta;

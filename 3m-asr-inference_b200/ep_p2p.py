@@ -69,6 +69,12 @@ class EpContext:
         lib = _lib.load()
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         dev = torch.device("cuda", torch.cuda.current_device())
+        # the buffers are SYMMETRIC: every rank addresses its peers' buffers with its own layout, so the layout parameters
+        # must be identical everywhere (a per-rank capacity silently sends rows to the wrong place)
+        shapes = [None] * world
+        dist.all_gather_object(shapes, (num_local_expert, d_model, cap), group=group)
+        if any(sh != shapes[0] for sh in shapes):
+            raise ValueError(f"EpContext: (num_local_expert, d_model, cap) differ across ranks: {shapes}")
         nbytes = cls.buffer_bytes(world, num_local_expert, d_model, cap)
         local = C.c_void_p()
         _lib.check(lib.b200moe_ep_alloc(nbytes, C.byref(local)), "b200moe_ep_alloc")

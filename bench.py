@@ -358,8 +358,10 @@ class Case:
         self.bufs = [torch.empty_like(self.x_dev), torch.empty_like(self.x_dev)]
         self.ep_ctx = None
         if b.world > 1 and b.args.ep == "p2p":
-            self.ep_ctx = b.ep_mod.EpContext.from_process_group(b.E_local, D, cap=cap or max(S * top_k, 1),
-                                                                timeout_ms=20000)
+            # symmetric buffers: one capacity for all ranks (their padded batches differ in length)
+            t = torch.tensor([cap or max(S * top_k, 1)], device=b.dev, dtype=torch.int64)
+            b.dist.all_reduce(t, op=b.dist.ReduceOp.MAX)
+            self.ep_ctx = b.ep_mod.EpContext.from_process_group(b.E_local, D, cap=int(t.item()), timeout_ms=20000)
         if self.ep_ctx is not None:
             # outputs inside the symmetric buffer: the owners' epilogue writes the finished rows there (folded combine)
             self.bufs = [self.ep_ctx.out_buffer(0, S), self.ep_ctx.out_buffer(1, S)]

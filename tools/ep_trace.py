@@ -44,8 +44,8 @@ def main():
     out = torch.empty_like(x)
     ctx = ep_p2p.EpContext.from_process_group(El, D, cap=S, timeout_ms=10000)
     for _ in range(3):
-        for Wr, ex, wp in layers:
-            ctx.forward(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
+        for li, (Wr, ex, wp) in enumerate(layers):
+            ctx.forward(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out_slot=li & 1, Wr_packed=wp, wait=li == 3)
     torch.cuda.synchronize()
     dist.barrier()
     cap, n_cta = 256, 148
@@ -55,7 +55,7 @@ def main():
         lib.b200moe_debug_ffn_trace(buf.data_ptr(), cap)
         lib.b200moe_debug_route_trace(rbuf.data_ptr())
     Wr, ex, wp = layers[0]
-    ctx.forward(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out=out, Wr_packed=wp)
+    ctx.forward(x, emb, Wr, None, ex, residual=x, ff_scale=0.5, out_slot=0, Wr_packed=wp)
     torch.cuda.synchronize()
     if rank == 0:
         lib.b200moe_debug_ffn_trace(None, 0)
