@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200moe.so")
 
 F32, F16, BF16 = 0, 1, 2
-ACT_SILU, ACT_RELU, ACT_GELU = 0, 1, 2
+ACT_SILU, ACT_RELU, ACT_GELU, ACT_NONE = 0, 1, 2, 3   # ACT_NONE: b200moe_expert_linear only
 GATE_3M, GATE_NAIVE = 0, 1
 COMPUTE_BF16, COMPUTE_TF32 = 0, 1
 
@@ -61,6 +61,9 @@ SIGNATURES = {
     "b200moe_dispatch": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200moe_expert_ffn": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200moe_combine": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]),
+    "b200moe_prepare": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200moe_scatter_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "b200moe_expert_linear": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200moe_forward": (_i, [C.POINTER(LayerArgs), _vp, _sz, _vp]),
     "b200moe_ep_buffer_bytes": (_sz, [_i, _i, _i, _i]),
     "b200moe_ep_alloc": (_i, [_sz, C.POINTER(_vp)]),

@@ -304,6 +304,69 @@ int b200moe_dispatch(const void* x, const int* idx, int S, int D, int E, int top
   return B200MOE_OK;
 }
 
+int b200moe_prepare(const int* idx, int S, int E, int top_k, int* counts, int* offsets, int* mapping, int* pos, void* ws,
+                    cudaStream_t stream) {
+  if (S < 0 || top_k < 1) return fail(B200MOE_ERR_ARG, "prepare: bad shape");
+  if (E < 1 || E > kMaxExperts) return fail(B200MOE_ERR_ARG, "prepare: E=%d outside [1, %d]", E, kMaxExperts);
+  if (!ws || (S > 0 && !idx)) return fail(B200MOE_ERR_ARG, "prepare: null pointer");
+  RouteWs w = carve_workspace(ws, S, E, 8, 0, top_k);
+  cudaError_t e = launch_dispatch(nullptr, idx, nullptr, S, 8, E, top_k, B200MOE_BF16, choose_bn(S * top_k, E), w, counts,
+                                  offsets, mapping, nullptr, nullptr, nullptr, nullptr, stream);
+  if (e == cudaSuccess && pos != nullptr && S > 0)
+    e = cudaMemcpyAsync(pos, w.pos, sizeof(int) * static_cast<size_t>(S) * top_k, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "prepare");
+  return B200MOE_OK;
+}
+
+int b200moe_scatter_rows(const void* in, const int* index, int n, int n_out, int D, int dtype, void* out,
+                         cudaStream_t stream) {
+  if (n < 0 || n_out < 0 || D < 1 || !dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "scatter_rows: bad argument");
+  const int row_bytes = D * (dtype == B200MOE_F32 ? 4 : 2);
+  if (row_bytes % 16 != 0) return fail(B200MOE_ERR_ARG, "scatter_rows: rows of %d bytes are not a multiple of 16", row_bytes);
+  if (n > 0 && (!in || !index || !out)) return fail(B200MOE_ERR_ARG, "scatter_rows: null pointer");
+  cudaError_t e = launch_scatter_rows(in, index, n, n_out, row_bytes, out, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "scatter_rows");
+  return B200MOE_OK;
+}
+
+int b200moe_expert_linear(const void* xbuf, const int* offsets, int n_rows, const void* W, const float* bias, int E,
+                          int K, int N, int act_type, void* out_bf16, void* ws, cudaStream_t stream) {
+  if (n_rows < 0) return fail(B200MOE_ERR_ARG, "expert_linear: n_rows < 0");
+  if (E < 1 || E > kMaxExperts) return fail(B200MOE_ERR_ARG, "expert_linear: E=%d outside [1, %d]", E, kMaxExperts);
+  if (K % 128 != 0 || N % 128 != 0)
+    return fail(B200MOE_ERR_ARG, "expert_linear: in=%d and out=%d features must be multiples of 128", K, N);
+  if (act_type < 0 || act_type > 3) return fail(B200MOE_ERR_ARG, "expert_linear: bad act_type %d (0 silu, 1 relu, 2 gelu, 3 none)", act_type);
+  if (!ws || !offsets || !W || (n_rows > 0 && (!xbuf || !out_bf16))) return fail(B200MOE_ERR_ARG, "expert_linear: null pointer");
+  if (n_rows == 0) return B200MOE_OK;
+  RouteWs w = carve_workspace(ws, n_rows, E, K, 0, 1);
+  const int bn = choose_bn(n_rows, E);
+  const int gmax = max_groups(n_rows, E, bn);
+  cudaError_t e = launch_build_groups(offsets, E, bn, w.groups, w.n_groups, w.h_ready, gmax, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "expert_linear/build_groups");
+  FfnLaunch a{};
+  a.xbuf = static_cast<const bf16*>(xbuf);
+  a.hbuf = static_cast<bf16*>(out_bf16);   // the first GEMM's output IS the result
+  a.W1 = static_cast<const bf16*>(W);
+  a.b1 = bias;
+  a.groups = w.groups;
+  a.n_groups = w.n_groups;
+  a.h_ready = w.h_ready;
+  a.n_rows = n_rows;
+  a.E = E;
+  a.D = K;
+  a.H = N;
+  a.bn = bn;
+  a.act = act_type;
+  a.gmax = gmax;
+  a.out_dtype = B200MOE_BF16;
+  a.top_k = 1;
+  a.ff_scale = 1.0f;
+  a.p1_only = 1;
+  e = launch_ffn(a, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "expert_linear");
+  return B200MOE_OK;
+}
+
 int b200moe_expert_ffn(const void* xbuf, const int* offsets, int n_rows, const void* W1, const float* b1,
                        const void* W2, const float* b2, int E, int D, int H, int act_type, int out_dtype, void* ybuf,
                        void* ws, cudaStream_t stream) {

@@ -194,7 +194,32 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const T* __restrict__ sr
     dst[i] = __float2bfloat16_rn(to_float(src[i]));
 }
 
+// out[index[i]] = in[i]: the row scatter of fmoe_cuda.local_gather (trainer_3m_fix/fmoe/functions.py:194 with pos as the
+// index).  One warp per row, 128-bit accesses; row_bytes is a multiple of 16.
+__global__ void __launch_bounds__(kCombineThreads)
+scatter_rows_kernel(const uint4* __restrict__ in, const int* __restrict__ index, int n, int n_out, int row_vec,
+                    uint4* __restrict__ out) {
+  const int wpb = blockDim.x / 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * wpb + warp; i < n; i += gridDim.x * wpb) {
+    const int d = index[i];
+    if (d < 0 || d >= n_out) continue;
+    for (int v = lane; v < row_vec; v += 32) out[static_cast<size_t>(d) * row_vec + v] = __ldg(in + static_cast<size_t>(i) * row_vec + v);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_scatter_rows(const void* in, const int* index, int n, int n_out, int row_bytes, void* out,
+                                cudaStream_t stream) {
+  if (row_bytes % 16 != 0) return cudaErrorInvalidValue;
+  if (n <= 0) return cudaSuccess;
+  int blocks = (n + 7) / 8;
+  if (blocks > 8 * 148) blocks = 8 * 148;
+  scatter_rows_kernel<<<blocks, kCombineThreads, 0, stream>>>(static_cast<const uint4*>(in), index, n, n_out,
+                                                              row_bytes / 16, static_cast<uint4*>(out));
+  count_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
                            float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream,

@@ -249,6 +249,8 @@ struct FfnLaunch {
   int* clear_ptr;     // optional: `clear_ints` ints zeroed at kernel start (the route kernel's tagged histogram)
   int clear_ints;
   int tf32;           // 1: xbuf, W1, W2 and hbuf hold fp32 (the pointers above are reinterpreted), TF32 tensor-core math
+  int p1_only;        // 1: first GEMM only -- hbuf [n_rows, H] = act(xbuf . W1^T + b1) is the result (one grouped linear:
+                      //    MOELinear / MOEbiasLinear, trainer_3m_fix/fmoe/functions.py:107-152); W2 / b2 / out unused
 };
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
 // Grid the expert kernel will be launched with (expert parallelism announces it ahead of the launch).
@@ -279,6 +281,8 @@ cudaError_t launch_layernorm(const void* in, const float* gamma, const float* be
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
                            float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream,
                            const float* ln_gamma = nullptr, const float* ln_beta = nullptr, float ln_eps = 0.0f);
+cudaError_t launch_scatter_rows(const void* in, const int* index, int n, int n_out, int row_bytes, void* out,
+                                cudaStream_t stream);
 cudaError_t launch_pack_bf16(const void* src, int src_dtype, bf16* dst, size_t n, cudaStream_t stream);
 cudaError_t launch_pack_tf32(const float* src, float* dst, size_t n, cudaStream_t stream);  // round to nearest TF32
 

@@ -232,6 +232,8 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
       s_cursor[ee] += add;
     }
     // 4. row copy: warp w moves rows w, w+8, ... of the segment, kRowsPerBatch rows (x 16 B per lane) in flight
+    //    (xbuf == nullptr: routing tables only -- moe_prepare_forward, trainer_3m_fix/fmoe/functions.py:13-52)
+    if (xbuf != nullptr || kEp)
     for (int j0 = warp; j0 < n; j0 += kWarps * kRowsPerBatch) {
       int d[kRowsPerBatch];
       const InT* src[kRowsPerBatch];

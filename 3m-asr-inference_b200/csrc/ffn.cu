@@ -48,6 +48,7 @@ constexpr int kSetThreads = 128;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kAccStride = 256;                        // TMEM columns per accumulator buffer
 constexpr int kStagingBytes = 32 * kBlockM * 4;        // per epilogue set: 32 columns x 128 features fp32 (or 2 x bf16)
+constexpr int kActNone = 3;                            // internal: no activation (grouped linear, b200moe_expert_linear)
 
 struct FfnParams {
   const GroupRec* groups;
@@ -67,6 +68,7 @@ struct FfnParams {
   int gmax;  // capacity of the group table
   int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
   int kps;  // k-blocks (of 64) per pipeline stage: one TMA instruction per operand brings all of them
+  int p1_only;  // first GEMM only (a single grouped linear): the tile list has no second-GEMM tiles
   int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
   int warm_mma;     // issue one throw-away MMA before the first tile (B200MOE_WARM, default 1)
   // expert parallelism: results go to the source rank's return buffer over peer-mapped memory (NVLink)
@@ -428,8 +430,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   const GroupRec gr_first = p.groups[g_first];
   const int ng = *p.n_groups;
   const int m1_flags = p.H / kBlockM;  // every CTA publishes its own 128-row slice of h: flags per group
-  const int lag = min(p.lag, ng);
-  const int n_tiles = ng * (m1 + m2);
+  const int lag = p.p1_only ? ng : min(p.lag, ng);
+  const int n_tiles = p.p1_only ? ng * m1 : ng * (m1 + m2);  // (p1_only: lag == ng puts every tile in the head)
   constexpr int kKel = kTf32 ? kBlockK / 2 : kBlockK;  // elements per 128-byte k-block
   const int kb1 = p.D / (kKel * kps);  // pipeline stages per tile of the first GEMM
   const int kb2 = p.H / (kKel * kps);
@@ -692,6 +694,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               sb[j * kBlockM + feat_l] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias, 0.0f));
+          } else if (act == kActNone) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sb[j * kBlockM + feat_l] = __float2bfloat16_rn(__uint_as_float(r[j]) + bias);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -1060,6 +1065,7 @@ int ffn_grid_ctas(int bn, int gmax, int D, int H, bool tf32) {
 cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   if (a.n_rows <= 0) return cudaSuccess;
   if (a.D % kBlockM != 0 || a.H % kBlockM != 0) return cudaErrorInvalidValue;
+  if (a.p1_only && (a.tf32 || a.ep != nullptr || a.fused)) return cudaErrorInvalidValue;
   if (a.bn % 16 != 0 || a.bn < 16 || a.bn > 256) return cudaErrorInvalidValue;
   if (a.fused && a.top_k != 1) return cudaErrorInvalidValue;
   const bool tf32 = a.tf32 != 0;
@@ -1082,6 +1088,12 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
         !make_tmap_f32_kblocks(&th, a.hbuf, a.n_rows, a.H, a.bn, kps)) {
       return cudaErrorInvalidValue;
     }
+  } else if (a.p1_only) {
+    if (!make_tmap_bf16_kblocks(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kps) ||
+        !make_tmap_bf16_kblocks(&tx, a.xbuf, a.n_rows, a.D, a.bn / ctas, kps))
+      return cudaErrorInvalidValue;
+    tw2 = tw1;  // (never used: there are no second-GEMM tiles)
+    th = tx;
   } else if (!make_tmap_bf16_kblocks(&tw1, a.W1, static_cast<uint64_t>(a.E) * a.H, a.D, kBlockM, kps) ||
       !make_tmap_bf16_kblocks(&tw2, a.W2, static_cast<uint64_t>(a.E) * a.D, a.H, kBlockM, kps) ||
       !make_tmap_bf16_kblocks(&tx, a.xbuf, a.n_rows, a.D, a.bn / ctas, kps) ||
@@ -1127,6 +1139,7 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   p.act = a.act;
   p.fused = a.fused;
   p.kps = kps;
+  p.p1_only = a.p1_only ? 1 : 0;
   p.stages = stages_for(a.bn / ctas, kps);
   {
     static const int dbg = [] {

@@ -15,7 +15,7 @@ from typing import Dict, NamedTuple, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_RELU, ACT_SILU, BF16, COMPUTE_BF16, COMPUTE_TF32, F16, F32, GATE_3M,  # noqa: F401
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, COMPUTE_BF16, COMPUTE_TF32, F16, F32, GATE_3M,  # noqa: F401
                    GATE_NAIVE)
 
 _DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
@@ -287,6 +287,67 @@ def combine(ybuf: torch.Tensor, mapping: torch.Tensor, score: Optional[torch.Ten
     lib = _lib.load()
     _lib.check(lib.b200moe_combine(_ptr(ybuf), _ptr(mapping), _ptr(score), _ptr(residual), float(ff_scale), S, D,
                                    top_k, dtype_code(ybuf), _ptr(out), _stream()), "b200moe_combine")
+    return out
+
+
+class Prepared(NamedTuple):
+    counts: torch.Tensor   # [E] int32
+    offsets: torch.Tensor  # [E + 1] int32
+    mapping: torch.Tensor  # [n] int32: row of entry i in expert order (-1 = not routed)
+    pos: torch.Tensor      # [n] int32: entry held by row r (the reference's `pos`: stable argsort of the expert ids)
+
+
+def prepare(idx: torch.Tensor, num_expert: int, *, top_k: int = 1) -> Prepared:
+    """Routing tables only (moe_prepare_forward, trainer_3m_fix/fmoe/functions.py:13-52): no row copy, no host sync.
+    idx: [n] int32 target experts, n = S * top_k entries."""
+    dev = _need_cuda(idx)
+    if idx.dtype != torch.int32:
+        raise TypeError("idx must be int32")
+    n = idx.numel()
+    if n % top_k:
+        raise ValueError("idx.numel() must be a multiple of top_k")
+    S = n // top_k
+    counts = torch.empty(num_expert, dtype=torch.int32, device=dev)
+    offsets = torch.empty(num_expert + 1, dtype=torch.int32, device=dev)
+    mapping = torch.empty(n, dtype=torch.int32, device=dev)
+    pos = torch.empty(n, dtype=torch.int32, device=dev)
+    ws = get_workspace(dev, S, num_expert, 8, 0, top_k)
+    _lib.check(_lib.load().b200moe_prepare(_ptr(idx), S, num_expert, top_k, _ptr(counts), _ptr(offsets), _ptr(mapping),
+                                           _ptr(pos), _ptr(ws), _stream()), "b200moe_prepare")
+    return Prepared(counts, offsets, mapping, pos)
+
+
+def scatter_rows(inp: torch.Tensor, index: torch.Tensor, n_out: int) -> torch.Tensor:
+    """out[index[i]] = inp[i] (fmoe_cuda.local_gather, functions.py:194); rows no index points at are zero."""
+    dev = _need_cuda(inp, index)
+    if index.dtype != torch.int32:
+        raise TypeError("index must be int32")
+    n, D = inp.shape
+    out = torch.zeros(n_out, D, dtype=inp.dtype, device=dev)
+    _lib.check(_lib.load().b200moe_scatter_rows(_ptr(inp), _ptr(index), n, n_out, D, dtype_code(inp), _ptr(out),
+                                                _stream()), "b200moe_scatter_rows")
+    return out
+
+
+def expert_linear(xbuf: torch.Tensor, offsets: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                  *, act_type: int = _lib.ACT_NONE) -> torch.Tensor:
+    """One grouped linear over expert-contiguous rows (fmoe_cuda.forward: MOELinear / MOEbiasLinear.forward,
+    functions.py:107-152): out[r] = act(xbuf[r] . weight[e]^T + bias[e]).  xbuf bf16 [rows, K], weight bf16 [E, N, K],
+    bias fp32 [E, N] or None -> bf16 [rows, N]."""
+    dev = _need_cuda(xbuf, offsets, weight, bias)
+    n_rows, K = xbuf.shape
+    E, N, K2 = weight.shape
+    if K2 != K or xbuf.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise ValueError("xbuf must be bf16 [rows, K] and weight bf16 [E, N, K]")
+    if bias is not None and (bias.dtype != torch.float32 or tuple(bias.shape) != (E, N)):
+        raise ValueError("bias must be fp32 [E, N]")
+    if offsets.dtype != torch.int32 or offsets.numel() != E + 1:
+        raise ValueError("offsets must be int32 [E + 1]")
+    out = torch.empty(n_rows, N, dtype=torch.bfloat16, device=dev)
+    ws = get_workspace(dev, n_rows, E, K, 0, 1)
+    _lib.check(_lib.load().b200moe_expert_linear(_ptr(xbuf), _ptr(offsets), n_rows, _ptr(weight), _ptr(bias), E, K, N,
+                                                 int(act_type), _ptr(out), _ptr(ws), _stream()),
+               "b200moe_expert_linear")
     return out
 
 

@@ -241,6 +241,29 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(torch, index):
+    """One process per GPU: run this rank's host threads -- and so first-touch its pinned staging buffers -- on the NUMA
+    node its GPU hangs off, instead of wherever the launcher left it (with 8 ranks on node 0 the host copies of the
+    GPUs behind the other socket cross the inter-socket link).  Best effort: returns the node or None."""
+    try:
+        props = torch.cuda.get_device_properties(index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class Bench:
     """One rank's state: device, process group, EP context, peaks."""
 
@@ -254,6 +277,7 @@ class Bench:
         self.ops = importlib.import_module(PKG + ".ops")   # raises if libb200moe.so is missing: no fallback
         assert torch.cuda.is_available(), "bench.py needs a CUDA device"
         torch.cuda.set_device(self.local_rank)
+        self.numa = pin_to_gpu_numa_node(torch, self.local_rank) if self.world > 1 else None
         self.dev = torch.device("cuda", self.local_rank)
         self.dist = None
         if self.world > 1:
@@ -803,6 +827,7 @@ def main():
                     "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
             "parity": parity,
             "sustained": sustained,
+            "host_numa_node": b.numa,
             "gpu_launches": case.launches_per_step * K,
             "gpu_launches_per_step": case.launches_per_step,
             "clocks": clocks,

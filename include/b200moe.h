@@ -145,6 +145,30 @@ int b200moe_expert_ffn(const void* xbuf, const int* offsets, int n_rows, const v
 int b200moe_combine(const void* ybuf, const int* mapping, const float* score, const void* residual, float ff_scale,
                     int S, int D, int top_k, int dtype, void* out, cudaStream_t stream);
 
+/* ---- the staged operator surface of trainer_3m_fix/fmoe/functions.py (forward halves) --------------------------
+ * What the reference's autograd Functions hand to the un-vendored `fmoe_cuda` extension, one entry point each, so that
+ * MOEScatter / MOELinear / MOEbiasLinear / MOEGather `.apply` (3m-asr-inference_b200/fmoe/functions.py) are thin.
+ *
+ * b200moe_prepare      <- moe_prepare_forward, functions.py:13-52: routing tables only, no row copy, no host sync.
+ *   idx [S*top_k] int32 target experts (-1 = not routed).  counts [E], offsets [E+1], mapping [S*top_k] as
+ *   b200moe_dispatch; pos [S*top_k] or NULL = the reference's `pos` (the STABLE argsort of idx: pos[mapping[i]] = i,
+ *   entries past offsets[E] unspecified).  ws >= b200moe_workspace_bytes(S, E, 8, 0, top_k).
+ * b200moe_scatter_rows <- fmoe_cuda.local_gather, functions.py:194 (and the backward of local_scatter :102):
+ *   out[index[i], :] = in[i, :] for i < n, rows of D elements in `dtype`; index values outside [0, n_out) are skipped.
+ *   (fmoe_cuda.local_scatter, functions.py:72, is the gather out[i] = in[pos[i]]: b200moe_combine with score = residual
+ *   = NULL, ff_scale = 1, top_k = 1.)
+ * b200moe_expert_linear <- fmoe_cuda.forward, functions.py:113-116,141-149 (MOELinear / MOEbiasLinear.forward): ONE
+ *   grouped linear, out[r, :] = act(xbuf[r, :] . W[e]^T + bias[e]) for the rows r of expert e.  xbuf [n_rows, K] bf16,
+ *   W [E, N, K] bf16, bias [E, N] fp32 or NULL, out [n_rows, N] bf16; act_type 0..2 as B200MOE_ACT_*, 3 = none (the
+ *   reference applies its activation between the two Functions, fmoe/transformer.py:27-29).  K, N multiples of 128.
+ *   The first GEMM of the expert kernel on its own.  ws >= b200moe_workspace_bytes(n_rows, E, K, 0, 1). */
+int b200moe_prepare(const int* idx, int S, int E, int top_k, int* counts, int* offsets, int* mapping, int* pos,
+                    void* ws, cudaStream_t stream);
+int b200moe_scatter_rows(const void* in, const int* index, int n, int n_out, int D, int dtype, void* out,
+                         cudaStream_t stream);
+int b200moe_expert_linear(const void* xbuf, const int* offsets, int n_rows, const void* W, const float* bias, int E,
+                          int K, int N, int act_type, void* out_bf16, void* ws, cudaStream_t stream);
+
 /* ---- the fused layer --------------------------------------------------------------------------------------- */
 typedef struct b200moe_layer_args {
   /* activations, `dtype` */
