@@ -48,6 +48,8 @@ SIGNATURES = {
     "b200moe_launch_count": (C.c_ulonglong, []),
     "b200moe_debug_ffn_trace": (_i, [_vp, _i]),
     "b200moe_debug_route_trace": (_i, [_vp]),
+    "b200moe_debug_timeline": (_i, [_vp, _i]),
+    "b200moe_debug_timeline_kind": (_i, [_i]),
     "b200moe_config": (_i, [C.c_char_p, _i]),
     "b200moe_profile_enable": (_i, [_i]),
     "b200moe_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),

@@ -160,6 +160,13 @@ int b200moe_debug_route_trace(void* dev_buf) {
   return B200MOE_OK;
 }
 
+int b200moe_debug_timeline(void* dev_buf, int max_launches) {
+  b200moe::set_timeline(dev_buf, max_launches);
+  return B200MOE_OK;
+}
+
+int b200moe_debug_timeline_kind(int slot) { return b200moe::timeline_kind(slot); }
+
 int b200moe_debug_ffn_trace(void* dev_buf, int records_per_cta) {
   set_ffn_trace(dev_buf, records_per_cta);
   return B200MOE_OK;
@@ -500,7 +507,9 @@ static int forward_impl(const b200moe_layer_args* a, void* ws, size_t ws_bytes, 
     e = launch_route(a->x, a->embed, ln ? ln->packed : a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E,
                      a->gate_mode, a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out,
                      w.xbuf, fused ? a->out : nullptr, a->residual, stream, nullptr, false, ln ? ln->gamma : nullptr,
-                     ln ? ln->beta : nullptr, ln ? ln->eps : 0.0f, ln ? ln_consts(ln, a->D + Demb) : nullptr);
+                     ln ? ln->beta : nullptr, ln ? ln->eps : 0.0f, ln ? ln_consts(ln, a->D + Demb) : nullptr, 0, 0,
+                     a->W1, static_cast<size_t>(a->E) * a->H * a->D * sizeof(bf16), a->W2,
+                     static_cast<size_t>(a->E) * a->H * a->D * sizeof(bf16));
     if (e != cudaSuccess) return cuda_fail(e, "forward/route");
   } else {
   {
@@ -801,7 +810,9 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
                      a->E, a->gate_mode, a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out,
                      w.xbuf, drop_out, a->residual, stream, &ep, true, ln_in ? ln_in->gamma : nullptr,
                      ln_in ? ln_in->beta : nullptr, ln_in ? ln_in->eps : 0.0f,
-                     ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr, mode, ffn_ctas);
+                     ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr, mode, ffn_ctas, a->W1,
+                     static_cast<size_t>(ep.E_local) * a->H * a->D * sizeof(bf16), a->W2,
+                     static_cast<size_t>(ep.E_local) * a->H * a->D * sizeof(bf16));
     if (e != cudaSuccess) return cuda_fail(e, "ep_forward/route");
   } else {
     if (S > 0 && (stages & 1)) {

@@ -214,7 +214,8 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream,
                          const EpPeers* ep = nullptr, bool ep_fold_wait = false, const float* ln_gamma = nullptr,
                          const float* ln_beta = nullptr, float ln_eps = 0.0f, const float* ln_c = nullptr,
-                         int ep_mode = 0, int ep_ffn_ctas = 0);
+                         int ep_mode = 0, int ep_ffn_ctas = 0, const void* pf0 = nullptr, size_t pf0_bytes = 0,
+                         const void* pf1 = nullptr, size_t pf1_bytes = 0);
 // Router packed for the route kernel's fused norm_ff: like launch_pack_router, with the x rows (k >= R - D) scaled by
 // gamma, followed by c1[32] = gamma^T Wr_x and c0[32] = beta^T Wr_x (fp32).  router_ln_pack_bytes(R) bytes.
 size_t router_ln_pack_bytes(int R);
@@ -257,6 +258,14 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream);
 int ffn_grid_ctas(int bn, int gmax, int D, int H, bool tf32);
 // Debug timeline: every following ffn launch records per-CTA events into dev_buf (16 B records); null disables.
 void set_ffn_trace(void* dev_buf, int records_per_cta);
+// Debug, across kernels: every launch of the route and expert kernels takes the next slot of 148 CTAs x 8 marks
+// (%globaltimer ns; 0 = not reached) while a buffer is set -- when its CTAs started, passed their dependency wait,
+// saw their first data, finished.  Works under CUDA-graph capture (the slot is frozen into the captured launch).
+// kind 1 = route, 2 = expert kernel; the slot header is written by the host side into `kinds`.
+constexpr int kTimelineMarks = 8;
+void set_timeline(void* dev_buf, int max_launches);
+unsigned long long* next_timeline_slot(int kind);  // nullptr when off or full
+int timeline_kind(int slot);
 
 // ep.cu
 // Waits until every rank's rows of the current layer call have landed (staged drivers; the one-call path folds the wait

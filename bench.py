@@ -43,6 +43,7 @@ WORKLOADS = {
     "cfg1": dict(layers=1, utts=1, tok_per_utt=50, desc="single fast_moe layer, one 206-frame utterance (50 tokens)"),
     "cfg2": dict(layers=12, utts=1, tok_per_utt=50, desc="12-layer encoder MoE path, batch 1 x 206 frames"),
     "cfg3": dict(layers=18, utts=64, tok_per_utt=50, desc="18-layer encoder MoE path, batch 64 x 206 frames"),
+    "cfg3x1": dict(layers=1, utts=64, tok_per_utt=50, desc="ONE layer x 3 200 tokens replayed (weights stay in L2: experiments)"),
     "cfg3f": dict(layers=18, utts=64, tok_per_utt=206, desc="18-layer encoder MoE path, batch 64, frames as tokens"),
     "big": dict(layers=18, utts=512, tok_per_utt=128, desc="18 layers x 65 536 tokens (compute-bound regime)"),
     "cfg4": dict(layers=18, utts=32, frames=(100, 1000),

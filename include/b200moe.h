@@ -363,6 +363,14 @@ int b200moe_profile_read(float* stage_ms, int* stage_calls);
  * records_per_cta/4 slots per CTA, CTA-major.  dev_buf must hold 148 * records_per_cta records.  See tools/ffn_trace.py. */
 int b200moe_debug_ffn_trace(void* dev_buf, int records_per_cta);
 
+/* Debug, across kernels: while dev_buf is non-NULL every launch of the fused gate + dispatch kernel and of the expert
+ * kernel takes the next slot of 148 CTAs x 8 marks of 8 bytes (%globaltimer in ns; 0 = not reached): 0 CTA start,
+ * 1 dependency wait passed, 2 first operand data on chip, 3 last weight request issued, 4 last MMA issued, 5 CTA end.
+ * dev_buf holds max_launches slots, zeroed by the caller; slots are handed out in launch order (and frozen into a
+ * captured CUDA graph).  b200moe_debug_timeline_kind(slot) -> 1 route, 2 expert kernel, 0 unused.  tools/timeline.py. */
+int b200moe_debug_timeline(void* dev_buf, int max_launches);
+int b200moe_debug_timeline_kind(int slot);
+
 /* Debug: timeline of the fused gate + dispatch kernel, 16 records of 16 bytes per CTA (148 CTAs at most). */
 int b200moe_debug_route_trace(void* dev_buf);
 
