@@ -89,6 +89,10 @@ SIGNATURES = {
     "b200moe_ep_block_workspace_bytes": (_sz, [_vp, _i]),
     "b200moe_ep_block_forward": (_i, [_vp, C.POINTER(BlockArgs), _vp, _sz, _vp]),
     "b200moe_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp]),
+    "b200moe_att_masked_softmax": (_i, [_vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b200moe_glu": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "b200moe_masked_fill": (_i, [_vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]),
+    "b200moe_rel_pos_encoding": (_i, [_vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200moe_plugin_create": (_vp, [_i, _i, _i, _i, _i]),
     "b200moe_plugin_clone": (_vp, [_vp]),
     "b200moe_plugin_serialization_size": (_sz, [_vp]),

@@ -1156,6 +1156,44 @@ int b200moe_layernorm(const void* in, const float* gamma, const float* beta, flo
   return B200MOE_OK;
 }
 
+int b200moe_att_masked_softmax(const void* in, const int* mask, float scale, int B, int N, int S, int ld, int dtype,
+                               void* out, cudaStream_t stream) {
+  if (B < 0 || N < 0 || S < 0 || !dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "att_masked_softmax: bad shape / dtype");
+  if (static_cast<long long>(B) * N * S == 0) return B200MOE_OK;
+  if (!masked_softmax_supported(ld)) return fail(B200MOE_ERR_ARG, "att_masked_softmax: ld=%d outside [1, 1024]", ld);
+  if (!in || !out) return fail(B200MOE_ERR_ARG, "att_masked_softmax: null pointer");
+  cudaError_t e = launch_att_masked_softmax(in, mask, scale, B, N, S, ld, dtype, out, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "att_masked_softmax");
+  return B200MOE_OK;
+}
+
+int b200moe_glu(const void* x, int M, int C, int N, int dtype, void* y, cudaStream_t stream) {
+  if (M < 0 || C < 0 || N < 0 || !dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "glu: bad shape / dtype");
+  if (static_cast<long long>(M) * C * N > 0 && (!x || !y)) return fail(B200MOE_ERR_ARG, "glu: null pointer");
+  cudaError_t e = launch_glu(x, M, C, N, dtype, y, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "glu");
+  return B200MOE_OK;
+}
+
+int b200moe_masked_fill(const void* in, const int* mask, float fill, int B, int dim, int T, int dtype, void* out,
+                        cudaStream_t stream) {
+  if (B < 0 || dim < 0 || T < 0 || !dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "masked_fill: bad shape / dtype");
+  if (static_cast<long long>(B) * dim * T > 0 && (!in || !mask || !out)) return fail(B200MOE_ERR_ARG, "masked_fill: null pointer");
+  cudaError_t e = launch_masked_fill(in, mask, fill, B, dim, T, dtype, out, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "masked_fill");
+  return B200MOE_OK;
+}
+
+int b200moe_rel_pos_encoding(const void* in, const void* pe, float scale, int B, int T, int D, int dtype, void* out,
+                             void* pos_emb, cudaStream_t stream) {
+  if (B < 0 || T < 0 || D < 0 || !dtype_ok(dtype)) return fail(B200MOE_ERR_ARG, "rel_pos_encoding: bad shape / dtype");
+  if (static_cast<long long>(B) * T * D > 0 && (!in || !pe || !out || !pos_emb))
+    return fail(B200MOE_ERR_ARG, "rel_pos_encoding: null pointer");
+  cudaError_t e = launch_rel_pos_encoding(in, pe, scale, B, T, D, dtype, out, pos_emb, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rel_pos_encoding");
+  return B200MOE_OK;
+}
+
 int b200moe_block_forward(const b200moe_block_args* b, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (!b) return fail(B200MOE_ERR_ARG, "block_forward: null args");
   const b200moe_layer_args& a = b->layer;

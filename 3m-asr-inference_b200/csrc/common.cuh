@@ -290,6 +290,15 @@ cudaError_t launch_layernorm(const void* in, const float* gamma, const float* be
 cudaError_t launch_combine(const void* ybuf, const int* mapping, const float* score, const void* residual,
                            float ff_scale, int S, int D, int top_k, int dtype, void* out, cudaStream_t stream,
                            const float* ln_gamma = nullptr, const float* ln_beta = nullptr, float ln_eps = 0.0f);
+// The other encoder plugins (encoder_ops.cu)
+bool masked_softmax_supported(int ld);
+cudaError_t launch_att_masked_softmax(const void* in, const int* mask, float scale, int B, int N, int S, int ld, int dtype,
+                                      void* out, cudaStream_t stream);
+cudaError_t launch_glu(const void* x, long long M, int C, int N, int dtype, void* y, cudaStream_t stream);
+cudaError_t launch_masked_fill(const void* in, const int* mask, float fill, int B, int dim, int T_len, int dtype, void* out,
+                               cudaStream_t stream);
+cudaError_t launch_rel_pos_encoding(const void* in, const void* pe, float scale, int B, int T_len, int D, int dtype,
+                                    void* out, void* pos_emb, cudaStream_t stream);
 cudaError_t launch_scatter_rows(const void* in, const int* index, int n, int n_out, int row_bytes, void* out,
                                 cudaStream_t stream);
 cudaError_t launch_pack_bf16(const void* src, int src_dtype, bf16* dst, size_t n, cudaStream_t stream);

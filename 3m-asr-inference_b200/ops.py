@@ -446,6 +446,51 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+# ---- the other encoder plugins ------------------------------------------------------------------------------
+def att_masked_softmax(scores: torch.Tensor, mask: Optional[torch.Tensor], scale: float) -> torch.Tensor:
+    """AttMaskedSoftmaxPluginDynamic: scores [B, N, S, ld], mask [B] int32 valid keys -> softmax(scale * scores), 0 behind."""
+    _need_cuda(scores, mask)
+    B, N, S, ld = scores.shape
+    out = torch.empty_like(scores)
+    _lib.check(_lib.load().b200moe_att_masked_softmax(_ptr(scores), _ptr(mask), float(scale), B, N, S, ld,
+                                                      dtype_code(scores), _ptr(out), _stream()), "b200moe_att_masked_softmax")
+    return out
+
+
+def glu(x: torch.Tensor) -> torch.Tensor:
+    """GluPluginDynamic over dim 1: x [M, 2C, N] -> [M, C, N]."""
+    _need_cuda(x)
+    M, C2, N = x.shape
+    if C2 % 2:
+        raise ValueError("GLU needs an even number of channels")
+    y = torch.empty(M, C2 // 2, N, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().b200moe_glu(_ptr(x), M, C2 // 2, N, dtype_code(x), _ptr(y), _stream()), "b200moe_glu")
+    return y
+
+
+def masked_fill(x: torch.Tensor, mask: torch.Tensor, fill: float = 0.0) -> torch.Tensor:
+    """MaskedFillPluginDynamic: x [B, dim, T], mask [B] int32 valid lengths; t >= mask[b] -> fill."""
+    _need_cuda(x, mask)
+    B, dim, T = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().b200moe_masked_fill(_ptr(x), _ptr(mask), float(fill), B, dim, T, dtype_code(x), _ptr(out),
+                                               _stream()), "b200moe_masked_fill")
+    return out
+
+
+def rel_pos_encoding(x: torch.Tensor, pe: torch.Tensor, scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """RelPositionalEncodingPluginDynamic: x [B, T, D], pe [max_len, D] -> (x * scale, pe[:T])."""
+    _need_cuda(x, pe)
+    B, T, D = x.shape
+    if pe.dtype != x.dtype or pe.shape[-1] != D or pe.shape[-2] < T:
+        raise ValueError("pe must be [max_len >= T, D] in the activation dtype")
+    out = torch.empty_like(x)
+    pos = torch.empty(T, D, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().b200moe_rel_pos_encoding(_ptr(x), _ptr(pe), float(scale), B, T, D, dtype_code(x), _ptr(out),
+                                                    _ptr(pos), _stream()), "b200moe_rel_pos_encoding")
+    return out, pos
+
+
 # ---- torch.library registration ---------------------------------------------------------------------------------------------
 # The layer as a registered PyTorch operator, `torch.ops.b200moe.fmoe_forward`: the op the reference's FMoE.forward /
 # LocalFmoeCatEmbedFeedForward.forward boil down to (trainer_3m_fix/fmoe/layers.py:186-210, positionwise_feed_forward.py:

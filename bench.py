@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--sweep-max", type=int, default=SWEEP_TOKENS[-1], help="largest sweep point (global tokens)")
     ap.add_argument("--sweep-points", default="", help="run only these sweep points: 'tokens:k[:zipf],...'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--encoder", action="store_true",
+                    help="also time the whole Conformer-MoE encoder around the path (SURVEY 8 f1): utterances/s, N = 1")
     return ap.parse_args()
 
 
@@ -659,6 +661,71 @@ def run_sweep(b: Bench):
             sys.exit(4)
 
 
+def encoder_bench(b, wl, steps, warmup, moe_ms_step):
+    """The whole encoder around the path (BASELINE metric "18L encoder utts/sec"): embed net (6 dense Conformer
+    blocks), Conv2dSubsampling4, `layers` FmoeConformerLayers whose feed-forward block runs through b200moe_block_forward,
+    after_norm + output linear.  Everything outside the fast_moe block is library code (torch: cuDNN / cuBLAS / SDPA).
+    Synthetic 206-frame, 40-dim features, random-init weights of the repo configuration, bf16, CUDA graph."""
+    torch, dev = b.torch, b.dev
+    enc = importlib.import_module(PKG + ".encoder")
+    L, B, frames = wl["layers"], wl["utts"], 206
+    torch.manual_seed(7)
+    model = enc.ConformerMoEEncoder(
+        40, 5000, attention_heads=8, attention_dim=512, num_blocks=L,
+        embed_conf=dict(attention_heads=4, attention_dim=512, linear_units=1024, num_blocks=6),
+        moe_conf=dict(num_experts=32, hidden_units=1024, rand_init_router=True)).to(dev)
+    model.to_inference(torch.bfloat16)
+    feats = (torch.randn(B, frames, 40, device=dev) * 0.5).bfloat16()
+    lens = torch.full((B,), frames, dtype=torch.int64, device=dev)
+    feats_host = feats.cpu().pin_memory()
+    ops = b.ops
+    stream = torch.cuda.Stream(device=dev)
+    with torch.no_grad(), torch.cuda.stream(stream):
+        for _ in range(2):
+            out = model(feats, lens)
+        stream.synchronize()
+        n0 = ops.launch_count()
+        out = model(feats, lens)
+        launches = ops.launch_count() - n0
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            out = model(feats, lens)
+        out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+
+        def timed(fn, n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stream.synchronize()
+            e0.record(stream)
+            for _ in range(n):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        def e2e():
+            feats.copy_(feats_host, non_blocking=True)
+            graph.replay()
+            out_host.copy_(out, non_blocking=True)
+
+        for _ in range(warmup):
+            graph.replay()
+        ms = timed(graph.replay, steps)
+        for _ in range(2):
+            e2e()
+        ms_e2e = timed(e2e, steps)
+    finite = bool(torch.isfinite(out.float()).all())
+    del graph, model
+    torch.cuda.empty_cache()
+    return {"utterances_per_sec": B / (ms * 1e-3), "ms_per_step": ms, "layers": L, "utterances": B, "frames": frames,
+            "tokens_per_utterance": 50, "moe_path_share": moe_ms_step / ms, "own_kernel_launches_per_step": int(launches),
+            "e2e": {"utterances_per_sec": B / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": feats_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 2},
+            "output_finite": finite, "mode": "cuda_graph", "dtype": "bf16",
+            "note": "fast_moe blocks: this repository's kernels (C ABI); embed net, attention, convolution, subsampling, "
+                    "output linear: torch library ops"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -808,6 +875,10 @@ def main():
                         "sample": f"{reps} passes of {n_layers} of the {L} layers x {valid} tokens of the CPU oracle, "
                                   f"{n_sets} weight sets cycled, torch {torch.__version__} fp32"}
 
+    encoder = None
+    if args.encoder and b.world == 1 and "tok_per_utt" in wl and wl["tok_per_utt"] == 50 and not b.tf32:
+        encoder = encoder_bench(b, wl, min(K, 30), max(3, min(args.warmup, 5)), ms_step)
+
     if b.rank == 0:
         line = {
             "metric": "moe_layer_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": b.world, "steps": K,
@@ -828,6 +899,7 @@ def main():
                     "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
             "parity": parity,
             "sustained": sustained,
+            "encoder": encoder,
             "host_numa_node": b.numa,
             "gpu_launches": case.launches_per_step * K,
             "gpu_launches_per_step": case.launches_per_step,

@@ -341,6 +341,27 @@ int b200moe_ep_block_forward(b200moe_ep_ctx* ctx, const b200moe_block_args* args
 size_t b200moe_router_ln_pack_bytes(int R);
 int b200moe_pack_router_ln(const float* Wr, int R, int E, int D, const float* gamma, const float* beta, void* packed,
                            cudaStream_t stream);
+/* ---- the other encoder plugins: what sits between the fast_moe blocks in the reference's TensorRT graph ----
+ * All in `dtype` (B200MOE_F32 / F16 / BF16) with fp32 arithmetic, caller's stream, in == out allowed.
+ * b200moe_att_masked_softmax <- AttMaskedSoftmaxPluginDynamic (TRTAPI++/plugin/att_masked_softmax_plugin/
+ *   att_masked_softmax_kernel.cu:198-277; called from layer/attention.py:199-239): in / out [B, N, S, ld] attention scores,
+ *   mask [B] int32 valid keys (NULL = all); out = softmax(scale * in) over keys < mask[b], exactly 0 behind; ld <= 1024.
+ *   A row with no valid key gives zeros (the reference divides by zero there).
+ * b200moe_glu <- GluPluginDynamic (glu_plugin/glu_kernel.cu:24-37; layer/convolution.py:125): x [M, 2C, N] -> y [M, C, N],
+ *   y = x[:, :C] * sigmoid(x[:, C:]).
+ * b200moe_masked_fill <- MaskedFillPluginDynamic (masked_fill_plugin/masked_fill_kernel.cu:25-39; layer/convolution.py:
+ *   89-113,153): in / out [B, dim, T], positions t >= mask[b] become `fill`.
+ * b200moe_rel_pos_encoding <- RelPositionalEncodingPluginDynamic (rel_positional_encoding_plugin/
+ *   rel_positional_encoding_kernel.cu:61-93; layer/positional_encoding.py:101-130): out [B, T, D] = in * scale,
+ *   pos_emb [T, D] = pe[:T] (pe [max_len, D], max_len >= T). */
+int b200moe_att_masked_softmax(const void* in, const int* mask, float scale, int B, int N, int S, int ld, int dtype,
+                               void* out, cudaStream_t stream);
+int b200moe_glu(const void* x, int M, int C, int N, int dtype, void* y, cudaStream_t stream);
+int b200moe_masked_fill(const void* in, const int* mask, float fill, int B, int dim, int T, int dtype, void* out,
+                        cudaStream_t stream);
+int b200moe_rel_pos_encoding(const void* in, const void* pe, float scale, int B, int T, int D, int dtype, void* out,
+                             void* pos_emb, cudaStream_t stream);
+
 /* The LayerNorm alone (LayerNormPluginDynamic, TRTAPI++/plugin/layer_norm_plugin/layer_norm_kernel.cu, with the eps the
  * plugin drops): out [S, D] = LN(in [S, D]); in == out allowed. */
 int b200moe_layernorm(const void* in, const float* gamma, const float* beta, float eps, int S, int D, int dtype,
