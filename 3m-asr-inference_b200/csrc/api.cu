@@ -507,9 +507,7 @@ static int forward_impl(const b200moe_layer_args* a, void* ws, size_t ws_bytes, 
     e = launch_route(a->x, a->embed, ln ? ln->packed : a->Wr_packed, a->br, a->x_len, a->B, a->T, a->D, Demb, a->E,
                      a->gate_mode, a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out,
                      w.xbuf, fused ? a->out : nullptr, a->residual, stream, nullptr, false, ln ? ln->gamma : nullptr,
-                     ln ? ln->beta : nullptr, ln ? ln->eps : 0.0f, ln ? ln_consts(ln, a->D + Demb) : nullptr, 0, 0,
-                     a->W1, static_cast<size_t>(a->E) * a->H * a->D * sizeof(bf16), a->W2,
-                     static_cast<size_t>(a->E) * a->H * a->D * sizeof(bf16));
+                     ln ? ln->beta : nullptr, ln ? ln->eps : 0.0f, ln ? ln_consts(ln, a->D + Demb) : nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "forward/route");
   } else {
   {
@@ -810,9 +808,7 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
                      a->E, a->gate_mode, a->keep_expert_output, idx, score, bn, w, a->counts_out, nullptr, a->mapping_out,
                      w.xbuf, drop_out, a->residual, stream, &ep, true, ln_in ? ln_in->gamma : nullptr,
                      ln_in ? ln_in->beta : nullptr, ln_in ? ln_in->eps : 0.0f,
-                     ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr, mode, ffn_ctas, a->W1,
-                     static_cast<size_t>(ep.E_local) * a->H * a->D * sizeof(bf16), a->W2,
-                     static_cast<size_t>(ep.E_local) * a->H * a->D * sizeof(bf16));
+                     ln_in ? ln_consts(ln_in, a->D + Demb) : nullptr, mode, ffn_ctas);
     if (e != cudaSuccess) return cuda_fail(e, "ep_forward/route");
   } else {
     if (S > 0 && (stages & 1)) {

@@ -214,8 +214,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream,
                          const EpPeers* ep = nullptr, bool ep_fold_wait = false, const float* ln_gamma = nullptr,
                          const float* ln_beta = nullptr, float ln_eps = 0.0f, const float* ln_c = nullptr,
-                         int ep_mode = 0, int ep_ffn_ctas = 0, const void* pf0 = nullptr, size_t pf0_bytes = 0,
-                         const void* pf1 = nullptr, size_t pf1_bytes = 0);
+                         int ep_mode = 0, int ep_ffn_ctas = 0);
 // Router packed for the route kernel's fused norm_ff: like launch_pack_router, with the x rows (k >= R - D) scaled by
 // gamma, followed by c1[32] = gamma^T Wr_x and c0[32] = beta^T Wr_x (fp32).  router_ln_pack_bytes(R) bytes.
 size_t router_ln_pack_bytes(int R);

@@ -22,19 +22,16 @@ __device__ __forceinline__ bool ep_wait_flag_sys(const int* flag, int want, unsi
 
 __device__ __forceinline__ int* ep_ctrl(const EpPeers& ep) { return reinterpret_cast<int*>(ep.base[ep.rank] + ep.lay.ctrl); }
 
-// Group table over expert-contiguous rows, STATIC in its first E entries: group e < E is always expert e's first token
-// tile (nrows == 0 when the expert got no rows), further tiles of experts with more than bn rows follow from index E on in
-// expert order.  So which weight rows a CTA of the expert kernel needs for its first tile does not depend on the routing
-// and can be requested before the routing tables exist (ffn.cu).  Runs in one CTA (every thread calls it); offsets_sm[E + 1]
-// in shared or global memory, scratch[E + 1] in shared memory.
+// Group table over expert-contiguous rows: expert e contributes ceil(count[e] / bn) groups, in expert order.  Runs in one
+// CTA (every thread calls it); offsets_sm[E + 1] in shared or global memory, scratch[E + 1] in shared memory.
 __device__ __forceinline__ void build_groups_block(const int* offsets_sm, int E, int bn, GroupRec* groups, int* n_groups,
                                                    int* h_ready, int gmax, int* scratch) {
   if (threadIdx.x == 0) {
-    int acc = E;
+    int acc = 0;
     for (int e = 0; e < E; ++e) {
       scratch[e] = acc;
       const int c = offsets_sm[e + 1] - offsets_sm[e];
-      acc += c > bn ? (c - 1) / bn : 0;
+      acc += (c + bn - 1) / bn;
     }
     scratch[E] = acc;
     n_groups[0] = acc < gmax ? acc : gmax;
@@ -42,19 +39,17 @@ __device__ __forceinline__ void build_groups_block(const int* offsets_sm, int E,
   __syncthreads();
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int c = offsets_sm[e + 1] - offsets_sm[e];
-    const int nt = c > 0 ? (c + bn - 1) / bn : 1;
+    const int nt = (c + bn - 1) / bn;
     const int g0 = scratch[e];
-    for (int j = 0; j < nt; ++j) {
-      const int g = j == 0 ? e : g0 + j - 1;
-      if (g >= gmax) break;
+    for (int j = 0; j < nt && g0 + j < gmax; ++j) {
       GroupRec r;
       r.expert = e;
       r.row0 = offsets_sm[e] + j * bn;
-      r.nrows = max(0, min(bn, c - j * bn));
+      r.nrows = min(bn, c - j * bn);
       r.src = 0;
       r.orow0 = r.row0;
       r.pad[0] = r.pad[1] = r.pad[2] = 0;
-      groups[g] = r;
+      groups[g0 + j] = r;
     }
   }
   for (int g = threadIdx.x; g < gmax; g += blockDim.x) h_ready[g] = 0;

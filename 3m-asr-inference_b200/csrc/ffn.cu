@@ -69,10 +69,6 @@ struct FfnParams {
   int lag;  // groups between a group's phase-1 and phase-2 tiles in the schedule
   int kps;  // k-blocks (of 64) per pipeline stage: one TMA instruction per operand brings all of them
   int p1_only;  // first GEMM only (a single grouped linear): the tile list has no second-GEMM tiles
-  int prefetch;     // 1: a CTA whose first tile is a first-GEMM tile of one of the E static groups (group e = expert e's
-                    //    first token tile, ep_device.cuh:build_groups_block) requests that tile's weights BEFORE the wait
-                    //    for the kernel in front of it: which weights it needs does not depend on the routing
-  int fit_n;        // 1: UMMA N = the group's rows rounded up to 16 instead of the full token tile (single-CTA tiles only)
   int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
   int warm_mma;     // issue one throw-away MMA before the first tile (B200MOE_WARM, default 1)
   // expert parallelism: results go to the source rank's return buffer over peer-mapped memory (NVLink)
@@ -312,10 +308,12 @@ struct Vec4Io<__half> {
 // kTf32: operands are fp32 in memory (x rows, the reference's fp32 FMoELinear weights, h) and the tensor cores read
 // them as TF32 (tcgen05.mma.kind::tf32: 10-bit mantissa, fp32 accumulation) -- the <= 1e-3 flavour of the path.  A
 // 128-byte swizzle row then holds 32 elements instead of 64, i.e. twice the k-blocks and twice the bytes per tile.
-template <typename OutT, bool kTrace, int kCtas, bool kTf32>
+// kMode: 0 = product, 1 = per-event tracing (tools/ffn_trace.py), 2 = the six cross-kernel timeline marks only.
+template <typename OutT, int kMode, int kCtas, bool kTf32>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
            const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const FfnParams p) {
+  constexpr bool kTrace = kMode == 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
@@ -354,8 +352,12 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   if (p.pdl_trigger) ptx::pdl_launch_dependents();  // the next kernel's prologue may overlap this whole kernel
+  // cross-kernel timeline (debug): a variant of its own -- as run-time branches in the product variant the six marks cost
+  // 0.2-0.3 us per layer (A/B on one box), and the per-event tracing variant is ~3 us slower than the product kernel
   auto mark = [&](int i) {
-    if (p.tl != nullptr) p.tl[blockIdx.x * kTimelineMarks + i] = global_ns();
+    if constexpr (kMode != 0) {
+      if (p.tl != nullptr) p.tl[blockIdx.x * kTimelineMarks + i] = global_ns();
+    }
   };
   if (threadIdx.x == 0) mark(0);
   if (warp == 0 && lane == 0) {
@@ -424,71 +426,46 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     }
   }
 
+  // Everything above touched only kernel parameters and on-chip state, so under programmatic dependent launch it
+  // overlaps the tail of the dispatch kernel.  The routing tables, xbuf and every output come after this wait.
+  ptx::pdl_wait();
+  if (threadIdx.x == 0) mark(1);
   // a tile is kCtas x 128 weight rows of one group; this CTA's share is rows (mb * kCtas + rank) * 128 ...
   const int m1 = p.H / (kBlockM * kCtas);
   const int m2 = p.D / (kBlockM * kCtas);
   const int tile0 = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = kCtas == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  constexpr int kKel = kTf32 ? kBlockK / 2 : kBlockK;  // elements per 128-byte k-block
-  const int kb1 = p.D / (kKel * kps);  // pipeline stages per tile of the first GEMM
-  const int kb2 = p.H / (kKel * kps);
-  const uint32_t tx_bytes = (a_stage_bytes + b_stage_bytes) * kCtas;  // both CTAs' tiles land on the leader's barrier
-  // arm a stage: the leader expects the bytes of both CTAs, the other CTA only announces that its loads are issued
-  auto arm = [&](int st, uint32_t bytes) {
-    if (kCtas == 1 || leader) ptx::mbar_arrive_expect_tx(full_bar(st), bytes);
-    else ptx::mbar_arrive_cluster(full_bar(st) & ptx::kPeerBitMask);
-  };
-  // rows [row, ..) x k-blocks [kb * kps, (kb + 1) * kps) of a [K/64][rows][64] view
-  auto load = [&](uint32_t dst, const CUtensorMap* tm, int st, int kb, int row, uint64_t pol) {
-    if constexpr (kCtas == 2)
-      ptx::tma_load_3d_pair(dst, tm, full_bar(st) & ptx::kPeerBitMask, 0, row, kb * kps, pol);
-    else
-      ptx::tma_load_3d(dst, tm, full_bar(st), 0, row, kb * kps, pol);
-  };
-  // The first E groups are static: group e is expert e's first token tile whatever the routing (possibly empty).  A CTA
-  // whose first tile is a first-GEMM tile of such a group knows its weight rows now: they are requested here, under
-  // programmatic dependent launch while the gate / dispatch kernel in front is still running, and the token rows are
-  // added to the same pipeline stages once the routing exists.  `first_static` is uniform over the CTA (and the pair).
-  const bool first_static = p.prefetch != 0 && tile0 < p.E * m1;
-  const int pf = first_static ? (kb1 < stages ? kb1 : stages) : 0;  // stages of the first tile requested ahead
-  const bool skip_b1 = (p.dbg & 8) != 0;
-  auto request_first_weights = [&]() {
-    const int a_row = (tile0 / m1) * p.H + ((tile0 % m1) * kCtas + static_cast<int>(cta_rank)) * kBlockM;
-    for (int kb = 0; kb < pf; ++kb) {
-      arm(kb, skip_b1 ? a_stage_bytes * kCtas : tx_bytes);
-      load(smem_a + kb * a_stage_bytes, &tm_w1, kb, kb, a_row, p.w_policy);
-    }
-  };
-  // prefetch == 1: before the wait.  (Measured: no gain -- the small loads of the routing tables that follow the wait
-  // then queue behind ~100 KB of bulk data on their way into this SM and take 2.5 us instead of 1.)
-  if (warp == 0 && lane == 0 && pf > 0 && p.prefetch == 1) request_first_weights();
-
-  // Everything above touched only kernel parameters, the weights and on-chip state, so under programmatic dependent
-  // launch it overlaps the tail of the dispatch kernel.  The routing tables, xbuf and every output come after this wait.
-  ptx::pdl_wait();
-  if (threadIdx.x == 0) mark(1);
   // The first tile of a CTA is a first-GEMM tile of group tile0 / m1 whenever it lies in the head of the schedule
   // (decode_tile), whatever the number of groups turns out to be: its table entry is requested together with the group
   // count instead of one L2 round trip after it.
   const int g_first = min(tile0 / m1, p.gmax - 1);
   const GroupRec gr_first = p.groups[g_first];
   const int ng = *p.n_groups;
-  // prefetch == 2: right behind the wait -- the table entries above are on their way (requested first, so nothing is
-  // queued in front of them), the weight requests go out before anybody needs the answers.
-  if (warp == 0 && lane == 0 && pf > 0 && p.prefetch == 2) request_first_weights();
-  const int m1_flags = p.H / kBlockM;  // every CTA publishes its own 128-row slice of h: one bit per slice and group
-  const uint32_t h_full = m1_flags >= 32 ? 0xffffffffu : (1u << m1_flags) - 1u;
+  const int m1_flags = p.H / kBlockM;  // every CTA publishes its own 128-row slice of h: flags per group
   const int lag = p.p1_only ? ng : min(p.lag, ng);
   const int n_tiles = p.p1_only ? ng * m1 : ng * (m1 + m2);  // (p1_only: lag == ng puts every tile in the head)
-  // Tiles of a group without rows (a static group of an expert nobody chose) are skipped by every role -- except a first
-  // tile whose weights are already on their way: that one runs as an ordinary tile that stores nothing.
-  auto skip_tile = [&](int t, int nrows) { return nrows <= 0 && !(first_static && t == tile0); };
+  constexpr int kKel = kTf32 ? kBlockK / 2 : kBlockK;  // elements per 128-byte k-block
+  const int kb1 = p.D / (kKel * kps);  // pipeline stages per tile of the first GEMM
+  const int kb2 = p.H / (kKel * kps);
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t tx_bytes = (a_stage_bytes + b_stage_bytes) * kCtas;  // both CTAs' tiles land on the leader's barrier
+      // arm a stage: the leader expects the bytes of both CTAs, the other CTA only announces that its loads are issued
+      auto arm = [&](int st, uint32_t bytes) {
+        if (kCtas == 1 || leader) ptx::mbar_arrive_expect_tx(full_bar(st), bytes);
+        else ptx::mbar_arrive_cluster(full_bar(st) & ptx::kPeerBitMask);
+      };
+      // rows [row, ..) x k-blocks [kb * kps, (kb + 1) * kps) of a [K/64][rows][64] view
+      auto load = [&](uint32_t dst, const CUtensorMap* tm, int st, int kb, int row, uint64_t pol) {
+        if constexpr (kCtas == 2)
+          ptx::tma_load_3d_pair(dst, tm, full_bar(st) & ptx::kPeerBitMask, 0, row, kb * kps, pol);
+        else
+          ptx::tma_load_3d(dst, tm, full_bar(st), 0, row, kb * kps, pol);
+      };
       Tracer<kTrace> tr(p, 0);
       tr.sync();
       tr.rec(-1, kEvKernelStart);
@@ -498,7 +475,6 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       for (int t = tile0; t < n_tiles; t += tile_step) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
         const GroupRec gr = (t == tile0 && tl.g == g_first) ? gr_first : p.groups[tl.g];
-        if (skip_tile(t, gr.nrows)) continue;
         tr.rec(t, kEvProdTileStart);
         const CUtensorMap* tm_a = tl.phase == 1 ? &tm_w1 : &tm_w2;
         const CUtensorMap* tm_b = tl.phase == 1 ? &tm_x : &tm_h;
@@ -510,58 +486,35 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         // how much of the time is the B operand's L2 -> SM traffic?), 32 = no wait for h (what does the hand-off cost?)
         const bool skip_b = (tl.phase == 1 && (p.dbg & 8)) || (tl.phase == 2 && (p.dbg & 16));
         const uint32_t st_bytes = skip_b ? a_stage_bytes * kCtas : tx_bytes;
-        // h of a group arrives in 128-wide slices, one per first-GEMM tile, each announced by its own bit: a pipeline
-        // stage of the second GEMM needs the slice(s) its k-blocks fall into, not the whole row
-        uint32_t h_have = (tl.phase == 2 && !(p.dbg & 32)) ? static_cast<uint32_t>(ptx::ld_acquire_gpu(p.h_ready + tl.g))
-                                                            : h_full;
-        auto stage_slices = [&](int kb) {  // bits of the h slices stage kb of a second-GEMM tile reads
-          const int lo = (kb * kps * kKel) / kBlockM, hi = ((kb + 1) * kps * kKel - 1) / kBlockM;
-          return (hi >= 31 ? 0xffffffffu : (2u << hi) - 1u) & ~((1u << lo) - 1u);
-        };
-        auto wait_slices = [&](int kb) {
-          const uint32_t need = stage_slices(kb);
-          if ((h_have & need) == need) return;
-          while (true) {
-            h_have = static_cast<uint32_t>(ptx::ld_acquire_gpu(p.h_ready + tl.g));
-            if ((h_have & need) == need) break;
-            __nanosleep(32);
-          }
-          ptx::fence_proxy_async_all();  // generic-proxy writes of h -> async-proxy (TMA) reads
-        };
-        const bool dep_pending = (tl.phase == 2 && h_have != h_full) || (tl.phase == 1 && !rows_ready);
-        if (tl.phase == 2) ptx::fence_proxy_async_all();  // the slices seen so far were written through the generic proxy
-        const bool ahead = t == tile0 && pf > 0;  // this tile's first `pf` weight stages went out before the wait
-        if (dep_pending || ahead) {
+        const bool dep_pending =
+            (tl.phase == 2 && !(p.dbg & 32) && ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) ||
+            (tl.phase == 1 && !rows_ready);
+        if (tl.phase == 2 && !dep_pending) ptx::fence_proxy_async_all();  // h was written through the generic proxy
+        if (dep_pending) {
           // The W2 tiles do not depend on h: fill the ring with them first, then wait until every phase-1 tile of this
           // group has published its slice of h and add the h tiles to the same stages (one full barrier per stage
           // expects both).  (Only when h is in fact late: in steady state this order would hold back the first h tile
           // until the whole ring has been re-filled with weights, a ~1.5 us bubble per tile.)
-          pre = ahead ? pf : (nkb < stages ? nkb : stages);
+          pre = nkb < stages ? nkb : stages;
           const int stage0 = stage;
           for (int kb = 0; kb < pre; ++kb) {
-            if (!ahead) {
-              ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-              arm(stage, st_bytes);
-              load(smem_a + stage * a_stage_bytes, tm_a, stage, kb, a_row, p.w_policy);
-            }
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            arm(stage, st_bytes);
+            load(smem_a + stage * a_stage_bytes, tm_a, stage, kb, a_row, p.w_policy);
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          if (!dep_pending || tl.phase == 2) {
-            // (nothing to wait for here: the token rows of the stages requested ahead are missing, or h slices that are
-            // waited for stage by stage below)
+          if (tl.phase == 2) {
+            while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) __nanosleep(32);
           } else {
             ep_wait_counters_1t(p.ep_peers, p.ep_peers.lay.arrive, kEpCtrlArrive, kEpErrDispatchTimeout);
             rows_ready = true;
-            // generic-proxy writes of the pushed rows -> async-proxy (TMA) reads.  (Not for rows a finished kernel
-            // wrote: the dependency wait covers every proxy, and this fence would sit out the weight loads in flight.)
-            ptx::fence_proxy_async_all();
           }
+          ptx::fence_proxy_async_all();  // generic-proxy writes of h / of the pushed rows -> async-proxy (TMA) reads
           int s2 = stage0;
           for (int kb = 0; kb < pre; ++kb) {
-            if (tl.phase == 2) wait_slices(kb);
             if (!skip_b) load(smem_b + s2 * b_stage_bytes, tm_b, s2, kb, b_row, ptx::kEvictLast);
             if (++s2 == stages) s2 = 0;
           }
@@ -572,7 +525,6 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           if (t < tile0 + 2 * tile_step) tr.rec(kb, kEvProdSlotFree);
           arm(stage, st_bytes);
           load(smem_a + stage * a_stage_bytes, tm_a, stage, kb, a_row, p.w_policy);
-          if (tl.phase == 2) wait_slices(kb);
           if (!skip_b) load(smem_b + stage * b_stage_bytes, tm_b, stage, kb, b_row, ptx::kEvictLast);
           if (++stage == stages) {
             stage = 0;
@@ -594,27 +546,13 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       uint32_t phase = 0;
       int it = 0;
       Tracer<kTrace> tr(p, 1);
-      // rows of the next tile's group, requested one tile ahead (a global load under full memory load takes 1-2 us)
-      long long mma_wait_cyc = 0, mma_issue_cyc = 0, acc_wait_cyc = 0;  // timeline only
-      int nrows_next = tile0 < n_tiles ? (decode_tile(tile0, ng, lag, m1, m2).g == g_first ? gr_first.nrows
-                                          : p.groups[decode_tile(tile0, ng, lag, m1, m2).g].nrows) : 0;
-      for (int t = tile0; t < n_tiles; t += tile_step) {
+      for (int t = tile0; t < n_tiles; t += tile_step, ++it) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
-        const int nrows = nrows_next;
-        if (t + tile_step < n_tiles) nrows_next = p.groups[decode_tile(t + tile_step, ng, lag, m1, m2).g].nrows;
-        if (skip_tile(t, nrows)) continue;
-        // UMMA N: the tile's rows rounded up to 16 (columns past them are never stored); CTA pairs split the token tile
-        // between the two CTAs by rows, so there N stays the full tile
-        const uint32_t idesc_t = (kCtas == 1 && p.fit_n)
-            ? ptx::make_idesc(kTf32 ? 2u : 1u, kBlockM, static_cast<uint32_t>(min(p.bn, max(16, (nrows + 15) & ~15))))
-            : idesc;
         const int nkb = tl.phase == 1 ? kb1 : kb2;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        const long long ca = p.tl ? clock64() : 0;
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
-        if (p.tl) acc_wait_cyc += clock64() - ca;
         tr.rec(t, kEvMmaAccFree);
         const uint32_t tmem_d = tmem_base + as * kAccStride;
         if ((p.dbg & 128) && t == tile0) {
@@ -623,11 +561,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           for (int s2 = 1; s2 < stages && s2 < nkb; ++s2) ptx::mbar_wait(full_bar(s2), 0);
         }
         for (int kb = 0; kb < nkb; ++kb) {
-          const long long c0 = p.tl ? clock64() : 0;
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const long long c1 = p.tl ? clock64() : 0;
-          mma_wait_cyc += c1 - c0;
           if (kb == 0) tr.rec(t, kEvMmaFirstData);
           if (kb == 0 && it == 0) mark(2);
           if (t < tile0 + 2 * tile_step) tr.rec(kb, kEvMmaStageData);
@@ -638,17 +573,15 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance both descriptors by k * 16 elements * 2 B = 32 B -> +2 in 16-byte units
               if constexpr (kTf32)
-                ptx::umma_tf32_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc_t, (kb | j | k) != 0 ? 1u : 0u);
+                ptx::umma_tf32_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
               else if constexpr (kCtas == 2)
-                ptx::umma_f16_ss_pair(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc_t, (kb | j | k) != 0 ? 1u : 0u);
+                ptx::umma_f16_ss_pair(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
               else
-                ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc_t, (kb | j | k) != 0 ? 1u : 0u);
+                ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
               if (kTrace && t == tile0 && kb == 0) tr.rec(j * 4 + k, kEvMmaInstr);
             }
           }
           if (t < tile0 + 2 * tile_step) tr.rec(kb, kEvMmaStageIssued);
-          const long long c2 = p.tl ? clock64() : 0;
-          mma_issue_cyc += c2 - c1;
           if constexpr (kCtas == 2) {
             // the slot is free in BOTH CTAs once these MMAs have read it; both epilogues get the accumulator signal
             ptx::umma_commit_pair(empty_bar(stage), 0x3);
@@ -661,17 +594,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
             stage = 0;
             phase ^= 1u;
           }
-          if (p.tl) acc_wait_cyc += clock64() - c2;  // (timeline: the commits, folded into the accumulator-wait counter)
         }
         tr.rec(t, kEvMmaIssued);
-        ++it;
       }
       mark(4);
-      if (p.tl != nullptr) {  // (cycles, not ns: data wait | MMA issue in marks 6 / 7; accumulator wait folded into 6's top half)
-        p.tl[blockIdx.x * kTimelineMarks + 6] = static_cast<unsigned long long>(mma_wait_cyc) |
-                                                (static_cast<unsigned long long>(acc_wait_cyc) << 32);
-        p.tl[blockIdx.x * kTimelineMarks + 7] = static_cast<unsigned long long>(mma_issue_cyc);
-      }
     }
   } else if (warp == 3) {
     // ============================ publisher (one thread) ============================
@@ -683,11 +609,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
       for (int t = tile0; t < n_tiles; t += tile_step) {
         const Tile tl = decode_tile(t, ng, lag, m1, m2);
         if (tl.phase != 1) continue;
-        if (skip_tile(t, p.groups[tl.g].nrows)) continue;
         const int slot = k & 1;
         ptx::mbar_wait(pfull_bar(slot), (k >> 1) & 1);  // acquire.cta: the four epilogue warps' h stores
         ptx::fence_proxy_async_all();                   // generic-proxy writes -> the consumers' TMA reads
-        ptx::red_release_gpu_or(p.h_ready + tl.g, 1 << (tl.mb * kCtas + static_cast<int>(cta_rank)));
+        ptx::red_release_gpu_add(p.h_ready + tl.g, 1);
         ptx::mbar_arrive(pempty_bar(slot));
         tr.rec(t, kEvEpiPublished);
         ++k;
@@ -716,15 +641,14 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
     int k1 = 0;  // phase-1 tiles so far (publisher hand-off ring)
     Tracer<kTrace> tr(p, 2);
     const bool tracer_thread = et == 0;
-    for (int t = tile0; t < n_tiles; t += tile_step) {
+    for (int t = tile0; t < n_tiles; t += tile_step, ++it) {
       const Tile tl = decode_tile(t, ng, lag, m1, m2);
       const GroupRec gr = p.groups[tl.g];
-      if (skip_tile(t, gr.nrows)) continue;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const int feat0 = (tl.mb * kCtas + static_cast<int>(cta_rank)) * kBlockM;  // first weight row of this CTA's part
-      const int nrows = (p.dbg & 256) ? 0 : gr.nrows;  // (experiment: 256 = epilogues do nothing)
+      const int nrows = gr.nrows;
       if (tl.phase == 1) {
         const float bias = p.b1 ? p.b1[static_cast<size_t>(gr.expert) * p.H + feat0 + feat_l] : 0.0f;
         const float hbias = 0.5f * bias;
@@ -1032,7 +956,6 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
           if (tracer_thread) tr.rec(t, kEvEpiStored);
         }
       }
-      ++it;
     }
   }
 
@@ -1105,10 +1028,13 @@ cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUten
   const size_t smem = smem_bytes_for(a.bn / kCtas, p.kps, p.stages);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_kernel<OutT, false, kCtas, kTf32>,
+    cudaError_t e = cudaFuncSetAttribute(ffn_kernel<OutT, 0, kCtas, kTf32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(ffn_kernel<OutT, true, kCtas, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(ffn_kernel<OutT, 1, kCtas, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(ffn_kernel<OutT, 2, kCtas, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -1137,9 +1063,11 @@ cudaError_t launch_typed(const FfnLaunch& a, const CUtensorMap& tw1, const CUten
   cfg.numAttrs = na;
   cudaError_t e;
   if (p.trace != nullptr)
-    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, true, kCtas, kTf32>, tw1, tw2, tx, th, p);
+    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, 1, kCtas, kTf32>, tw1, tw2, tx, th, p);
+  else if (p.tl != nullptr)
+    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, 2, kCtas, kTf32>, tw1, tw2, tx, th, p);
   else
-    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, false, kCtas, kTf32>, tw1, tw2, tx, th, p);
+    e = cudaLaunchKernelEx(&cfg, ffn_kernel<OutT, 0, kCtas, kTf32>, tw1, tw2, tx, th, p);
   count_launch();
   return e;
 }
@@ -1163,7 +1091,6 @@ unsigned long long* next_timeline_slot(int kind) {
 }
 int timeline_kind(int slot) { return slot >= 0 && slot < g_tl_used ? g_tl_kind[slot] : 0; }
 
-
 void set_ffn_trace(void* dev_buf, int records_per_cta) {
   g_trace_buf = dev_buf;
   g_trace_cap = records_per_cta;
@@ -1178,7 +1105,6 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
   if (a.D % kBlockM != 0 || a.H % kBlockM != 0) return cudaErrorInvalidValue;
   if (a.p1_only && (a.tf32 || a.ep != nullptr || a.fused)) return cudaErrorInvalidValue;
   if (a.bn % 16 != 0 || a.bn < 16 || a.bn > 256) return cudaErrorInvalidValue;
-  if (!a.p1_only && a.H / kBlockM > 32) return cudaErrorInvalidValue;  // one readiness bit per 128-wide slice of h
   if (a.fused && a.top_k != 1) return cudaErrorInvalidValue;
   const bool tf32 = a.tf32 != 0;
   if (tf32 && (a.out_dtype != B200MOE_F32 || a.ep != nullptr)) return cudaErrorInvalidValue;
@@ -1265,28 +1191,10 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
       return (v && *v) ? std::atoi(v) : 1;
     }();
     p.warm_mma = warm;
-    static const int prefetch = [] {
-      const char* v = std::getenv("B200MOE_FFN_PREFETCH");
-      return (v && *v) ? std::atoi(v) : 0;  // (1 and 2 measured: no gain at 3 200 tokens, a loss at 50 -- see DESIGN.md)
-    }();
-    static const int fit_n = [] {
-      const char* v = std::getenv("B200MOE_FIT_N");
-      return (v && *v) ? std::atoi(v) : 1;
-    }();
-    p.prefetch = prefetch;
-    p.fit_n = fit_n;
   }
   // about one token tile per expert: every weight tile is read exactly once, so it can leave L2 right after
   p.w_policy = (static_cast<long long>(a.n_rows) <= static_cast<long long>(a.E) * a.bn) ? ptx::kEvictFirst
                                                                                       : ptx::kEvictNormal;
-  {
-    static const int wpol = [] {  // experiments: 1 = weights with the normal L2 policy, 2 = evict-last
-      const char* v = std::getenv("B200MOE_WPOL");
-      return (v && *v) ? std::atoi(v) : 0;
-    }();
-    if (wpol == 1) p.w_policy = ptx::kEvictNormal;
-    if (wpol == 2) p.w_policy = ptx::kEvictLast;
-  }
   p.trace = static_cast<uint4*>(g_trace_buf);
   p.trace_cap = g_trace_cap;
   p.tl = next_timeline_slot(2);

@@ -185,13 +185,6 @@ struct RouteParams {
   const float* ln_c;   // c1[32], c0[32] behind the pre-scaled packed router (b200moe_pack_router_ln)
   float ln_eps;
   int warm_mma;
-  // DRAM -> L2 prefetch of the layer's expert weights, spread over the CTAs and issued before the dependency wait: this
-  // kernel is a latency chain over ~3 KiB per token, HBM is otherwise idle while it runs, and the expert kernel that
-  // follows then streams its weights out of L2 (measured: 17 TB/s with 32 KiB TMA instructions against 7 TB/s from HBM)
-  const uint8_t* pf_ptr[2];
-  unsigned long long pf_bytes[2];
-  int pdl_trigger;  // 1: release the dependent (expert) kernel at the start, so that its CTAs set themselves up and request
-                    //    their first weight tiles on every SM this grid leaves free or vacates (ffn.cu, `prefetch`)
   uint4* trace;  // debug timeline: 16 records per CTA {event, clock64 lo, hi, -}; slots 14 / 15 hold %globaltimer
   unsigned long long* tl;  // cross-kernel timeline slot of this launch (common.cuh: set_timeline) or null
 };
@@ -242,27 +235,10 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   if ((smem_base & 1023u) != 0) __trap();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (p.pdl_trigger) ptx::pdl_launch_dependents();
-  auto mark = [&](int i) {
+  auto mark = [&](int i) {  // cross-kernel timeline (debug; off = one predicated branch)
     if (p.tl != nullptr) p.tl[blockIdx.x * kTimelineMarks + i] = ptx::globaltimer_ns();
   };
   if (threadIdx.x == 0) mark(0);
-  if (warp == 7) {  // (a warp with nothing to do before the wait in either variant)
-    constexpr unsigned kPfChunk = 16384;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const unsigned long long n = p.pf_bytes[r];
-      if (p.pf_ptr[r] == nullptr || n == 0) continue;
-      const unsigned long long nchunks = (n + kPfChunk - 1) / kPfChunk;
-      for (unsigned long long c = static_cast<unsigned long long>(blockIdx.x) * 32 + lane; c < nchunks;
-           c += static_cast<unsigned long long>(gridDim.x) * 32) {
-        const unsigned long long off = c * kPfChunk;
-        const unsigned long long left = n - off;
-        const unsigned bytes = left < kPfChunk ? static_cast<unsigned>(left & ~15ull) : kPfChunk;
-        if (bytes) ptx::prefetch_l2_bulk(p.pf_ptr[r] + off, bytes);
-      }
-    }
-  }
   const uint32_t bar_base = smem_base + kRSlots * kRSlot;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kRSlots + s); };
@@ -363,16 +339,18 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           }
           // Programmatic dependent launch: the embed half of the router GEMM (embed and the router are constants) runs
           // while the previous layer's FFN kernel is still draining; x, its output, is only touched after this wait.
-          if (!is_e && !waited) {
-            ptx::pdl_wait();
-            mark(1);
-            waited = true;
-          }
           ptx::mbar_wait(empty_bar(slot), phase ^ 1u);
           ptx::mbar_arrive_expect_tx(full_bar(slot), static_cast<uint32_t>(nkb) * (kRABlk + kRBBlk));
           const uint32_t sa = smem_base + slot * kRSlot;
           // router k-blocks of this part: rows 0..63 of the packed router, k-blocks [kb0, kb0 + nkb)
           ptx::tma_load_3d(sa, is_e ? &tm_we : &tm_wx, full_bar(slot), 0, 0, is_e ? 0 : kb_e, ptx::kEvictLast);
+          // (The x half of the router is a constant as well: it is on its way before the wait, only the 32 KiB of token
+          // rows are requested behind it.)
+          if (!is_e && !waited) {
+            ptx::pdl_wait();
+            mark(1);
+            waited = true;
+          }
           // the tile's 32 tokens, all k-blocks of the part
           if (is_e)
             ptx::tma_load_3d(sa + kRSlotA, &tm_e, full_bar(slot), 0, t * kTok, 0, ptx::kEvictFirst);
@@ -828,31 +806,28 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       if (p.offsets_out) p.offsets_out[e] = s_off[e];
     }
     if (!kEp) {
-      // FFN group table (layout of build_groups_block, ep_device.cuh): group e < E = expert e's first token tile, possibly
-      // empty; the other tiles of experts with more than bn rows follow from index E on
+      // FFN group table: expert e contributes ceil(count / bn) groups, in expert order
       if (threadIdx.x == 0) {
-        int acc = E;
+        int acc = 0;
         for (int e = 0; e < E; ++e) {
           s_scratch[e] = acc;
-          acc += s_total[e] > p.bn ? (s_total[e] - 1) / p.bn : 0;
+          acc += (s_total[e] + p.bn - 1) / p.bn;
         }
-        p.n_groups[0] = acc < p.gmax ? acc : p.gmax;
+        p.n_groups[0] = acc;
       }
       __syncthreads();
       for (int e = threadIdx.x; e < E; e += blockDim.x) {
         const int cnt = s_total[e];
-        const int nt = cnt > 0 ? (cnt + p.bn - 1) / p.bn : 1;
+        const int nt = (cnt + p.bn - 1) / p.bn;
         for (int j = 0; j < nt; ++j) {
-          const int g = j == 0 ? e : s_scratch[e] + j - 1;
-          if (g >= p.gmax) break;
           GroupRec r;
           r.expert = e;
           r.row0 = s_off[e] + j * p.bn;
-          r.nrows = max(0, min(p.bn, cnt - j * p.bn));
+          r.nrows = min(p.bn, cnt - j * p.bn);
           r.src = 0;
           r.orow0 = r.row0;
           r.pad[0] = r.pad[1] = r.pad[2] = 0;
-          p.groups[g] = r;
+          p.groups[s_scratch[e] + j] = r;
         }
       }
       for (int g = threadIdx.x; g < p.gmax; g += blockDim.x) p.h_ready[g] = 0;
@@ -937,8 +912,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
                          float* score, int bn, const RouteWs& ws, int* counts_out, int* offsets_out, int* mapping_out,
                          bf16* xbuf, void* drop_out, const void* drop_residual, cudaStream_t stream, const EpPeers* ep,
                          bool ep_fold_wait, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* ln_c,
-                         int ep_mode, int ep_ffn_ctas, const void* pf0, size_t pf0_bytes, const void* pf1,
-                         size_t pf1_bytes) {
+                         int ep_mode, int ep_ffn_ctas) {
   const int S = B * T;
   if (embed == nullptr) Demb = 0;
   if (!route_supported(S, D, Demb, E, 1, B200MOE_BF16)) return cudaErrorInvalidValue;
@@ -1005,13 +979,6 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
     return (v && *v) ? std::atoi(v) : 1;
   }();
   p.warm_mma = warm;
-  p.pdl_trigger = (pdl_trigger() & kPdlGate) ? 1 : 0;
-  // (both weight tensors have to fit L2 next to the activations: bf16 3M-ASR layers are 64 MiB, TF32 ones are not)
-  const bool pf = prefetch_mode() != 0 && pf0_bytes + pf1_bytes <= (size_t(96) << 20);
-  p.pf_ptr[0] = pf ? static_cast<const uint8_t*>(pf0) : nullptr;
-  p.pf_ptr[1] = pf ? static_cast<const uint8_t*>(pf1) : nullptr;
-  p.pf_bytes[0] = pf && pf0 ? pf0_bytes : 0;
-  p.pf_bytes[1] = pf && pf1 ? pf1_bytes : 0;
   p.trace = static_cast<uint4*>(g_route_trace);
   p.tl = next_timeline_slot(1);
   EpPeers epv{};

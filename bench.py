@@ -459,6 +459,49 @@ class Case:
         ops.profile_enable(False)
         return {k: (ms[k] / calls[k] * 1e3 if calls.get(k) else None) for k in ms}
 
+    def kernel_spans(self):
+        """In-graph kernel durations from the kernels' own %globaltimer marks (b200moe_debug_timeline): a second graph of
+        the same step is captured with the marks on and replayed; span = first CTA start -> last CTA end, averaged over
+        the launches of one replay.  Unlike CUDA events around a launch it holds no launch gap, and unlike an eager run
+        it sees the kernel next to its real neighbours (programmatic dependent launch).  Single GPU, graph mode only."""
+        b, torch = self.b, self.b.torch
+        if not self.use_graph or b.world != 1:
+            return None
+        lib = importlib.import_module(PKG + "._lib").load()
+        n_slots = self.launches_per_step + 4
+        tl = torch.zeros(n_slots, 148, 8, dtype=torch.int64, device=b.dev)
+        lib.b200moe_debug_timeline(tl.data_ptr(), n_slots)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=b.stream):
+                self.step()
+            kinds = [lib.b200moe_debug_timeline_kind(i) for i in range(n_slots)]
+        finally:
+            lib.b200moe_debug_timeline(None, 0)
+        with torch.cuda.stream(b.stream):
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            tl.zero_()
+            torch.cuda.synchronize()
+            g.replay()
+            torch.cuda.synchronize()
+        t = tl.cpu().numpy().astype("float64")
+        spans = {1: [], 2: []}
+        for i, k in enumerate(kinds):
+            if k in spans:
+                a = t[i]
+                used = a[:, 0] > 0
+                if used.any() and (a[used, 5] > 0).all():
+                    spans[k].append((a[used, 5].max() - a[used, 0].min()) / 1e3)
+        del g
+        out = {}
+        for k, name in ((1, "route"), (2, "expert_ffn")):
+            if len(spans[k]) > 2:
+                v = sorted(spans[k][1:])   # (the first launch of a replay has no predecessor to overlap with)
+                out[name] = {"mean_us": sum(v) / len(v), "median_us": v[len(v) // 2], "launches": len(v)}
+        return out or None
+
     def nonempty_experts(self):
         """Mean number of LOCAL experts per layer that receive at least one row (their weights are what a layer call
         has to stream): from one untimed pass with the routing returned."""
@@ -843,7 +886,16 @@ def main():
     case.check_status()
 
     nonempty = case.nonempty_experts()
+    spans = None if os.environ.get("B200MOE_AB_OLD_LIB") else case.kernel_spans()
     roofline, stages, layer_roofline = rooflines(b, case, stage_us, ms_step, nonempty)
+    if roofline is not None and spans and "expert_ffn" in spans:
+        # the same algorithmic bytes / flops over the kernel's own in-graph duration (see Case.kernel_spans)
+        us = spans["expert_ffn"]["mean_us"]
+        work = roofline.get("algorithmic_bytes_per_launch") or roofline.get("algorithmic_flops_per_launch")
+        scale = 1e3 if roofline["bound"] == "hbm" else 1e6
+        roofline["in_graph_span_us"] = us
+        roofline["achieved_in_graph"] = work / us / scale
+        roofline["frac_in_graph"] = work / us / scale / roofline["peak"]
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample (rank 0, N = 1 only)
     cpu_baseline = None
@@ -892,6 +944,7 @@ def main():
             "stage_us_per_layer": stage_us,
             "roofline": roofline,
             "roofline_stages": stages,
+            "kernel_spans_in_graph": spans,
             "layer_roofline": layer_roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e,

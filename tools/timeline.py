@@ -109,12 +109,6 @@ def main():
         rw = rw[rw > 0]
         route = f"{(np.median(r[ru, 5]) - np.median(rw)) / 1e3:7.2f} (max end {(ref - np.median(rw)) / 1e3:6.2f})" if rw.size else "-"
         print(f"{i:>8} " + " ".join(cols) + f" {route:>22}")
-        raw = tl_raw[i][used]
-        w = (raw[:, 6] & 0xFFFFFFFF).astype(np.float64) / 1.85e3
-        aw = (raw[:, 6] >> 32).astype(np.float64) / 1.85e3
-        iss = raw[:, 7].astype(np.float64) / 1.85e3
-        print(f"{'':>8} MMA thread, us at 1.85 GHz (median / max over CTAs): waiting for operand data {np.median(w):5.2f}/{w.max():5.2f}, "
-              f"issuing MMAs {np.median(iss):5.2f}/{iss.max():5.2f}, waiting for a free accumulator {np.median(aw):5.2f}/{aw.max():5.2f}")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.save(os.path.join(ROOT, "gpurun_out", f"timeline_{S}.npy"), t)
 
