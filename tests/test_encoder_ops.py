@@ -62,3 +62,32 @@ def test_rel_pos_encoding(ops, dtype):
     out, pos = ops.rel_pos_encoding(x.cuda(), pe.cuda(), math.sqrt(512))
     assert torch.equal(pos.cpu(), pe[:50])
     torch.testing.assert_close(out.float().cpu(), x.float() * math.sqrt(512), rtol=TOL[dtype], atol=0)
+
+
+def test_plugin_registry_serves_the_encoder_plugins(ops):
+    """The reference's plugin names / creator fields (TRTAPI++/plugin/*/..._plugin.cpp) through the registry mirror."""
+    plugin = __import__("conftest").pkg("plugin")
+    reg = plugin.PluginRegistry()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 6, 40, generator=g).cuda()
+    lens = torch.tensor([40, 13], dtype=torch.int32).cuda()
+    mf = reg.get_plugin_creator("MaskedFillPluginDynamic", "1", "").create_plugin("m", {"data_type": 0, "fill": 0.0})
+    out = mf.enqueue([x.view(2, 6, 1, 40), lens])
+    assert out.shape == (2, 6, 1, 40) and float(out[1, :, :, 13:].abs().max()) == 0.0 and torch.equal(out[0], x.view(2, 6, 1, 40)[0])
+    glu = reg.get_plugin_creator("GluPluginDynamic", "1", "").create_plugin("g", {"data_type": 0, "axis_dim": 1})
+    torch.testing.assert_close(glu.enqueue([x.view(2, 6, 1, 40)]), torch.nn.functional.glu(x.view(2, 6, 1, 40), 1),
+                               rtol=2e-6, atol=1e-7)
+    sm = reg.get_plugin_creator("AttMaskedSoftmaxPluginDynamic", "1", "").create_plugin("s", {"data_type": 0, "scale": 0.125})
+    p = sm.enqueue([x, lens])          # [batch, seq_len, dim] as the reference's enqueue reads it
+    assert p.shape == x.shape and float(p[1, :, 13:].abs().max()) == 0.0
+    torch.testing.assert_close(p[1, :, :13].sum(-1), torch.ones(6, device="cuda"), rtol=1e-5, atol=1e-6)
+    rp = reg.get_plugin_creator("RelPositionalEncodingPluginDynamic", "1", "").create_plugin(
+        "r", {"data_type": 0, "scale": 2.0, "max_len": 64, "dim": 40, "streaming": 0})
+    y, pos = rp.enqueue([x])
+    torch.testing.assert_close(y, x * 2.0)
+    assert pos.shape == (6, 40) and float(pos[0, 1]) == 1.0 and float(pos[0, 0]) == 0.0
+    ln = reg.get_plugin_creator("LayerNormPluginDynamic", "1", "").create_plugin("l", {"data_type": 0, "eps": 1e-12, "dim": 40})
+    gam, bet = torch.ones(40).cuda(), torch.zeros(40).cuda()
+    torch.testing.assert_close(ln.enqueue([x, gam, bet]), torch.nn.functional.layer_norm(x, (40,), gam, bet, 1e-12),
+                               rtol=1e-4, atol=1e-5)
+    assert reg.get_plugin_creator("GluPluginDynamic", "2", "") is None
