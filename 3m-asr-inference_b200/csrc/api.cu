@@ -797,7 +797,7 @@ static int ep_forward_impl(b200moe_ep_ctx* c, const b200moe_layer_args* a, void*
   const bool tc_gate = a->Wr_packed != nullptr && gate_tc_supported(a->D, Demb, a->E, a->top_k, a->dtype);
   // merged layout: every local expert's rows are contiguous whatever rank they came from, about Sk / E_local each
   const int bn = choose_bn(Sk, ep.E_local);
-  const int gmax = max_groups(rows_cap, ep.E_local, bn);
+  const int gmax = max_groups(rows_cap, ep.world * ep.E_local, bn);  // one run of tiles per (local expert, source rank)
   const bool one_call = (stages & 11) == 11;   // gate, scatter and the expert kernel in this call
   const bool route = one_call && tc_gate && route_supported(S, a->D, Demb, a->E, a->top_k, a->dtype);
   void* drop_out = fold ? a->out : nullptr;     // padded / dropped tokens: output row = residual row, written locally

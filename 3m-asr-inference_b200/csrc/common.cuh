@@ -39,11 +39,13 @@ constexpr int kMaxEpWorld = 8;
 // Protocol of one layer call `seq` on rank r (W ranks, E_local experts per rank, E = W * E_local):
 //   1. gate -> r's per-expert counts for ALL E experts.  One CTA stores them into cnt_all[r][:] of EVERY rank, each as a
 //      self-validating word (seq << 32 | count).
-//   2. every CTA of the dispatch / route kernel waits until all W x E words carry `seq` (local memory) and derives, for each expert,
-//      the row of the OWNER's receive buffer where r's first row for that expert belongs: the owner's rows are laid out
-//      expert-major, source-rank-major inside an expert, stable inside a source -- i.e. every local expert's rows are
-//      CONTIGUOUS whatever rank they came from, so the expert kernel runs full token tiles per expert instead of one
-//      tile per (expert, source) (functions.py:37-50's count exchange, without the host).
+//   2. every owner keeps one segment of `cap` receive rows per SOURCE rank; a source lays its rows for an owner out in its
+//      own expert order, so where r's rows belong follows from r's own offsets: nothing is waited for before the rows
+//      leave.  (An earlier layout merged the sources' rows of an expert into contiguous rows: full token tiles, but every
+//      rank's counts had to arrive before the first row could leave -- a system-scope round trip in front of the pushes.)
+//      The counts are needed by the owner only, for its expert kernel's group table: one run of token tiles per (local
+//      expert, source rank), built by one CTA at the end of the dispatch / route kernel (functions.py:37-50's count
+//      exchange, without the host and off the senders' path).
 //   3. rows -> recv_x[row] and 8 bytes of routing data -> meta[row] on the owner; every CTA: fence.acq_rel.sys, then one
 //      remote increment of arrive[r] on every rank ("one more CTA of r has delivered").  How many CTAs there will have been
 //      after this call travels with the counts (cumulative, never reset), so nobody has to be the last.
@@ -67,7 +69,7 @@ struct EpLayout {
                      //   this call.  Self-validating words: no flag, no fence behind them
   size_t meta;       // int2 [world * cap]: per received row {residual? << 31 | source rank << 27 | index at the source,
                      //   gate score bits}; index = the token (fold) or the source's expert-order row (ret_y + ep_combine)
-  size_t recv_x;     // bf16 [world * cap][D]: received rows, expert-major / source-major / stable
+  size_t recv_x;     // bf16 [world][cap][D]: received rows, one segment per source rank, in the source's expert order
   size_t ret_y;      // bf16 [cap][D]: expert outputs for this rank's own entries, in its expert order (un-folded path)
   size_t out_heap;   // bf16 [2][cap][D]: two layer-output buffers inside the symmetric heap (the folded path writes the
                      //   source rank's output rows remotely, so `out` has to live where the peers can reach it)

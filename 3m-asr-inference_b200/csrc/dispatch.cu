@@ -110,7 +110,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
                         const InT* __restrict__ drop_residual, int early_trigger, const EpPeers ep,
                         int ep_fold_wait, int ep_mode, int ep_send, int ep_ffn_ctas) {
   constexpr int kWarps = kDispatchThreads / 32;
-  constexpr int kRowsPerBatch = 4;            // rows a warp keeps in flight during the copy
+  constexpr int kRowsPerBatch = 8;            // rows a warp keeps in flight during the copy (x 16 B per lane: 4 KiB per warp and pass)
   constexpr int kMaxParts = 8;
   // All shared memory is dynamic and sized by E (about 4.6 KB at E = 32), so that a CTA of the expert-FFN kernel
   // (launched early under programmatic dependent launch, ~211 KB) fits on the same SM beside a dispatch CTA.
@@ -181,7 +181,7 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
   if (kEp) {
     ep_seq = ep_ctrl(ep)[0] + 1;   // (only this kernel's last CTA advances the word, after every CTA has read it)
     if (blockIdx.x == 0 && ep_send) ep_send_counts(ep, ep_seq, s_total, E, ep_mode, gridDim.x, ep_ffn_ctas, s_dst);
-    ep_ok = ep_wait_counts(ep, ep_seq, E, ep_mode, s_cnt, s_base);
+    ep_local_bases(ep, E, s_off, s_base);  // (no wait: rows go into this rank's own segment of the owners' buffers)
   }
 
   const int begin = blockIdx.x * chunk;
@@ -329,8 +329,12 @@ dispatch_scatter_kernel(const InT* __restrict__ x, const int* __restrict__ idx, 
       if (offsets_out) offsets_out[e] = s_off[e];
     }
     if (!kEp) build_groups_block(s_off, E, bn, groups, n_groups, h_ready, gmax, s_scratch);
-    // this rank as an OWNER: group table over the merged rows of its local experts (s_part is free by now)
-    else ep_build_groups_merged(ep, E, s_cnt, ep_ok, bn, groups, n_groups, h_ready, gmax, s_part, s_part + E + 1);
+    // this rank as an OWNER: every rank's counts are needed only now, for the group table over the received rows
+    // (s_part is free by now)
+    else {
+      const bool ok = ep_wait_counts(ep, ep_seq, E, ep_mode, s_cnt);
+      ep_build_groups_segmented(ep, E, s_cnt, ok, bn, groups, n_groups, h_ready, gmax, s_part);
+    }
   }
 
   if (kEp) {
@@ -401,7 +405,7 @@ cudaError_t launch_dispatch(const void* x, const int* idx, const float* score, i
   if (top_k != 1) drop_out = nullptr;  // (expert parallelism: only the folded path passes one)
   if (ep != nullptr && (ep->world * ep->E_local != E || Sk > ep->cap || ep->D != D)) return cudaErrorInvalidValue;
   if (E > kMaxExperts || E < 1 || D % 8 != 0) return cudaErrorInvalidValue;
-  const int gmax = ep ? max_groups(ep->world * ep->cap, ep->E_local, bn) : max_groups(Sk, E, bn);
+  const int gmax = ep ? max_groups(ep->world * ep->cap, ep->world * ep->E_local, bn) : max_groups(Sk, E, bn);
   if (Sk == 0 && ep == nullptr) {
     // nothing to route: still publish zero counts / offsets and an empty group table
     cudaError_t e = cudaMemsetAsync(ws.counts, 0, sizeof(int) * E, stream);

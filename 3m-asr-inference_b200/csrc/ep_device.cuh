@@ -80,13 +80,23 @@ __device__ __forceinline__ void ep_send_counts(const EpPeers& ep, int seq, const
   }
 }
 
-// Step 2.  Called by every thread of a CTA.  Waits for every rank's counts of call `seq`, copies the matrix into s_cnt
-// (world x (E + kEpCntExtra) ints) and derives s_base[e]: the row of the owner's receive buffer where THIS rank's first
-// row for global expert e belongs (owner rows: expert-major, source-major inside an expert).  Returns false when a peer
-// did not deliver or the ranks disagree on the mode: the caller then pushes nothing (the output is poisoned further down).
-__device__ __forceinline__ bool ep_wait_counts(const EpPeers& ep, int seq, int E, int mode, int* s_cnt, int* s_base) {
+// Where this rank's rows go (step 2, sender side; every thread of a CTA calls it): every owner keeps one segment of `cap`
+// rows per SOURCE rank, and a source lays its rows for an owner out in its own expert order -- so the row of the owner's
+// receive buffer where THIS rank's first row for global expert e belongs follows from this rank's own offsets alone.
+// (Round 2 first merged the sources' rows of an expert into contiguous rows; that needs every rank's counts before the
+// first row can leave, i.e. a system-scope round trip in front of the pushes: ~6 us per layer on 2 GPUs.)
+__device__ __forceinline__ void ep_local_bases(const EpPeers& ep, int E, const int* s_off, int* s_base) {
+  for (int e = threadIdx.x; e < E; e += blockDim.x)
+    s_base[e] = ep.rank * ep.cap + s_off[e] - s_off[(e / ep.E_local) * ep.E_local];
+  __syncthreads();
+}
+
+// Owner side of step 2.  Called by every thread of ONE CTA (the one that builds the expert kernel's group table).  Waits for
+// every rank's counts of call `seq` and copies the matrix into s_cnt (world x (E + kEpCntExtra) ints).  Returns false when
+// a peer did not deliver or the ranks disagree on the mode (status word raised; the output is poisoned further down).
+__device__ __forceinline__ bool ep_wait_counts(const EpPeers& ep, int seq, int E, int mode, int* s_cnt) {
   int* ctrl = ep_ctrl(ep);
-  const int W = ep.world, El = ep.E_local, stride = E + kEpCntExtra;
+  const int W = ep.world, stride = E + kEpCntExtra;
   {
     // (written by other GPUs during this kernel's lifetime: system-scope loads that bypass L1)
     const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(ep.base[ep.rank] + ep.lay.cnt_all);
@@ -114,42 +124,67 @@ __device__ __forceinline__ bool ep_wait_counts(const EpPeers& ep, int seq, int E
   if (ok)
     for (int s = 0; s < W; ++s) ok = ok && ((s_cnt[s * stride + E] ^ mode) & kEpModeFold) == 0;
   if (!failed && !ok && threadIdx.x == 0) atomicExch(&ctrl[3], kEpErrModeMismatch);
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const int owner = e / El;
-    int row = 0;
-    for (int e2 = owner * El; e2 < e; ++e2)
-      for (int s = 0; s < W; ++s) row += s_cnt[s * stride + e2];
-    for (int s = 0; s < ep.rank; ++s) row += s_cnt[s * stride + e];
-    s_base[e] = ok ? row : 0;
-  }
   __syncthreads();
   return ok;
 }
 
 // Owner side of step 2, one CTA (every thread calls it, after ep_wait_counts): what this rank's expert kernel and its
-// consumers will wait for in this call (local bookkeeping), and the expert kernel's group table over the merged rows of
-// this rank's E_local experts.  s_off / s_scr: E_local + 1 ints of shared memory each.
-__device__ __forceinline__ void ep_build_groups_merged(const EpPeers& ep, int E, const int* s_cnt, bool ok, int bn,
-                                                       GroupRec* groups, int* n_groups, int* h_ready, int gmax,
-                                                       int* s_off, int* s_scr) {
+// consumers will wait for in this call (local bookkeeping), and the expert kernel's group table over the received rows:
+// one run of token tiles per (local expert, source rank); GroupRec::src = the source rank.  Rows of source s for local
+// expert e start at  s * cap + (rows of s for this rank's experts before e).
+// s_scr: E + 1 ints of shared memory.
+__device__ __forceinline__ void ep_build_groups_segmented(const EpPeers& ep, int E, const int* s_cnt, bool ok, int bn,
+                                                          GroupRec* groups, int* n_groups, int* h_ready, int gmax,
+                                                          int* s_scr) {
   const int W = ep.world, El = ep.E_local, stride = E + kEpCntExtra;
   if (static_cast<int>(threadIdx.x) < W && ok) {
     int* ctrl = ep_ctrl(ep);
     ctrl[kEpCtrlArrive + threadIdx.x] = s_cnt[threadIdx.x * stride + E + 1];
     ctrl[kEpCtrlDone + threadIdx.x] = s_cnt[threadIdx.x * stride + E + 2];
   }
+  auto count = [&](int s, int el) { return ok ? min(s_cnt[s * stride + ep.rank * El + el], ep.cap) : 0; };
+  // Order of the runs: this rank's OWN rows first (they are there when the kernel starts: the expert kernel works on them
+  // while the peers' rows are still crossing NVLink), then the other sources' rows, expert-major.
+  auto run = [&](int i, int& el, int& s) {
+    if (i < El) {
+      el = i;
+      s = ep.rank;
+    } else {
+      const int j = i - El, k = j % (W - 1);
+      el = j / (W - 1);
+      s = k < ep.rank ? k : k + 1;
+    }
+  };
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int e = 0; e < El; ++e) {
-      s_off[e] = acc;
-      if (ok)
-        for (int s = 0; s < W; ++s) acc += s_cnt[s * stride + ep.rank * El + e];
+    for (int i = 0; i < El * W; ++i) {
+      int el, s2;
+      run(i, el, s2);
+      s_scr[i] = acc;
+      acc += (count(s2, el) + bn - 1) / bn;
     }
-    const int cap_rows = W * ep.cap;
-    s_off[El] = acc < cap_rows ? acc : cap_rows;
+    n_groups[0] = acc < gmax ? acc : gmax;
   }
   __syncthreads();
-  build_groups_block(s_off, El, bn, groups, n_groups, h_ready, gmax, s_scr);
+  for (int i = threadIdx.x; i < El * W; i += blockDim.x) {
+    int el, s;
+    run(i, el, s);
+    const int c = count(s, el);
+    int base = s * ep.cap;
+    for (int e2 = 0; e2 < el; ++e2) base += count(s, e2);
+    const int nt = (c + bn - 1) / bn;
+    for (int j = 0; j < nt && s_scr[i] + j < gmax; ++j) {
+      GroupRec r;
+      r.expert = el;
+      r.row0 = base + j * bn;
+      r.nrows = min(bn, c - j * bn);
+      r.src = s;
+      r.orow0 = r.row0;
+      r.pad[0] = r.pad[1] = r.pad[2] = 0;
+      groups[s_scr[i] + j] = r;
+    }
+  }
+  for (int g = threadIdx.x; g < gmax; g += blockDim.x) h_ready[g] = 0;
 }
 
 // Step 3, sending side.  Every CTA of the dispatch / route kernel, after a __syncthreads behind its last row store: the

@@ -486,9 +486,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
         // how much of the time is the B operand's L2 -> SM traffic?), 32 = no wait for h (what does the hand-off cost?)
         const bool skip_b = (tl.phase == 1 && (p.dbg & 8)) || (tl.phase == 2 && (p.dbg & 16));
         const uint32_t st_bytes = skip_b ? a_stage_bytes * kCtas : tx_bytes;
+        // (expert parallelism: rows this rank sent to itself were written by the kernel in front -- no counter to wait for)
         const bool dep_pending =
             (tl.phase == 2 && !(p.dbg & 32) && ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) ||
-            (tl.phase == 1 && !rows_ready);
+            (tl.phase == 1 && !rows_ready && gr.src != p.ep_rank);
         if (tl.phase == 2 && !dep_pending) ptx::fence_proxy_async_all();  // h was written through the generic proxy
         if (dep_pending) {
           // The W2 tiles do not depend on h: fill the ring with them first, then wait until every phase-1 tile of this

@@ -26,9 +26,15 @@ namespace {
 constexpr int kTokTile = 128;   // tokens per tile == UMMA M
 constexpr int kBlkK = 64;
 constexpr int kNCols = 64;      // UMMA N: 32 hi + 32 lo expert columns
-constexpr int kStagesG = 8;
-constexpr int kAStage = kTokTile * kBlkK * 2;  // 16 KiB
-constexpr int kBStage = kNCols * kBlkK * 2;    // 8 KiB
+// A pipeline stage holds kKpsG k-blocks of both operands, each brought by ONE TMA instruction through a
+// [K/64][rows][64] view: one producer thread issues ~3.7 bulk copies per us, so with one 16 KiB + one 8 KiB instruction
+// per k-block the issue rate, not HBM, paced the kernel (4.2 TB/s of activations at 65 536 tokens).
+constexpr int kKpsG = 2;
+constexpr int kStagesG = 4;
+constexpr int kABlk = kTokTile * kBlkK * 2;    // 16 KiB: 128 tokens of one k-block
+constexpr int kBBlk = kNCols * kBlkK * 2;      // 8 KiB: 64 packed router rows of one k-block
+constexpr int kAStage = kKpsG * kABlk;         // 32 KiB
+constexpr int kBStage = kKpsG * kBBlk;         // 16 KiB
 constexpr int kThreadsG = 256;
 constexpr uint32_t kTmemColsG = 128;
 
@@ -45,6 +51,7 @@ struct GateTcParams {
   unsigned long long pf_bytes[2];
   int pdl_trigger;
   int pf_mode;  // 0 off, 1 before the dependency wait (weights are constants), 2 after it
+  int kps;      // k-blocks per pipeline stage (see kKpsG)
 };
 
 constexpr unsigned kPfChunk = 16384;
@@ -111,8 +118,9 @@ gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_tiles = (p.S + kTokTile - 1) / kTokTile;
-  const int kb_e = p.Demb / kBlkK;
-  const int nkb = (p.Demb + p.D) / kBlkK;
+  const int kps = p.kps;                        // k-blocks per stage: kKpsG, or 1 when Demb / 64 or D / 64 is odd
+  const int kb_e = p.Demb / (kBlkK * kps);      // stages of the embed part
+  const int nkb = (p.Demb + p.D) / (kBlkK * kps);
 
   if (warp == 3 && p.pf_mode == 2) {
     ptx::pdl_wait();
@@ -126,14 +134,14 @@ gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar(stage), kAStage + kBStage);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(kps) * (kABlk + kBBlk));
           if (kb < kb_e)
-            ptx::tma_load_2d(smem_a + stage * kAStage, &tm_e, full_bar(stage), kb * kBlkK, t * kTokTile,
+            ptx::tma_load_3d(smem_a + stage * kAStage, &tm_e, full_bar(stage), 0, t * kTokTile, kb * kps,
                              ptx::kEvictFirst);
           else
-            ptx::tma_load_2d(smem_a + stage * kAStage, &tm_x, full_bar(stage), (kb - kb_e) * kBlkK, t * kTokTile,
+            ptx::tma_load_3d(smem_a + stage * kAStage, &tm_x, full_bar(stage), 0, t * kTokTile, (kb - kb_e) * kps,
                              ptx::kEvictNormal);  // x is read again by the dispatch kernel
-          ptx::tma_load_2d(smem_b + stage * kBStage, &tm_w, full_bar(stage), kb * kBlkK, 0, ptx::kEvictLast);
+          ptx::tma_load_3d(smem_b + stage * kBStage, &tm_w, full_bar(stage), 0, 0, kb * kps, ptx::kEvictLast);
           if (++stage == kStagesG) {
             stage = 0;
             phase ^= 1u;
@@ -156,11 +164,13 @@ gate_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a + stage * kAStage);
-          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b + stage * kBStage);
+          for (int j = 0; j < kps; ++j) {
+            const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a + stage * kAStage + j * kABlk);
+            const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b + stage * kBStage + j * kBBlk);
 #pragma unroll
-          for (int k = 0; k < kBlkK / 16; ++k)
-            ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlkK / 16; ++k)
+              ptx::umma_f16_ss(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | j | k) != 0 ? 1u : 0u);
+          }
           ptx::umma_commit(empty_bar(stage));
           if (kb == nkb - 1) ptx::umma_commit(tfull_bar(as));
           if (++stage == kStagesG) {
@@ -364,14 +374,17 @@ cudaError_t launch_gate_tc(const void* x, const void* embed, const void* wr_pack
   if (embed == nullptr) Demb = 0;
   if (!gate_tc_supported(D, Demb, E, top_k, B200MOE_BF16)) return cudaErrorInvalidValue;
   CUtensorMap tx, te, tw;
-  if (!make_tmap_bf16(&tx, x, S, D, kTokTile, kBlkK)) return cudaErrorInvalidValue;
+  const int kps = ((D / kBlkK) % kKpsG == 0 && (Demb / kBlkK) % kKpsG == 0) ? kKpsG : 1;
+  if (!make_tmap_bf16_kblocks(&tx, x, S, D, kTokTile, kps)) return cudaErrorInvalidValue;
   if (Demb > 0) {
-    if (!make_tmap_bf16(&te, embed, S, Demb, kTokTile, kBlkK)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_kblocks(&te, embed, S, Demb, kTokTile, kps)) return cudaErrorInvalidValue;
   } else {
     te = tx;
   }
-  if (!make_tmap_bf16(&tw, wr_packed, 64, static_cast<uint64_t>(D + Demb), kNCols, kBlkK)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_kblocks(&tw, wr_packed, 64, static_cast<uint64_t>(D + Demb), kNCols, kps))
+    return cudaErrorInvalidValue;
   GateTcParams p;
+  p.kps = kps;
   p.br = br;
   p.x_len = x_len;
   p.idx = idx;

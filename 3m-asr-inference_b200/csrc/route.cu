@@ -620,7 +620,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   __syncthreads();
   if (threadIdx.x == 0) rtrace(p, 6);
   // Expert parallelism, steps 1 and 2 of the protocol (common.cuh): CTA 0 tells every rank how many rows this rank has for
-  // each expert, every CTA waits for all ranks' counts and learns where its rows belong in the owners' receive buffers.
+  // each expert; where this rank's rows belong in the owners' receive buffers follows from its own offsets.
   // s_part is free again: [0, W * (E + 1)) count matrix, then s_base[E], then scratch for the group table.
   int* s_cnt = s_part;
   int* s_base = s_part + kMaxEpWorld * (32 + kEpCntExtra);
@@ -629,7 +629,7 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   if (kEp) {
     ep_seq = ep_ctrl(ep)[0] + 1;   // (only this kernel's last CTA advances the word, after every CTA has read it)
     if (blockIdx.x == 0) ep_send_counts(ep, ep_seq, s_total, E, p.ep_mode, gridDim.x, p.ep_ffn_ctas, s_dst);
-    ep_ok = ep_wait_counts(ep, ep_seq, E, p.ep_mode, s_cnt, s_base);
+    ep_local_bases(ep, E, s_off, s_base);  // (no wait: rows go into this rank's own segment of the owners' buffers)
   }
   if (threadIdx.x == 0) rtrace(p, 7);
 
@@ -832,9 +832,10 @@ route_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       }
       for (int g = threadIdx.x; g < p.gmax; g += blockDim.x) p.h_ready[g] = 0;
     } else {
-      // this rank as an OWNER: the expert kernel's group table over the merged rows of its local experts
-      ep_build_groups_merged(ep, E, s_cnt, ep_ok, p.bn, p.groups, p.n_groups, p.h_ready, p.gmax,
-                             s_base + 40, s_base + 40 + kMaxExperts / 4 + 8);
+      // this rank as an OWNER: every rank's counts are needed only now (they left the peers before their rows did), for
+      // the expert kernel's group table over the received rows
+      const bool ok = ep_wait_counts(ep, ep_seq, E, p.ep_mode, s_cnt);
+      ep_build_groups_segmented(ep, E, s_cnt, ok, p.bn, p.groups, p.n_groups, p.h_ready, p.gmax, s_base + 40);
     }
   }
 
@@ -953,7 +954,7 @@ cudaError_t launch_route(const void* x, const void* embed, const void* wr_packed
   p.n_groups = ws.n_groups;
   p.h_ready = ws.h_ready;
   p.bn = bn;
-  p.gmax = ep ? max_groups(ep->world * ep->cap, ep->E_local, bn) : max_groups(S, E, bn);
+  p.gmax = ep ? max_groups(ep->world * ep->cap, ep->world * ep->E_local, bn) : max_groups(S, E, bn);
   p.counts_out = counts_out;
   p.offsets_out = offsets_out;
   p.mapping_out = mapping_out;
