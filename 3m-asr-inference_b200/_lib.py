@@ -120,7 +120,7 @@ def load() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         if os.environ.get("B200MOE_AB_OLD_LIB") and not hasattr(lib, name):
-            continue             # (tools/gpu_ab_lib.sh only: an older build of the library without the newest symbols)
+            continue             # (tools/gpu_ab_libs.sh only: an older build of the library without the newest symbols)
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync
         fn.restype = res
         fn.argtypes = args
