@@ -19,7 +19,8 @@
 //    its phase-1 tiles and wait on a per-group counter in global memory, so h only ever travels through L2.
 //  * warp roles (384 threads): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier ring of stages
 //    holding two k-blocks each), warp 1 = single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, double
-//    buffered: 2 x 256 columns), warp 2 = TMEM allocator, warp 3 = publisher of the h flags, warps 4-11 = epilogue
+//    buffered: 2 x 256 columns), warp 2 = TMEM allocator and second TMA producer (token rows; warp 0 then requests
+//    the weights only), warp 3 = publisher of the h flags, warps 4-11 = epilogue
 //    (two sets of four warps; tcgen05.ld -> bias/activation -> smem transpose -> row-wise vector stores).
 //  * 256-token tiles run on CTA pairs (cta_group::2, kCtas = 2): see ffn_kernel.
 //  * expert parallelism: the second GEMM's epilogue stores its rows straight into the source GPU's return buffer and
@@ -71,6 +72,7 @@ struct FfnParams {
   int p1_only;  // first GEMM only (a single grouped linear): the tile list has no second-GEMM tiles
   int pdl_trigger;  // release the dependent kernel at the start (1) or at exit (0)
   int warm_mma;     // issue one throw-away MMA before the first tile (B200MOE_WARM, default 1)
+  int two_prod;     // 1: weights and token rows are requested by two threads in two warps (see the producers)
   // expert parallelism: results go to the source rank's return buffer over peer-mapped memory (NVLink)
   int ep;                           // 0 = off
   int ep_world, ep_rank;
@@ -368,7 +370,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      ptx::mbar_init(full_bar(s), kCtas);  // pair: the leader's barrier takes one arrival from each CTA's producer
+      // pair: the leader's barrier takes one arrival from each CTA's producer (two producers: one from each of them)
+      ptx::mbar_init(full_bar(s), kCtas * (p.two_prod ? 2 : 1));
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -448,24 +451,76 @@ ffn_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CU
   const int kb1 = p.D / (kKel * kps);  // pipeline stages per tile of the first GEMM
   const int kb2 = p.H / (kKel * kps);
 
-  if (warp == 0) {
+  // arm a stage: the leader expects the bytes of both CTAs, the other CTA only announces that its loads are issued
+  auto arm = [&](int st, uint32_t bytes) {
+    if (kCtas == 1 || leader) ptx::mbar_arrive_expect_tx(full_bar(st), bytes);
+    else ptx::mbar_arrive_cluster(full_bar(st) & ptx::kPeerBitMask);
+  };
+  // rows [row, ..) x k-blocks [kb * kps, (kb + 1) * kps) of a [K/64][rows][64] view
+  auto load = [&](uint32_t dst, const CUtensorMap* tm, int st, int kb, int row, uint64_t pol) {
+    if constexpr (kCtas == 2)
+      ptx::tma_load_3d_pair(dst, tm, full_bar(st) & ptx::kPeerBitMask, 0, row, kb * kps, pol);
+    else
+      ptx::tma_load_3d(dst, tm, full_bar(st), 0, row, kb * kps, pol);
+  };
+
+  if (p.two_prod && (warp == 0 || warp == 2)) {
+    // ============================ two TMA producers ============================
+    // Warp 0 requests the weight tiles, warp 2 the token rows (x for the first GEMM, h for the second); a stage's full
+    // barrier takes one arrival and the bytes of each.  The weight stream depends on nothing but the routing table, so it
+    // never stops: only the token producer waits for h (or, under expert parallelism, for the peers' rows), and the ring
+    // fills with the tile's weights meanwhile.  Two issuing threads also get a stage's requests out of the SM sooner: one
+    // thread manages ~2.5 bulk copies per us whatever their size, two threads ~4.7 (tools/tma_issue_bench.cu,
+    // profiles/r02_tma_issue_bench.txt).  Measured against the single producer on one box: -0.2 us per layer at 3 200
+    // tokens, -0.5 us at 50, -1.5 us at 65 536.
+    if (lane == 0) {
+      const bool weights = warp == 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      bool rows_ready = !p.ep;
+      for (int t = tile0; t < n_tiles; t += tile_step) {
+        const Tile tl = decode_tile(t, ng, lag, m1, m2);
+        const GroupRec gr = (t == tile0 && tl.g == g_first) ? gr_first : p.groups[tl.g];
+        const int nkb = tl.phase == 1 ? kb1 : kb2;
+        const CUtensorMap* tm;
+        int row;
+        if (weights) {
+          tm = tl.phase == 1 ? &tm_w1 : &tm_w2;
+          row = gr.expert * (tl.phase == 1 ? p.H : p.D) + (tl.mb * kCtas + static_cast<int>(cta_rank)) * kBlockM;
+        } else {
+          tm = tl.phase == 1 ? &tm_x : &tm_h;
+          row = gr.row0 + static_cast<int>(cta_rank) * b_rows;
+          if (tl.phase == 2) {
+            if (!(p.dbg & 32))
+              while (ptx::ld_acquire_gpu(p.h_ready + tl.g) < m1_flags) __nanosleep(32);
+            ptx::fence_proxy_async_all();  // h was written through the generic proxy, TMA reads it through the async one
+          } else if (!rows_ready && gr.src != p.ep_rank) {
+            ep_wait_counters_1t(p.ep_peers, p.ep_peers.lay.arrive, kEpCtrlArrive, kEpErrDispatchTimeout);
+            rows_ready = true;
+            ptx::fence_proxy_async_all();
+          }
+        }
+        const uint32_t dst0 = weights ? smem_a : smem_b;
+        const uint32_t sbytes = weights ? a_stage_bytes : b_stage_bytes;
+        const uint64_t pol = weights ? p.w_policy : ptx::kEvictLast;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          arm(stage, sbytes * kCtas);
+          load(dst0 + stage * sbytes, tm, stage, kb, row, pol);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      if (weights) mark(3);
+    }
+  } else if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (a_stage_bytes + b_stage_bytes) * kCtas;  // both CTAs' tiles land on the leader's barrier
-      // arm a stage: the leader expects the bytes of both CTAs, the other CTA only announces that its loads are issued
-      auto arm = [&](int st, uint32_t bytes) {
-        if (kCtas == 1 || leader) ptx::mbar_arrive_expect_tx(full_bar(st), bytes);
-        else ptx::mbar_arrive_cluster(full_bar(st) & ptx::kPeerBitMask);
-      };
-      // rows [row, ..) x k-blocks [kb * kps, (kb + 1) * kps) of a [K/64][rows][64] view
-      auto load = [&](uint32_t dst, const CUtensorMap* tm, int st, int kb, int row, uint64_t pol) {
-        if constexpr (kCtas == 2)
-          ptx::tma_load_3d_pair(dst, tm, full_bar(st) & ptx::kPeerBitMask, 0, row, kb * kps, pol);
-        else
-          ptx::tma_load_3d(dst, tm, full_bar(st), 0, row, kb * kps, pol);
-      };
       Tracer<kTrace> tr(p, 0);
       tr.sync();
       tr.rec(-1, kEvKernelStart);
@@ -1192,6 +1247,11 @@ cudaError_t launch_ffn(const FfnLaunch& a, cudaStream_t stream) {
       return (v && *v) ? std::atoi(v) : 1;
     }();
     p.warm_mma = warm;
+    static const int two = [] {
+      const char* v = std::getenv("B200MOE_2PROD");
+      return (v && *v) ? std::atoi(v) : 1;   // (0 = the single-producer code below, kept for A/B runs and the traces)
+    }();
+    p.two_prod = (two && g_trace_buf == nullptr) ? 1 : 0;  // (the per-event trace instruments the single producer)
   }
   // about one token tile per expert: every weight tile is read exactly once, so it can leave L2 right after
   p.w_policy = (static_cast<long long>(a.n_rows) <= static_cast<long long>(a.E) * a.bn) ? ptx::kEvictFirst
