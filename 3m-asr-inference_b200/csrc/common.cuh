@@ -315,6 +315,7 @@ void count_launch(int n = 1);
 //                       the gate waits for the previous kernel; 2 = issued after that wait
 //   B200MOE_2PROD=0     expert kernel with ONE TMA producer thread for both operands (default 1: weights from warp 0, token
 //                       rows from warp 2; ffn.cu); B200MOE_KPS=1: one k-block per TMA instruction instead of two
+//   B200MOE_ROUTE_TCTA=0  no extra table-writing CTA in the fused gate + dispatch kernel (default 1; route.cu: launch_route)
 int pdl_mask();      // bit 0 gate, bit 1 dispatch, bit 2 expert FFN, bit 3 LayerNorm: kernel launched with the PDL attribute
 int pdl_trigger();   // same bits: kernel executes griddepcontrol.launch_dependents at its start
 int prefetch_mode();
